@@ -1,0 +1,268 @@
+"""ctypes binding of the C ABI declared in include/elmk_b200.h.
+
+`Library` wraps one shared object that exports the elmk_* symbols; `Columns` is one handle
+(one device, one contiguous range of land columns).  The product library is
+elmkernels_b200/libelmk_b200.so (hand-written CUDA for sm_100a); the test suite also points
+this same binding at the oracle libraries under oracle/ - the ABI is identical on purpose so that
+parity tests push the same bytes through both.
+
+Host arrays use the reference's layout (column outer, level inner: numpy shape (ncols,) or
+(ncols, nlev), C-contiguous), see reference src/utils/array.hh:176-183.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, Mapping, Optional, Sequence
+
+import numpy as np
+
+F64, I32, U8 = 0, 1, 2
+COL_OUTER, COL_INNER = 0, 1
+_NP = {F64: np.float64, I32: np.int32, U8: np.uint8}
+
+# kernel groups, include/elmk_b200.h
+G_FRAC_WET = 1 << 0
+G_ALBEDO = 1 << 1
+G_CANOPY_HYDROLOGY = 1 << 2
+G_SURFACE_RADIATION = 1 << 3
+G_CANOPY_TEMPERATURE = 1 << 4
+G_BAREGROUND_FLUXES = 1 << 5
+G_CANOPY_FLUXES = 1 << 6
+G_SOIL_TEMPERATURE = 1 << 7
+G_SNOW_HYDROLOGY = 1 << 8
+G_SURFACE_FLUXES = 1 << 9
+G_CONSERVATION = 1 << 10
+G_ALL = 0x7FF
+GROUP_NAMES = ["frac_wet", "albedo_snicar", "canopy_hydrology", "surface_radiation", "canopy_temperature",
+               "bareground_fluxes", "canopy_fluxes", "soil_temperature", "snow_hydrology", "surface_fluxes",
+               "conservation"]
+
+NPFT_TABLES = 40
+PFT_ORDER = ("fnr act25 kcha koha cpha vcmaxha jmaxha tpuha lmrha vcmaxhd jmaxhd tpuhd lmrhd lmrse qe theta_cj "
+             "bbbopt mbbopt c3psn slatop leafcn flnr fnitr dleaf smpso smpsc tc_stress z0mr displar xl roota_par "
+             "rootb_par rholvis rholnir rhosvis rhosnir taulvis taulnir tausvis tausnir").split()
+# the 27 members of the reference's PFTDataPSN, in declaration order (src/data/pft_data.h:20-24)
+PSN_ORDER = PFT_ORDER[:27]
+SNICAR_BAND = [f"{k}_{s}" for s in ("oc1", "oc2", "dst1", "dst2", "dst3", "dst4")
+               for k in ("ss_alb", "asm_prm", "ext_cff_mss")]
+SNICAR_SNOW = [f"{k}_snw_{d}" for d in ("drc", "dfs") for k in ("ss_alb", "asm_prm", "ext_cff_mss")]
+SNICAR_BC = [f"{k}_{s}" for s in ("bc1", "bc2") for k in ("ss_alb", "asm_prm", "ext_cff_mss")]
+
+_PD = C.POINTER(C.c_double)
+
+
+class Tables(C.Structure):
+    """struct elmk_tables"""
+    _fields_ = [("ltype", C.c_int32), ("ctype", C.c_int32), ("vtype", C.c_int32), ("urbpoi", C.c_int32),
+                ("lakpoi", C.c_int32), ("oldfflag", C.c_int32), ("dewmx", C.c_double),
+                ("pft", _PD * NPFT_TABLES), ("albsat", _PD), ("albdry", _PD), ("snicar_band", _PD * 18),
+                ("snicar_snow", _PD * 6), ("snicar_bc", _PD * 6), ("bcenh", _PD), ("snowage", _PD * 3)]
+
+
+class ElmkError(RuntimeError):
+    pass
+
+
+class Library:
+    """One shared object exporting the elmk_* C ABI."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise ElmkError(f"shared library not found: {path}")
+        self.path = path
+        self.dll = C.CDLL(path, mode=getattr(os, "RTLD_LOCAL", 0) | getattr(os, "RTLD_NOW", 2))
+        d = self.dll
+        H = C.c_void_p
+        sig = {
+            "elmk_abi_version": (C.c_int, []),
+            "elmk_backend": (C.c_char_p, []),
+            "elmk_field_count": (C.c_int, []),
+            "elmk_field_id": (C.c_int, [C.c_char_p]),
+            "elmk_field_info": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+            "elmk_create": (C.c_int, [C.POINTER(H), C.c_int, C.c_int64]),
+            "elmk_destroy": (C.c_int, [H]),
+            "elmk_last_error": (C.c_char_p, [H]),
+            "elmk_ncols": (C.c_int64, [H]),
+            "elmk_set_tables": (C.c_int, [H, C.POINTER(Tables)]),
+            "elmk_upload": (C.c_int, [H, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int]),
+            "elmk_download": (C.c_int, [H, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int]),
+            "elmk_fill": (C.c_int, [H, C.c_int, C.c_double]),
+            "elmk_upload_many": (C.c_int, [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_int64,
+                                           C.c_int64, C.c_int]),
+            "elmk_download_many": (C.c_int, [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_int64,
+                                             C.c_int64, C.c_int]),
+            "elmk_init_timestep": (C.c_int, [H, C.c_int]),
+            "elmk_step": (C.c_int, [H, C.c_double, C.c_double, C.c_double, C.c_uint32]),
+            "elmk_sync": (C.c_int, [H]),
+            "elmk_launch_count": (C.c_int64, [H]),
+            "elmk_errors": (C.c_int, [H, C.POINTER(C.c_uint32), C.POINTER(C.c_int64)]),
+            "elmk_clear_errors": (C.c_int, [H]),
+            "elmk_error_text": (C.c_char_p, [C.c_uint32]),
+            "elmk_diag_reduce": (C.c_int, [H, _PD]),
+            "elmk_device_ptr": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+        }
+        self.symbols = list(sig)
+        for name, (res, args) in sig.items():
+            fn = getattr(d, name)  # AttributeError here = the library does not export the declared ABI
+            fn.restype, fn.argtypes = res, args
+        self.backend = d.elmk_backend().decode()
+        self.fields: Dict[str, tuple] = {}
+        self.field_names = []
+        nm, dt, nl = C.c_char_p(), C.c_int(), C.c_int()
+        for i in range(d.elmk_field_count()):
+            d.elmk_field_info(i, C.byref(nm), C.byref(dt), C.byref(nl))
+            self.fields[nm.value.decode()] = (i, dt.value, nl.value)
+            self.field_names.append(nm.value.decode())
+
+    def columns(self, ncols: int, device: int = 0) -> "Columns":
+        return Columns(self, ncols, device)
+
+
+class Columns:
+    """One handle: `ncols` land columns resident on one device."""
+
+    def __init__(self, lib: Library, ncols: int, device: int = 0):
+        self.lib, self.ncols = lib, int(ncols)
+        self._h = C.c_void_p()
+        self._keep = None
+        rc = lib.dll.elmk_create(C.byref(self._h), int(device), self.ncols)
+        if rc != 0:
+            raise ElmkError(f"elmk_create({ncols}) failed with {rc} on {lib.backend}")
+
+    # -- plumbing --
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.dll.elmk_last_error(self._h)
+            raise ElmkError(f"{what} failed with {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._h:
+            self.lib.dll.elmk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- tables --
+    def set_tables(self, params: Mapping[str, np.ndarray], land: Optional[Mapping[str, int]] = None,
+                   dewmx: float = 0.1, oldfflag: int = 1):
+        """params: arrays keyed pft_<name>, snicar_<name>, albsat, albdry, snowage_{tau,kappa,drdt0}."""
+        land = dict(ltype=1, ctype=1, vtype=12, urbpoi=0, lakpoi=0, **(land or {}))
+        t = Tables()
+        keep = []
+
+        def ptr(a, size):
+            a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+            if a.size < size:
+                raise ElmkError(f"table too small: {a.size} < {size}")
+            keep.append(a)
+            return a.ctypes.data_as(_PD)
+
+        for k in ("ltype", "ctype", "vtype", "urbpoi", "lakpoi"):
+            setattr(t, k, int(land[k]))
+        t.oldfflag, t.dewmx = int(oldfflag), float(dewmx)
+        for i, n in enumerate(PFT_ORDER):
+            t.pft[i] = ptr(params["pft_" + n], 1 if n == "tc_stress" else 17)
+        t.albsat, t.albdry = ptr(params["albsat"], 40), ptr(params["albdry"], 40)
+        for i, n in enumerate(SNICAR_BAND):
+            t.snicar_band[i] = ptr(params["snicar_" + n], 5)
+        for i, n in enumerate(SNICAR_SNOW):
+            t.snicar_snow[i] = ptr(params["snicar_" + n], 5 * 1471)
+        for i, n in enumerate(SNICAR_BC):
+            t.snicar_bc[i] = ptr(params["snicar_" + n], 50)
+        t.bcenh = ptr(params["snicar_bcenh"], 400)
+        for i, n in enumerate(("tau", "kappa", "drdt0")):
+            t.snowage[i] = ptr(params["snowage_" + n], 11 * 31 * 8)
+        self._check(self.lib.dll.elmk_set_tables(self._h, C.byref(t)), "elmk_set_tables")
+        self._keep = keep
+
+    # -- state movement --
+    def _spec(self, name: str):
+        try:
+            return self.lib.fields[name]
+        except KeyError:
+            raise ElmkError(f"unknown field {name!r}") from None
+
+    def host_array(self, name: str, n: Optional[int] = None) -> np.ndarray:
+        _, dt, nl = self._spec(name)
+        n = self.ncols if n is None else n
+        return np.zeros((n,) if nl == 1 else (n, nl), dtype=_NP[dt])
+
+    def upload(self, name: str, arr: np.ndarray, col0: int = 0):
+        fid, dt, nl = self._spec(name)
+        a = np.ascontiguousarray(arr, dtype=_NP[dt])
+        n = a.shape[0]
+        if a.size != n * nl:
+            raise ElmkError(f"{name}: expected {nl} elements per column, got shape {a.shape}")
+        self._check(self.lib.dll.elmk_upload(self._h, fid, a.ctypes.data, col0, n, COL_OUTER), f"elmk_upload({name})")
+
+    def download(self, name: str, col0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None):
+        fid, dt, nl = self._spec(name)
+        n = self.ncols - col0 if n is None else n
+        a = self.host_array(name, n) if out is None else out
+        self._check(self.lib.dll.elmk_download(self._h, fid, a.ctypes.data, col0, n, COL_OUTER),
+                    f"elmk_download({name})")
+        return a
+
+    def upload_state(self, state: Mapping[str, np.ndarray], col0: int = 0):
+        for k, v in state.items():
+            self.upload(k, v, col0)
+
+    def download_state(self, names: Optional[Iterable[str]] = None) -> Dict[str, np.ndarray]:
+        return {k: self.download(k) for k in (names or self.lib.field_names)}
+
+    def fill(self, name: str, value: float):
+        self._check(self.lib.dll.elmk_fill(self._h, self._spec(name)[0], float(value)), f"elmk_fill({name})")
+
+    def plan(self, names: Sequence[str], arrays: Sequence[np.ndarray]):
+        """Pre-marshal a (fields, host buffers) pair for upload_many/download_many."""
+        ids = (C.c_int * len(names))(*[self._spec(n)[0] for n in names])
+        ptrs = (C.c_void_p * len(names))(*[a.ctypes.data for a in arrays])
+        return ids, ptrs, len(names), list(arrays)
+
+    def upload_many(self, plan, col0: int = 0, n: Optional[int] = None):
+        ids, ptrs, k, _ = plan
+        self._check(self.lib.dll.elmk_upload_many(self._h, k, ids, ptrs, col0, self.ncols if n is None else n,
+                                                  COL_OUTER), "elmk_upload_many")
+
+    def download_many(self, plan, col0: int = 0, n: Optional[int] = None):
+        ids, ptrs, k, _ = plan
+        self._check(self.lib.dll.elmk_download_many(self._h, k, ids, ptrs, col0, self.ncols if n is None else n,
+                                                    COL_OUTER), "elmk_download_many")
+
+    # -- stepping --
+    def init_timestep(self, reset_forc_hgt: bool = True):
+        self._check(self.lib.dll.elmk_init_timestep(self._h, int(reset_forc_hgt)), "elmk_init_timestep")
+
+    def step(self, dtime: float = 1800.0, dayl: float = 50000.0, max_dayl: float = 86400.0, groups: int = G_ALL):
+        self._check(self.lib.dll.elmk_step(self._h, dtime, dayl, max_dayl, groups), "elmk_step")
+
+    def sync(self):
+        self._check(self.lib.dll.elmk_sync(self._h), "elmk_sync")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.dll.elmk_launch_count(self._h))
+
+    def errors(self):
+        any_, first = C.c_uint32(), C.c_int64()
+        self._check(self.lib.dll.elmk_errors(self._h, C.byref(any_), C.byref(first)), "elmk_errors")
+        return any_.value, first.value
+
+    def clear_errors(self):
+        self._check(self.lib.dll.elmk_clear_errors(self._h), "elmk_clear_errors")
+
+    def diag_reduce(self) -> np.ndarray:
+        out = np.zeros(24)
+        self._check(self.lib.dll.elmk_diag_reduce(self._h, out.ctypes.data_as(_PD)), "elmk_diag_reduce")
+        return out
+
+    def device_ptr(self, name: str):
+        p, s = C.c_void_p(), C.c_int64()
+        self._check(self.lib.dll.elmk_device_ptr(self._h, self._spec(name)[0], C.byref(p), C.byref(s)),
+                    "elmk_device_ptr")
+        return p.value, s.value

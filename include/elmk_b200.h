@@ -1,0 +1,191 @@
+/* elmk_b200.h - C ABI of the B200-native ELM column-timestep library (libelmk_b200.so).
+ *
+ * This is the drop-in boundary below the reference's kernel-group wrappers
+ * (reference driver/kokkos/*_kokkos.{hh,cc}, called from ELMInterface::advance,
+ * driver/kokkos/elm_kokkos_interface.cc:269-322).  Plain pointers and sizes only.
+ *
+ * Every entry point returns 0 on success or a negative ELMK_E* code; the text of the
+ * last failure on a handle is available from elmk_last_error().
+ *
+ * Threading: a handle owns one CUDA stream on one device.  Calls on one handle are not
+ * thread-safe; different handles are independent (reference: single host thread,
+ * SURVEY.md section 8(b)).
+ */
+#ifndef ELMK_B200_H_
+#define ELMK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELMK_ABI_VERSION 1
+
+/* ---- dimensions (reference src/data/elm_constants.h:84-98) ---- */
+#define ELMK_NLEVSNO 5
+#define ELMK_NLEVGRND 15
+#define ELMK_NLEVTOT 20
+#define ELMK_NUMRAD 2
+#define ELMK_NUMPFT 17
+#define ELMK_NUMRAD_SNW 5
+#define ELMK_SNO_NBR_AER 8
+#define ELMK_MIE_SNW 1471
+#define ELMK_BC_NCLRDS 10
+#define ELMK_BCINT_ICERDS 8
+#define ELMK_SNOWAGE_T 11
+#define ELMK_SNOWAGE_TGRD 31
+#define ELMK_SNOWAGE_RHOS 8
+#define ELMK_NSOILCOL 20
+#define ELMK_NPFT_TABLES 40
+
+/* ---- error codes ---- */
+#define ELMK_OK 0
+#define ELMK_EINVAL (-1)   /* bad argument                                           */
+#define ELMK_ECUDA (-2)    /* CUDA runtime failure (text in elmk_last_error)          */
+#define ELMK_ENOTABLES (-3)/* elmk_step before elmk_set_tables                        */
+#define ELMK_EUNSUPPORTED (-4) /* land-unit configuration outside the hot path's scope */
+#define ELMK_ECOLUMN (-5)  /* a column raised one of the reference's throw/assert sites */
+
+/* ---- element types of per-column fields ---- */
+#define ELMK_F64 0
+#define ELMK_I32 1
+#define ELMK_U8 2
+
+/* ---- host memory layouts for upload/download ---- */
+#define ELMK_COL_OUTER 0 /* host[(col)*nlev + lev]  : the reference's layout (array.hh:176-183) */
+#define ELMK_COL_INNER 1 /* host[(lev)*n + col]     : the device layout                         */
+
+/* ---- kernel groups = the reference's wrapper calls, in chain order
+ *      (elm_kokkos_interface.cc:289-318); a step runs the selected groups in this order ---- */
+#define ELMK_G_FRAC_WET (1u << 0)           /* kokkos_frac_wet            canopy_hydrology_kokkos.cc:98  */
+#define ELMK_G_ALBEDO (1u << 1)             /* kokkos_albedo_snicar       albedo_kokkos.cc:10            */
+#define ELMK_G_CANOPY_HYDROLOGY (1u << 2)   /* kokkos_canopy_hydrology    canopy_hydrology_kokkos.cc:7   */
+#define ELMK_G_SURFACE_RADIATION (1u << 3)  /* kokkos_surface_radiation   surface_radiation_kokkos.cc:7  */
+#define ELMK_G_CANOPY_TEMPERATURE (1u << 4) /* kokkos_canopy_temperature  canopy_temperature_kokkos.cc:6 */
+#define ELMK_G_BAREGROUND_FLUXES (1u << 5)  /* kokkos_bareground_fluxes   bareground_fluxes_kokkos.cc:7  */
+#define ELMK_G_CANOPY_FLUXES (1u << 6)      /* kokkos_canopy_fluxes       canopy_fluxes_kokkos.cc:6      */
+#define ELMK_G_SOIL_TEMPERATURE (1u << 7)   /* kokkos_soil_temperature    soil_temperature_kokkos.cc:6   */
+#define ELMK_G_SNOW_HYDROLOGY (1u << 8)     /* kokkos_snow_hydrology      snow_hydrology_kokkos.cc:23    */
+#define ELMK_G_SURFACE_FLUXES (1u << 9)     /* kokkos_surface_fluxes      surface_fluxes_kokkos.cc:6     */
+#define ELMK_G_CONSERVATION (1u << 10)      /* kokkos_evaluate_conservation conserved_quantity_kokkos.cc:8 */
+#define ELMK_G_ALL 0x7FFu
+#define ELMK_NGROUPS 11
+
+/* ---- per-column error bits (one per reference throw/assert site) ---- */
+#define ELMK_ERR_CANOPY_LAYER (1u << 0)     /* surface_albedo_impl.hh:270               */
+#define ELMK_ERR_SNICAR_RADIUS (1u << 1)    /* snow_snicar_impl.hh:76                   */
+#define ELMK_ERR_SNICAR_NEGABS (1u << 2)    /* snow_snicar_impl.hh:618                  */
+#define ELMK_ERR_SNICAR_ENERGY (1u << 3)    /* snow_snicar_impl.hh:658                  */
+#define ELMK_ERR_SNICAR_ALBEDO (1u << 4)    /* snow_snicar_impl.hh:664                  */
+#define ELMK_ERR_SABG_LAYERS (1u << 5)      /* surface_radiation_impl.hh:173 (assert)   */
+#define ELMK_ERR_FORC_HEIGHT (1u << 6)      /* canopy_fluxes_impl.hh:178 (assert)       */
+#define ELMK_ERR_QUADRATIC (1u << 7)        /* photosynthesis_impl.hh:289               */
+#define ELMK_ERR_BRENT_BRACKET (1u << 8)    /* photosynthesis_impl.hh:439               */
+#define ELMK_ERR_NEG_STOMATAL (1u << 9)     /* photosynthesis_impl.hh:232               */
+#define ELMK_ERR_SNOWAGE_DR (1u << 10)      /* snow_hydrology_impl.hh:146               */
+#define ELMK_ERR_DIVIDE_RADIUS (1u << 11)   /* snow_hydrology_impl.hh:1022,1100,1176,1253 */
+
+typedef struct elmk_ctx* elmk_handle;
+
+/* Global (not per-column) inputs.  All pointers are host pointers, copied by elmk_set_tables.
+ *
+ * pft[k] follows the member order of the reference's PFTData (src/data/pft_data.h:38-77):
+ *   0 fnr 1 act25 2 kcha 3 koha 4 cpha 5 vcmaxha 6 jmaxha 7 tpuha 8 lmrha 9 vcmaxhd 10 jmaxhd
+ *   11 tpuhd 12 lmrhd 13 lmrse 14 qe 15 theta_cj 16 bbbopt 17 mbbopt 18 c3psn 19 slatop
+ *   20 leafcn 21 flnr 22 fnitr 23 dleaf 24 smpso 25 smpsc 26 tc_stress 27 z0mr 28 displar 29 xl
+ *   30 roota_par 31 rootb_par 32 rholvis 33 rholnir 34 rhosvis 35 rhosnir 36 taulvis 37 taulnir
+ *   38 tausvis 39 tausnir
+ * each ELMK_NUMPFT doubles, except tc_stress which is one double (pft_data_impl.hh:54).
+ *
+ * snicar_band[k] ([ELMK_NUMRAD_SNW] each) in the member order of SnicarData
+ * (src/data/snicar_data.h:40-57): ss_alb/asm_prm/ext_cff_mss for oc1, oc2, dst1..dst4.
+ * snicar_snow[k] ([ELMK_NUMRAD_SNW][ELMK_MIE_SNW] each): ss_alb_snw_drc, asm_prm_snw_drc,
+ * ext_cff_mss_snw_drc, ss_alb_snw_dfs, asm_prm_snw_dfs, ext_cff_mss_snw_dfs (:58-63).
+ * snicar_bc[k] ([ELMK_BC_NCLRDS][ELMK_NUMRAD_SNW] each): ss_alb_bc1, asm_prm_bc1,
+ * ext_cff_mss_bc1, ss_alb_bc2, asm_prm_bc2, ext_cff_mss_bc2 (:64-69).
+ * bcenh [ELMK_BCINT_ICERDS][ELMK_BC_NCLRDS][ELMK_NUMRAD_SNW] (:70).
+ * snowage[k] ([ELMK_SNOWAGE_T][ELMK_SNOWAGE_TGRD][ELMK_SNOWAGE_RHOS] each): tau, kappa, drdt0 (:80-82).
+ * albsat/albdry [ELMK_NSOILCOL][ELMK_NUMRAD] (elm_state_impl.hh:106-107).
+ */
+typedef struct elmk_tables {
+  int32_t ltype, ctype, vtype, urbpoi, lakpoi; /* LandType, src/data/land_data.h:36-44 */
+  int32_t oldfflag;                            /* elm_state.h:224 */
+  double dewmx;                                /* elm_state.h:223 */
+  const double* pft[ELMK_NPFT_TABLES];
+  const double* albsat;
+  const double* albdry;
+  const double* snicar_band[18];
+  const double* snicar_snow[6];
+  const double* snicar_bc[6];
+  const double* bcenh;
+  const double* snowage[3];
+} elmk_tables;
+
+/* ---- introspection of the per-column field table (include/elmk_fields.def) ---- */
+int elmk_abi_version(void);
+const char* elmk_backend(void); /* "cuda-sm100a" for the product library */
+int elmk_field_count(void);
+int elmk_field_id(const char* name);                                   /* -1 if unknown */
+int elmk_field_info(int field, const char** name, int* dtype, int* nlev);
+
+/* ---- lifetime: replaces ELMInterface::ELMInterface(ncols) / ELMState allocation
+ *      (elm_kokkos_interface.cc:38-56, elm_state_impl.hh:369-403) ---- */
+int elmk_create(elmk_handle* out, int device, int64_t ncols);
+int elmk_destroy(elmk_handle h);
+const char* elmk_last_error(elmk_handle h);
+int64_t elmk_ncols(elmk_handle h);
+
+/* ---- tables: replaces the table part of initialize_kokkos_elm
+ *      (initialize_elm_kokkos.cc:267-366) ---- */
+int elmk_set_tables(elmk_handle h, const elmk_tables* t);
+
+/* ---- state movement: replaces Kokkos::deep_copy of ELMState arrays
+ *      (elm_kokkos_interface.cc:145-255, copyPrimaryVars :324-347).
+ *      host holds n columns [col0, col0+n) of one field, element type per elmk_field_info ---- */
+int elmk_upload(elmk_handle h, int field, const void* host, int64_t col0, int64_t n, int layout);
+int elmk_download(elmk_handle h, int field, void* host, int64_t col0, int64_t n, int layout);
+/* set every element of a field (Utils::assign, helper_functions.hh:18-19) */
+int elmk_fill(elmk_handle h, int field, double value);
+
+/* several fields in one call: hosts[i] is the host buffer of fields[i] (same col0, n, layout).
+ * Used for the per-step forcing refresh and the per-step result read-back. */
+int elmk_upload_many(elmk_handle h, int nfields, const int* fields, const void* const* hosts,
+                     int64_t col0, int64_t n, int layout);
+int elmk_download_many(elmk_handle h, int nfields, const int* fields, void* const* hosts,
+                       int64_t col0, int64_t n, int layout);
+
+/* ---- the per-column part of kokkos_init_timestep (init_timestep_kokkos.cc:53-72):
+ *      h2osno_old, dtbegin_column_h2o, ELM::init_timestep; resets forc_hgt_*_patch to
+ *      forc_hgt (atm_physics_impl.hh:197-202) when reset_forc_hgt != 0 ---- */
+int elmk_init_timestep(elmk_handle h, int reset_forc_hgt);
+
+/* ---- one pass of the selected kernel groups over all columns, asynchronous on the
+ *      handle's stream: replaces the 11 wrapper calls of ELMInterface::advance ---- */
+int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_t group_mask);
+int elmk_sync(elmk_handle h);
+
+/* number of kernel launches issued by this handle since creation (for bench accounting) */
+int64_t elmk_launch_count(elmk_handle h);
+
+/* ---- error convention: replaces C++ exceptions thrown inside kernels.  any = OR of all
+ *      columns' errmask words, first_col = lowest column index with a non-zero word (-1 if none).
+ *      Synchronises the stream. ---- */
+int elmk_errors(elmk_handle h, uint32_t* any, int64_t* first_col);
+int elmk_clear_errors(elmk_handle h);
+const char* elmk_error_text(uint32_t bit); /* the reference's message for one error bit */
+
+/* ---- optional global balance diagnostic: sum/min/max over all columns of this handle of the
+ *      8 fields dtend_column_h2o, errh2o, errh2osno, dwb, errsol, errlon, errseb, netrad
+ *      (conserved_quantity_kokkos.cc:13-20), out[0..7]=sum, out[8..15]=min, out[16..23]=max.
+ *      Counterpart of ELMKokkos::min_max_sum (src/utils/kokkos_utils.hh:13-58); the cross-rank
+ *      reduction of the 24 doubles is done by the caller (NCCL all-reduce in the Python host). ---- */
+int elmk_diag_reduce(elmk_handle h, double out[24]);
+
+/* raw device pointer + level stride of a field (for zero-copy interop with torch tensors) */
+int elmk_device_ptr(elmk_handle h, int field, void** ptr, int64_t* level_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELMK_B200_H_ */

@@ -1,0 +1,496 @@
+// TEST INFRASTRUCTURE (oracle) - not part of the product path.
+//
+// libelmref.so: the UNMODIFIED reference (its driver/kokkos/*_kokkos.cc wrappers and
+// src/physics headers, compiled where they lie under /root/reference against the shims in
+// oracle/shim) behind the same C ABI as the product library (include/elmk_b200.h), so that
+// tests can push identical inputs through both and compare, and so that bench.py can time the
+// reference's own OpenMP path as the CPU baseline.  Nothing here computes physics: every
+// group call is one call of the reference's wrapper, in the chain order of
+// ELMInterface::advance (reference driver/kokkos/elm_kokkos_interface.cc:289-318).
+//
+// The only restated bindings are:
+//   * the per-column lambda of kokkos_init_timestep (init_timestep_kokkos.cc:53-72), because
+//     the wrapper itself reads NetCDF forcing files that are not in the container;
+//   * the argument binding of kokkos_evaluate_conservation (conserved_quantity_kokkos.cc:22-68),
+//     because the wrapper keeps its eight results in local Views and only prints column 0.
+// Both call the reference's own physics functions.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "compile_options.hh"
+#include "data_types.hh"
+#include "elm_constants.h"
+#include "helper_functions.hh"
+
+#include "albedo_kokkos.hh"
+#include "bareground_fluxes_kokkos.hh"
+#include "canopy_fluxes_kokkos.hh"
+#include "canopy_hydrology_kokkos.hh"
+#include "canopy_temperature_kokkos.hh"
+#include "conserved_quantity_kokkos.hh"
+#include "snow_hydrology_kokkos.hh"
+#include "soil_temperature_kokkos.hh"
+#include "surface_fluxes_kokkos.hh"
+#include "surface_radiation_kokkos.hh"
+
+#include "conserved_quantity_evaluators.h"
+#include "init_snow_state.h"
+#include "init_soil_state.h"
+#include "init_timestep.h"
+#include "init_topography.h"
+#include "soil_texture_hydraulic_model.h"
+
+#include "../include/elmk_b200.h"
+
+namespace {
+
+struct FieldRef {
+  std::string name;
+  int dtype;
+  int nlev;
+  void* base;    // reference storage, row-major [ncols][nlev]
+  size_t esize;
+};
+
+struct RefCtx {
+  int64_t ncols = 0;
+  std::unique_ptr<ELMStateType> S;
+  std::vector<FieldRef> fields;
+  std::map<std::string, int> index;
+  // the eight wrapper-local diagnostics + error word, owned here
+  ViewD1 dtend_column_h2o, errh2o, errh2osno, dwb, errsol, errlon, errseb, netrad;
+  ViewI1 errmask;
+  bool tables_set = false;
+  int64_t launches = 0;
+  std::string last_error;
+};
+
+uint32_t bit_for_message(const std::string& what) {
+  if (what.find("multi-layer canopy") != std::string::npos) return ELMK_ERR_CANOPY_LAYER;
+  if (what.find("grain radius out of bounds") != std::string::npos) return ELMK_ERR_SNICAR_RADIUS;
+  if (what.find("negative absoption") != std::string::npos) return ELMK_ERR_SNICAR_NEGABS;
+  if (what.find("Energy conservation") != std::string::npos) return ELMK_ERR_SNICAR_ENERGY;
+  if (what.find("Albedo > 1.0") != std::string::npos) return ELMK_ERR_SNICAR_ALBEDO;
+  if (what.find("quadratic solution") != std::string::npos) return ELMK_ERR_QUADRATIC;
+  if (what.find("bracketed for brent") != std::string::npos) return ELMK_ERR_BRENT_BRACKET;
+  if (what.find("Negative stomatal") != std::string::npos) return ELMK_ERR_NEG_STOMATAL;
+  if (what.find("SnowAge dr_fresh") != std::string::npos) return ELMK_ERR_SNOWAGE_DR;
+  if (what.find("snow::divide_layers") != std::string::npos) return ELMK_ERR_DIVIDE_RADIUS;
+  return 1u << 31;
+}
+
+template <class V> void add_field(RefCtx& c, const char* name, int dtype, int nlev, V& view) {
+  FieldRef f{name, dtype, nlev, static_cast<void*>(view.data()), sizeof(typename V::value_type)};
+  if (std::string(name) == "psn_pft") f.esize = sizeof(double);
+  c.index[name] = static_cast<int>(c.fields.size());
+  c.fields.push_back(f);
+}
+
+// field table in the order of include/elmk_fields.def
+struct Spec { const char* name; int dtype; int nlev; };
+const Spec kSpecs[] = {
+#define F64 ELMK_F64
+#define I32 ELMK_I32
+#define U8 ELMK_U8
+#define ELMK_FIELD(name, type, nlev, cls) {#name, type, nlev},
+#include "../include/elmk_fields.def"
+#undef ELMK_FIELD
+#undef F64
+#undef I32
+#undef U8
+};
+constexpr int kNumFields = sizeof(kSpecs) / sizeof(kSpecs[0]);
+constexpr int kNumStateFields = 191;
+
+void build_registry(RefCtx& c) {
+  ELMStateType& S = *c.S;
+  int i = 0;
+  // the 191 ELMStateViews members, bound by name
+#define BIND(MEMBER) add_field(c, kSpecs[i].name, kSpecs[i].dtype, kSpecs[i].nlev, S.MEMBER); ++i;
+  // (bound explicitly: the 191 ELMStateViews members first, then the aerosol containers and diagnostics)
+  BIND(forc_tbot) BIND(forc_thbot) BIND(forc_pbot) BIND(forc_qbot) BIND(forc_lwrad) BIND(forc_u) BIND(forc_v)
+  BIND(forc_hgt) BIND(forc_hgt_u_patch) BIND(forc_hgt_t_patch) BIND(forc_hgt_q_patch) BIND(forc_rain) BIND(forc_snow)
+  BIND(forc_solai) BIND(forc_solad) BIND(tlai) BIND(tsai) BIND(elai) BIND(esai) BIND(htop) BIND(hbot)
+  BIND(frac_veg_nosno_alb) BIND(frac_veg_nosno) BIND(watsat) BIND(sucsat) BIND(bsw) BIND(watdry) BIND(watopt) BIND(watfc)
+  BIND(n_melt) BIND(micro_sigma) BIND(topo_slope) BIND(topo_std) BIND(isoicol) BIND(tkmg) BIND(tkdry) BIND(csol)
+  BIND(snl) BIND(snow_depth) BIND(frac_sno) BIND(int_snow) BIND(snw_rds) BIND(swe_old) BIND(frac_iceold)
+  BIND(h2osoi_liq) BIND(h2osoi_ice) BIND(h2osoi_vol) BIND(h2ocan) BIND(h2osno) BIND(h2osno_old) BIND(fwet) BIND(fdry)
+  BIND(h2osfc) BIND(frac_h2osfc) BIND(frac_sno_eff) BIND(qflx_snwcp_liq) BIND(qflx_snwcp_ice) BIND(qflx_snow_grnd)
+  BIND(qflx_rain_grnd) BIND(qflx_snow_melt) BIND(t_soisno) BIND(t_grnd) BIND(nrad) BIND(laisun) BIND(laisha)
+  BIND(parsun_z) BIND(parsha_z) BIND(laisun_z) BIND(laisha_z) BIND(sabg_soil) BIND(sabg_snow) BIND(sabg) BIND(sabv)
+  BIND(fsa) BIND(fsr) BIND(sabg_lyr) BIND(tlai_z) BIND(fsun_z) BIND(fabd_sun_z) BIND(fabd_sha_z) BIND(fabi_sun_z)
+  BIND(fabi_sha_z) BIND(ftdd) BIND(ftid) BIND(ftii) BIND(fabd) BIND(fabi) BIND(albsod) BIND(albsoi) BIND(albgrd)
+  BIND(albgri) BIND(flx_absdv) BIND(flx_absdn) BIND(flx_absiv) BIND(flx_absin) BIND(albd) BIND(albi) BIND(t_h2osfc)
+  BIND(t_h2osfc_bef) BIND(soilbeta) BIND(qg_snow) BIND(qg_soil) BIND(qg) BIND(qg_h2osfc) BIND(dqgdT) BIND(htvp)
+  BIND(emg) BIND(emv) BIND(z0mg) BIND(z0hg) BIND(z0qg) BIND(z0mv) BIND(z0hv) BIND(z0qv) BIND(thv) BIND(z0m)
+  BIND(displa) BIND(thm) BIND(eflx_sh_tot) BIND(eflx_lh_tot) BIND(eflx_sh_veg) BIND(qflx_evap_tot) BIND(qflx_evap_veg)
+  BIND(qflx_tran_veg) BIND(tssbef) BIND(dlrad) BIND(ulrad) BIND(eflx_sh_grnd) BIND(eflx_sh_snow) BIND(eflx_sh_soil)
+  BIND(eflx_sh_h2osfc) BIND(qflx_evap_soi) BIND(qflx_ev_snow) BIND(qflx_ev_soil) BIND(qflx_ev_h2osfc) BIND(t_ref2m)
+  BIND(q_ref2m) BIND(rh_ref2m) BIND(cgrnds) BIND(cgrndl) BIND(cgrnd) BIND(altmax_indx) BIND(altmax_lastyear_indx)
+  BIND(t10) BIND(vcmaxcintsha) BIND(vcmaxcintsun) BIND(btran) BIND(t_veg) BIND(rootfr) BIND(rootr) BIND(eff_porosity)
+  BIND(eflx_soil_grnd) BIND(qflx_evap_grnd) BIND(qflx_sub_snow) BIND(qflx_dew_snow) BIND(qflx_dew_grnd)
+  BIND(eflx_lwrad_out) BIND(eflx_lwrad_net) BIND(soil_e_balance) BIND(sabg_chk) BIND(fact) BIND(coszen) BIND(fabd_sun)
+  BIND(fabd_sha) BIND(fabi_sun) BIND(fabi_sha) BIND(albsnd) BIND(albsni) BIND(imelt) BIND(xmf) BIND(xmf_h2osfc)
+  BIND(qflx_sl_top_soil) BIND(qflx_snow2topsoi) BIND(mflx_snowlyr_col) BIND(qflx_top_soil) BIND(mflx_neg_snow)
+  BIND(eflx_snomelt) BIND(qflx_snomelt) BIND(eflx_h2osfc_snow) BIND(qflx_h2osfc_ice) BIND(qflx_snofrz)
+  BIND(qflx_snofrz_lyr) BIND(qflx_rootsoi) BIND(dtbegin_column_h2o) BIND(dz) BIND(zsoi) BIND(zisoi) BIND(vtype)
+  BIND(psn_pft) BIND(veg_active) BIND(do_capsnow)
+#undef BIND
+  if (i != kNumStateFields) std::abort();
+  auto& ai = *S.aero_input;
+  auto& am = *S.aero_mass;
+  auto& ac = *S.aero_concen;
+#define BINDX(VIEW) add_field(c, kSpecs[i].name, kSpecs[i].dtype, kSpecs[i].nlev, VIEW); ++i;
+  BINDX(ai.bcphi) BINDX(ai.bcpho) BINDX(ai.bcdep) BINDX(ai.dst1_1) BINDX(ai.dst1_2) BINDX(ai.dst2_1) BINDX(ai.dst2_2)
+  BINDX(ai.dst3_1) BINDX(ai.dst3_2) BINDX(ai.dst4_1) BINDX(ai.dst4_2)
+  BINDX(am.mss_bcphi) BINDX(am.mss_bcpho) BINDX(am.mss_dst1) BINDX(am.mss_dst2) BINDX(am.mss_dst3) BINDX(am.mss_dst4)
+  BINDX(ac.cnc_bcphi) BINDX(ac.cnc_bcpho) BINDX(ac.cnc_dst1) BINDX(ac.cnc_dst2) BINDX(ac.cnc_dst3) BINDX(ac.cnc_dst4)
+  BINDX(c.dtend_column_h2o) BINDX(c.errh2o) BINDX(c.errh2osno) BINDX(c.dwb) BINDX(c.errsol) BINDX(c.errlon)
+  BINDX(c.errseb) BINDX(c.netrad) BINDX(c.errmask)
+#undef BINDX
+  if (i != kNumFields) std::abort();
+  for (int k = 0; k < kNumFields; ++k)
+    if (c.fields[k].name != kSpecs[k].name) std::abort();
+}
+
+RefCtx* ctx(elmk_handle h) { return reinterpret_cast<RefCtx*>(h); }
+
+template <class V> void fill_view(V& v, const double* src) {
+  for (size_t i = 0; i < v.size(); ++i) v.data()[i] = src[i];
+}
+
+void collect_errors(RefCtx& c) {
+  std::lock_guard<std::mutex> g(kokkos_shim::error_mutex());
+  for (const auto& e : kokkos_shim::errors()) {
+    if (e.col >= 0 && e.col < c.ncols) c.errmask(e.col) |= static_cast<int>(bit_for_message(e.what));
+    c.last_error = e.what;
+  }
+  kokkos_shim::errors().clear();
+}
+
+// kokkos_evaluate_conservation keeps its results in wrapper-local Views; this repeats the wrapper's
+// argument binding (conserved_quantity_kokkos.cc:22-68) on the reference's own evaluator functions.
+void conservation_outputs(RefCtx& c, double dtime) {
+  ELMStateType& S = *c.S;
+  const double hydrology_source_sink = 0.0;
+  namespace ce = ELM::conservation_eval;
+  using Kokkos::ALL;
+  using Kokkos::subview;
+  Kokkos::parallel_for("ref_conservation_outputs", c.ncols, [&](const int idx) {
+    c.dtend_column_h2o(idx) = ce::column_water_mass(S.h2ocan(idx), S.h2osno(idx), S.h2osfc(idx),
+                                                    subview(S.h2osoi_ice, idx, ALL), subview(S.h2osoi_liq, idx, ALL));
+    c.dwb(idx) = ce::dh2o_dt(S.dtbegin_column_h2o(idx), c.dtend_column_h2o(idx), dtime);
+    c.errh2o(idx) = ce::column_water_balance_error(S.dtbegin_column_h2o(idx), c.dtend_column_h2o(idx),
+                                                   hydrology_source_sink, S.forc_rain(idx), S.forc_snow(idx),
+                                                   S.qflx_evap_tot(idx), S.qflx_snwcp_ice(idx), dtime);
+    c.errh2osno(idx) = ce::snow_water_balance_error(
+        S.snl(idx), S.qflx_dew_snow(idx), S.qflx_dew_grnd(idx), S.qflx_sub_snow(idx), S.qflx_evap_grnd(idx),
+        S.qflx_snow_melt(idx), S.qflx_snwcp_ice(idx), S.qflx_snwcp_liq(idx), S.qflx_sl_top_soil(idx),
+        S.frac_sno_eff(idx), S.qflx_rain_grnd(idx), S.qflx_snow_grnd(idx), S.qflx_h2osfc_ice(idx), S.h2osno(idx),
+        S.h2osno_old(idx), dtime, S.do_capsnow(idx));
+    c.errsol(idx) = ce::solar_shortwave_balance_error(S.fsa(idx), S.fsr(idx), subview(S.forc_solad, idx, ALL),
+                                                      subview(S.forc_solai, idx, ALL));
+    c.errlon(idx) = ce::solar_longwave_balance_error(S.eflx_lwrad_out(idx), S.eflx_lwrad_net(idx), S.forc_lwrad(idx));
+    c.errseb(idx) = ce::surface_energy_balance_error(S.sabv(idx), S.sabg_chk(idx), S.forc_lwrad(idx),
+                                                     S.eflx_lwrad_out(idx), S.eflx_sh_tot(idx), S.eflx_lh_tot(idx),
+                                                     S.eflx_soil_grnd(idx));
+    c.netrad(idx) = ce::net_radiation(S.fsa(idx), S.eflx_lwrad_net(idx));
+  });
+}
+
+} // namespace
+
+extern "C" {
+
+int elmk_abi_version(void) { return ELMK_ABI_VERSION; }
+const char* elmk_backend(void) {
+#ifdef _OPENMP
+  return "reference-openmp";
+#else
+  return "reference-serial";
+#endif
+}
+int elmk_field_count(void) { return kNumFields; }
+int elmk_field_id(const char* name) {
+  for (int i = 0; i < kNumFields; ++i)
+    if (std::strcmp(kSpecs[i].name, name) == 0) return i;
+  return -1;
+}
+int elmk_field_info(int field, const char** name, int* dtype, int* nlev) {
+  if (field < 0 || field >= kNumFields) return ELMK_EINVAL;
+  if (name) *name = kSpecs[field].name;
+  if (dtype) *dtype = kSpecs[field].dtype;
+  if (nlev) *nlev = kSpecs[field].nlev;
+  return ELMK_OK;
+}
+
+int elmk_create(elmk_handle* out, int /*device*/, int64_t ncols) {
+  if (!out || ncols <= 0 || ncols > INT32_MAX) return ELMK_EINVAL;
+  auto* c = new RefCtx;
+  c->ncols = ncols;
+  const int n = static_cast<int>(ncols);
+  // as ELMInterface::ELMInterface (elm_kokkos_interface.cc:49-55) but with an empty forcing file name:
+  // the ELMState constructor does no file IO (elm_state_impl.hh:369-403)
+  c->S = std::make_unique<ELMStateType>(
+      n, ELM::Utils::create_domain_decomposition_2D(ELM::Utils::square_numprocs(1), {1, 1}, {0, 0}), std::string(),
+      ELM::Utils::Date(1985, 1, 1), 1);
+  c->dtend_column_h2o = ViewD1("dtend_column_h2o", n);
+  c->errh2o = ViewD1("errh2o", n);
+  c->errh2osno = ViewD1("errh2osno", n);
+  c->dwb = ViewD1("dwb", n);
+  c->errsol = ViewD1("errsol", n);
+  c->errlon = ViewD1("errlon", n);
+  c->errseb = ViewD1("errseb", n);
+  c->netrad = ViewD1("netrad", n);
+  c->errmask = ViewI1("errmask", n);
+  build_registry(*c);
+  *out = reinterpret_cast<elmk_handle>(c);
+  return ELMK_OK;
+}
+int elmk_destroy(elmk_handle h) {
+  delete ctx(h);
+  return ELMK_OK;
+}
+const char* elmk_last_error(elmk_handle h) { return h ? ctx(h)->last_error.c_str() : "null handle"; }
+int64_t elmk_ncols(elmk_handle h) { return ctx(h)->ncols; }
+
+int elmk_set_tables(elmk_handle h, const elmk_tables* t) {
+  RefCtx& c = *ctx(h);
+  ELMStateType& S = *c.S;
+  S.Land.ltype = t->ltype;
+  S.Land.ctype = t->ctype;
+  S.Land.vtype = t->vtype;
+  S.Land.urbpoi = t->urbpoi != 0;
+  S.Land.lakpoi = t->lakpoi != 0;
+  S.dewmx = t->dewmx;
+  S.oldfflag = t->oldfflag;
+  auto& p = *S.pft_data;
+  ViewD1* pft[ELMK_NPFT_TABLES] = {&p.fnr, &p.act25, &p.kcha, &p.koha, &p.cpha, &p.vcmaxha, &p.jmaxha, &p.tpuha,
+      &p.lmrha, &p.vcmaxhd, &p.jmaxhd, &p.tpuhd, &p.lmrhd, &p.lmrse, &p.qe, &p.theta_cj, &p.bbbopt, &p.mbbopt,
+      &p.c3psn, &p.slatop, &p.leafcn, &p.flnr, &p.fnitr, &p.dleaf, &p.smpso, &p.smpsc, &p.tc_stress, &p.z0mr,
+      &p.displar, &p.xl, &p.roota_par, &p.rootb_par, &p.rholvis, &p.rholnir, &p.rhosvis, &p.rhosnir, &p.taulvis,
+      &p.taulnir, &p.tausvis, &p.tausnir};
+  for (int k = 0; k < ELMK_NPFT_TABLES; ++k) fill_view(*pft[k], t->pft[k]);
+  fill_view(S.albsat, t->albsat);
+  fill_view(S.albdry, t->albdry);
+  auto& s = *S.snicar_data;
+  ViewD1* band[18] = {&s.ss_alb_oc1, &s.asm_prm_oc1, &s.ext_cff_mss_oc1, &s.ss_alb_oc2, &s.asm_prm_oc2,
+      &s.ext_cff_mss_oc2, &s.ss_alb_dst1, &s.asm_prm_dst1, &s.ext_cff_mss_dst1, &s.ss_alb_dst2, &s.asm_prm_dst2,
+      &s.ext_cff_mss_dst2, &s.ss_alb_dst3, &s.asm_prm_dst3, &s.ext_cff_mss_dst3, &s.ss_alb_dst4, &s.asm_prm_dst4,
+      &s.ext_cff_mss_dst4};
+  for (int k = 0; k < 18; ++k) fill_view(*band[k], t->snicar_band[k]);
+  ViewD2* snow[6] = {&s.ss_alb_snw_drc, &s.asm_prm_snw_drc, &s.ext_cff_mss_snw_drc, &s.ss_alb_snw_dfs,
+      &s.asm_prm_snw_dfs, &s.ext_cff_mss_snw_dfs};
+  for (int k = 0; k < 6; ++k) fill_view(*snow[k], t->snicar_snow[k]);
+  ViewD2* bc[6] = {&s.ss_alb_bc1, &s.asm_prm_bc1, &s.ext_cff_mss_bc1, &s.ss_alb_bc2, &s.asm_prm_bc2,
+      &s.ext_cff_mss_bc2};
+  for (int k = 0; k < 6; ++k) fill_view(*bc[k], t->snicar_bc[k]);
+  fill_view(s.bcenh, t->bcenh);
+  auto& a = *S.snw_rds_table;
+  fill_view(a.snowage_tau, t->snowage[0]);
+  fill_view(a.snowage_kappa, t->snowage[1]);
+  fill_view(a.snowage_drdt0, t->snowage[2]);
+  c.tables_set = true;
+  return ELMK_OK;
+}
+
+static int move_field(RefCtx& c, int field, void* host, int64_t col0, int64_t n, int layout, bool to_state) {
+  if (field < 0 || field >= kNumFields || col0 < 0 || n < 0 || col0 + n > c.ncols) return ELMK_EINVAL;
+  const FieldRef& f = c.fields[field];
+  char* state = static_cast<char*>(f.base) + static_cast<size_t>(col0) * f.nlev * f.esize;
+  char* hb = static_cast<char*>(host);
+  if (layout == ELMK_COL_OUTER || f.nlev == 1) {
+    const size_t bytes = static_cast<size_t>(n) * f.nlev * f.esize;
+    if (to_state) std::memcpy(state, hb, bytes); else std::memcpy(hb, state, bytes);
+  } else {
+    for (int64_t col = 0; col < n; ++col)
+      for (int l = 0; l < f.nlev; ++l) {
+        char* s = state + (static_cast<size_t>(col) * f.nlev + l) * f.esize;
+        char* d = hb + (static_cast<size_t>(l) * n + col) * f.esize;
+        if (to_state) std::memcpy(s, d, f.esize); else std::memcpy(d, s, f.esize);
+      }
+  }
+  return ELMK_OK;
+}
+int elmk_upload(elmk_handle h, int field, const void* host, int64_t col0, int64_t n, int layout) {
+  return move_field(*ctx(h), field, const_cast<void*>(host), col0, n, layout, true);
+}
+int elmk_download(elmk_handle h, int field, void* host, int64_t col0, int64_t n, int layout) {
+  return move_field(*ctx(h), field, host, col0, n, layout, false);
+}
+int elmk_upload_many(elmk_handle h, int nfields, const int* fields, const void* const* hosts, int64_t col0, int64_t n,
+                     int layout) {
+  for (int i = 0; i < nfields; ++i) {
+    int rc = elmk_upload(h, fields[i], hosts[i], col0, n, layout);
+    if (rc) return rc;
+  }
+  return ELMK_OK;
+}
+int elmk_download_many(elmk_handle h, int nfields, const int* fields, void* const* hosts, int64_t col0, int64_t n,
+                       int layout) {
+  for (int i = 0; i < nfields; ++i) {
+    int rc = elmk_download(h, fields[i], hosts[i], col0, n, layout);
+    if (rc) return rc;
+  }
+  return ELMK_OK;
+}
+int elmk_fill(elmk_handle h, int field, double value) {
+  RefCtx& c = *ctx(h);
+  if (field < 0 || field >= kNumFields) return ELMK_EINVAL;
+  const FieldRef& f = c.fields[field];
+  const size_t count = static_cast<size_t>(c.ncols) * f.nlev;
+  if (f.dtype == ELMK_F64) std::fill_n(static_cast<double*>(f.base), count, value);
+  else if (f.dtype == ELMK_I32) std::fill_n(static_cast<int*>(f.base), count, static_cast<int>(value));
+  else std::fill_n(static_cast<unsigned char*>(f.base), count, static_cast<unsigned char>(value != 0.0));
+  return ELMK_OK;
+}
+
+int elmk_init_timestep(elmk_handle h, int reset_forc_hgt) {
+  RefCtx& c = *ctx(h);
+  ELMStateType& S = *c.S;
+  using Kokkos::ALL;
+  using Kokkos::subview;
+  // per-column body of kokkos_init_timestep (init_timestep_kokkos.cc:53-70) and, optionally,
+  // ProcessZBOT (atm_physics_impl.hh:197-202)
+  Kokkos::parallel_for("ref_init_timestep", c.ncols, [&](const int idx) {
+    if (reset_forc_hgt) {
+      S.forc_hgt_u_patch(idx) = S.forc_hgt(idx);
+      S.forc_hgt_t_patch(idx) = S.forc_hgt(idx);
+      S.forc_hgt_q_patch(idx) = S.forc_hgt(idx);
+    }
+    S.h2osno_old(idx) = S.h2osno(idx);
+    S.dtbegin_column_h2o(idx) = ELM::conservation_eval::column_water_mass(
+        S.h2ocan(idx), S.h2osno(idx), S.h2osfc(idx), subview(S.h2osoi_ice, idx, ALL), subview(S.h2osoi_liq, idx, ALL));
+    ELM::init_timestep(S.Land.lakpoi, S.veg_active(idx), S.frac_veg_nosno_alb(idx), S.snl(idx), S.h2osno(idx),
+                       subview(S.h2osoi_ice, idx, ALL), subview(S.h2osoi_liq, idx, ALL), S.do_capsnow(idx),
+                       S.frac_veg_nosno(idx), subview(S.frac_iceold, idx, ALL));
+  });
+  c.launches += 1;
+  return ELMK_OK;
+}
+
+int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_t mask) {
+  RefCtx& c = *ctx(h);
+  if (!c.tables_set) return ELMK_ENOTABLES;
+  ELMStateType& S = *c.S;
+  S.dayl = dayl;
+  S.max_dayl = max_dayl;
+  const ELM::Utils::Date unused_date(1985, 1, 1); // kokkos_snow_hydrology ignores its Date argument
+  // chain order of ELMInterface::advance, elm_kokkos_interface.cc:289-318
+  if (mask & ELMK_G_FRAC_WET) { ELM::kokkos_frac_wet(S); c.launches += 1; }
+  if (mask & ELMK_G_ALBEDO) { ELM::kokkos_albedo_snicar(S); c.launches += 1; }
+  if (mask & ELMK_G_CANOPY_HYDROLOGY) { ELM::kokkos_canopy_hydrology(S, dtime); c.launches += 1; }
+  if (mask & ELMK_G_SURFACE_RADIATION) { ELM::kokkos_surface_radiation(S); c.launches += 1; }
+  if (mask & ELMK_G_CANOPY_TEMPERATURE) { ELM::kokkos_canopy_temperature(S); c.launches += 1; }
+  if (mask & ELMK_G_BAREGROUND_FLUXES) { ELM::kokkos_bareground_fluxes(S); c.launches += 1; }
+  if (mask & ELMK_G_CANOPY_FLUXES) { ELM::kokkos_canopy_fluxes(S, dtime); c.launches += 1; }
+  if (mask & ELMK_G_SOIL_TEMPERATURE) { ELM::kokkos_soil_temperature(S, dtime); c.launches += 9; }
+  if (mask & ELMK_G_SNOW_HYDROLOGY) { ELM::kokkos_snow_hydrology(S, dtime, unused_date); c.launches += 5; }
+  if (mask & ELMK_G_SURFACE_FLUXES) { ELM::kokkos_surface_fluxes(S, dtime); c.launches += 1; }
+  if (mask & ELMK_G_CONSERVATION) {
+    // the wrapper itself (prints column 0 to std::cout - silenced), then its eight per-column results
+    std::streambuf* keep = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    ELM::kokkos_evaluate_conservation(S, dtime);
+    std::cout.rdbuf(keep);
+    conservation_outputs(c, dtime);
+    c.launches += 1;
+  }
+  collect_errors(c);
+  return ELMK_OK;
+}
+int elmk_sync(elmk_handle) { return ELMK_OK; }
+int64_t elmk_launch_count(elmk_handle h) { return ctx(h)->launches; }
+
+int elmk_errors(elmk_handle h, uint32_t* any, int64_t* first_col) {
+  RefCtx& c = *ctx(h);
+  uint32_t acc = 0;
+  int64_t first = -1;
+  for (int64_t i = 0; i < c.ncols; ++i) {
+    const uint32_t w = static_cast<uint32_t>(c.errmask(i));
+    if (w && first < 0) first = i;
+    acc |= w;
+  }
+  if (any) *any = acc;
+  if (first_col) *first_col = first;
+  return ELMK_OK;
+}
+int elmk_clear_errors(elmk_handle h) {
+  RefCtx& c = *ctx(h);
+  for (int64_t i = 0; i < c.ncols; ++i) c.errmask(i) = 0;
+  return ELMK_OK;
+}
+const char* elmk_error_text(uint32_t) { return "see the reference's runtime_error text in elmk_last_error"; }
+
+int elmk_diag_reduce(elmk_handle h, double out[24]) {
+  RefCtx& c = *ctx(h);
+  ViewD1* d[8] = {&c.dtend_column_h2o, &c.errh2o, &c.errh2osno, &c.dwb, &c.errsol, &c.errlon, &c.errseb, &c.netrad};
+  for (int k = 0; k < 8; ++k) {
+    double s = 0.0, lo = (*d[k])(0), hi = (*d[k])(0);
+    for (int64_t i = 0; i < c.ncols; ++i) {
+      const double v = (*d[k])(i);
+      s += v;
+      lo = std::min(lo, v);
+      hi = std::max(hi, v);
+    }
+    out[k] = s;
+    out[8 + k] = lo;
+    out[16 + k] = hi;
+  }
+  return ELMK_OK;
+}
+int elmk_device_ptr(elmk_handle, int, void**, int64_t*) { return ELMK_EUNSUPPORTED; }
+
+// ---- oracle-only extra: the reference's one-time column initialisation, per column exactly as
+//      initialize_elm_kokkos.cc:374-431, used to check the product's ensemble generator ----
+int elmref_init_columns(elmk_handle h, const double* pct_sand, const double* pct_clay, const double* organic,
+                        double organic_max, const double* snow_depth_in) {
+  RefCtx& c = *ctx(h);
+  ELMStateType& S = *c.S;
+  using Kokkos::ALL;
+  using Kokkos::subview;
+  const int n = static_cast<int>(c.ncols);
+  ViewD2 sand("pct_sand", n, ELM::ELMdims::nlevgrnd()), clay("pct_clay", n, ELM::ELMdims::nlevgrnd()),
+      org("organic", n, ELM::ELMdims::nlevgrnd());
+  for (size_t i = 0; i < sand.size(); ++i) {
+    sand.data()[i] = pct_sand[i];
+    clay.data()[i] = pct_clay[i];
+    org.data()[i] = organic[i];
+  }
+  auto& pft_data = *S.pft_data;
+  Kokkos::parallel_for("ref_init_columns", c.ncols, [&](const int idx) {
+    S.snow_depth(idx) = snow_depth_in[idx];
+    S.psn_pft(idx) = pft_data.get_pft_psn(S.vtype(idx));
+    S.topo_slope(idx) = ELM::init_topo_slope(S.topo_slope(idx));
+    S.n_melt(idx) = ELM::init_melt_factor(S.Land.ltype, S.topo_std(idx));
+    S.micro_sigma(idx) = ELM::init_micro_sigma(S.topo_slope(idx));
+    ELM::init_snow_layers(S.snow_depth(idx), S.Land.lakpoi, S.snl(idx), subview(S.dz, idx, ALL),
+                          subview(S.zsoi, idx, ALL), subview(S.zisoi, idx, ALL));
+    ELM::init_soil_hydraulics(organic_max, subview(sand, idx, ALL), subview(clay, idx, ALL), subview(org, idx, ALL),
+                              subview(S.zsoi, idx, ALL), subview(S.watsat, idx, ALL), subview(S.bsw, idx, ALL),
+                              subview(S.sucsat, idx, ALL), subview(S.watdry, idx, ALL), subview(S.watopt, idx, ALL),
+                              subview(S.watfc, idx, ALL), subview(S.tkmg, idx, ALL), subview(S.tkdry, idx, ALL),
+                              subview(S.csol, idx, ALL));
+    ELM::init_vegrootfr(S.vtype(idx), pft_data.roota_par(S.vtype(idx)), pft_data.rootb_par(S.vtype(idx)),
+                        subview(S.zisoi, idx, ALL), subview(S.rootfr, idx, ALL));
+    ELM::init_soil_temp(S.Land, S.snl(idx), subview(S.t_soisno, idx, ALL), S.t_grnd(idx));
+    ELM::init_snow_state(S.Land.urbpoi, S.snl(idx), S.h2osno(idx), S.int_snow(idx), S.snow_depth(idx), S.h2osfc(idx),
+                         S.h2ocan(idx), S.frac_h2osfc(idx), S.fwet(idx), S.fdry(idx), S.frac_sno(idx),
+                         subview(S.snw_rds, idx, ALL));
+    ELM::init_soilh2o_state(S.Land, S.snl(idx), subview(S.watsat, idx, ALL), subview(S.t_soisno, idx, ALL),
+                            subview(S.dz, idx, ALL), subview(S.h2osoi_vol, idx, ALL), subview(S.h2osoi_liq, idx, ALL),
+                            subview(S.h2osoi_ice, idx, ALL));
+  });
+  return ELMK_OK;
+}
+
+} // extern "C"

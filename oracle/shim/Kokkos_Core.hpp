@@ -1,0 +1,144 @@
+// TEST INFRASTRUCTURE (oracle) - not part of the product path.
+//
+// Minimal host stand-in for the slice of the Kokkos API that the reference's
+// driver/kokkos/*_kokkos.cc wrappers use, so that those files compile UNMODIFIED
+// from /root/reference into oracle/_ref/libelmref.so (see oracle/build_ref.py).
+// Semantics that the reference relies on and that are reproduced here:
+//   * View storage is zero-initialised (the wrappers' scratch Views are assumed zero,
+//     SURVEY.md quirks 3/4), and it is first-touched inside an OpenMP loop so that the
+//     107 scratch allocations per step do not serialise the CPU baseline;
+//   * row-major (LayoutRight) indexing, like Kokkos' host default and ELM::Array
+//     (reference src/utils/array.hh:176-183);
+//   * every allocation is padded: the reference writes rt_snow(c, 5) one past a 5-wide
+//     row (soil_temp_rhs_impl.hh:93,101 - SURVEY.md quirk 12); the pad absorbs the write for
+//     the last column;
+//   * parallel_for runs the functor under "#pragma omp parallel for"; a C++ exception
+//     thrown by one column (the reference throws inside kernels) is caught per column and
+//     recorded in kokkos_shim::errors() instead of terminating the process.
+#pragma once
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#define KOKKOS_INLINE_FUNCTION inline
+#define KOKKOS_FUNCTION
+#define KOKKOS_LAMBDA [=]
+
+namespace kokkos_shim {
+struct ColumnError { long col; std::string what; };
+inline std::mutex& error_mutex() { static std::mutex m; return m; }
+inline std::vector<ColumnError>& errors() { static std::vector<ColumnError> e; return e; }
+inline void record(long col, const char* what) {
+  std::lock_guard<std::mutex> g(error_mutex());
+  if (errors().size() < 4096) errors().push_back({col, what});
+}
+} // namespace kokkos_shim
+
+namespace Kokkos {
+
+struct ALL_t {};
+inline constexpr ALL_t ALL{};
+
+inline void initialize(int&, char**) {}
+inline void initialize() {}
+inline void finalize() {}
+
+namespace detail {
+template <class T> struct strip { static constexpr int rank = 0; using type = T; };
+template <class T> struct strip<T*> { static constexpr int rank = 1 + strip<T>::rank; using type = typename strip<T>::type; };
+} // namespace detail
+
+template <class DataType> class View {
+public:
+  static constexpr int rank = detail::strip<DataType>::rank;
+  using value_type = typename detail::strip<DataType>::type;
+  using HostMirror = View<DataType>;
+
+  View() = default;
+  View(const std::string& label, size_t n0, size_t n1 = 1, size_t n2 = 1) : label_(label) { reshape(n0, n1, n2); }
+  // non-owning (subview) constructor
+  View(value_type* p, size_t n0, size_t n1 = 1, size_t n2 = 1) : ptr_(p) { n_[0] = n0; n_[1] = n1; n_[2] = n2; }
+
+  value_type& operator()(size_t i) const { return ptr_[i]; }
+  value_type& operator()(size_t i, size_t j) const { return ptr_[i * n_[1] + j]; }
+  value_type& operator()(size_t i, size_t j, size_t k) const { return ptr_[(i * n_[1] + j) * n_[2] + k]; }
+  value_type& operator[](size_t i) const { return ptr_[i]; }
+
+  size_t extent(int r) const { return n_[r]; }
+  size_t size() const { return n_[0] * n_[1] * n_[2]; }
+  value_type* data() const { return ptr_; }
+  const std::string& label() const { return label_; }
+
+  void reshape(size_t n0, size_t n1 = 1, size_t n2 = 1) {
+    n_[0] = n0; n_[1] = n1; n_[2] = n2;
+    const size_t count = size() + pad;
+    if constexpr (std::is_trivially_default_constructible_v<value_type> && std::is_trivially_destructible_v<value_type>) {
+      value_type* raw = static_cast<value_type*>(std::malloc(count * sizeof(value_type)));
+      unsigned char* bytes = reinterpret_cast<unsigned char*>(raw);
+      const long nbytes = static_cast<long>(count * sizeof(value_type));
+      const long chunk = 1 << 16;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) if (nbytes > (1 << 20))
+#endif
+      for (long b = 0; b < nbytes; b += chunk) std::memset(bytes + b, 0, static_cast<size_t>(nbytes - b < chunk ? nbytes - b : chunk));
+      owner_ = std::shared_ptr<value_type>(raw, [](value_type* p) { std::free(p); });
+    } else {
+      owner_ = std::shared_ptr<value_type>(new value_type[count](), std::default_delete<value_type[]>());
+    }
+    ptr_ = owner_.get();
+  }
+
+private:
+  static constexpr size_t pad = 64;
+  std::string label_;
+  size_t n_[3] = {0, 1, 1};
+  std::shared_ptr<value_type> owner_;
+  value_type* ptr_ = nullptr;
+};
+
+template <class DT> auto subview(const View<DT>& v, size_t i, ALL_t) {
+  static_assert(View<DT>::rank == 2, "row subview needs a rank-2 View");
+  using T = typename View<DT>::value_type;
+  return View<T*>(&v(i, 0), v.extent(1));
+}
+template <class DT> auto subview(const View<DT>& v, size_t i, ALL_t, ALL_t) {
+  static_assert(View<DT>::rank == 3, "plane subview needs a rank-3 View");
+  using T = typename View<DT>::value_type;
+  return View<T**>(&v(i, 0, 0), v.extent(1), v.extent(2));
+}
+
+template <class DT> View<DT> create_mirror_view(const View<DT>& v) { return v; }
+
+template <class DT> void deep_copy(const View<DT>& dst, const View<DT>& src) {
+  if (dst.data() == src.data()) return;
+  for (size_t i = 0; i < src.size(); ++i) dst.data()[i] = src.data()[i];
+}
+template <class DT, class S, class = std::enable_if_t<std::is_convertible_v<S, typename View<DT>::value_type>>>
+void deep_copy(const View<DT>& dst, const S& value) {
+  for (size_t i = 0; i < dst.size(); ++i) dst.data()[i] = value;
+}
+template <class DT, class... Extents> void resize(View<DT>& v, Extents... e) { v.reshape(static_cast<size_t>(e)...); }
+
+template <class Functor> void parallel_for(const std::string&, size_t n, const Functor& f) {
+  const long count = static_cast<long>(n);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (long i = 0; i < count; ++i) {
+    try {
+      f(static_cast<int>(i));
+    } catch (const std::exception& e) {
+      kokkos_shim::record(i, e.what());
+    }
+  }
+}
+template <class Functor> void parallel_for(size_t n, const Functor& f) { parallel_for(std::string(), n, f); }
+
+} // namespace Kokkos
