@@ -101,6 +101,10 @@ class Library:
             "elmk_error_text": (C.c_char_p, [C.c_uint32]),
             "elmk_diag_reduce": (C.c_int, [H, _PD]),
             "elmk_device_ptr": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+            "elmk_stream": (C.c_int, [H, C.POINTER(C.c_void_p)]),
+            "elmk_timing_enable": (C.c_int, [H, C.c_int]),
+            "elmk_timing_read": (C.c_int, [H, C.c_int, C.POINTER(C.c_char_p), _PD, C.POINTER(C.c_int64),
+                                           C.POINTER(C.c_uint32)]),
         }
         self.symbols = list(sig)
         for name, (res, args) in sig.items():
@@ -260,6 +264,27 @@ class Columns:
         out = np.zeros(24)
         self._check(self.lib.dll.elmk_diag_reduce(self._h, out.ctypes.data_as(_PD)), "elmk_diag_reduce")
         return out
+
+    @property
+    def stream(self) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.dll.elmk_stream(self._h, C.byref(p)), "elmk_stream")
+        return p.value or 0
+
+    def timing(self, on: bool):
+        self._check(self.lib.dll.elmk_timing_enable(self._h, int(on)), "elmk_timing_enable")
+
+    def timing_read(self):
+        """[(launch name, group mask, total ms, launches)] since timing(True)."""
+        k = 64
+        names = (C.c_char_p * k)()
+        ms = (C.c_double * k)()
+        cnt = (C.c_int64 * k)()
+        masks = (C.c_uint32 * k)()
+        n = self.lib.dll.elmk_timing_read(self._h, k, names, ms, cnt, masks)
+        if n < 0:
+            self._check(n, "elmk_timing_read")
+        return [(names[i].decode(), int(masks[i]), float(ms[i]), int(cnt[i])) for i in range(min(n, k))]
 
     def device_ptr(self, name: str):
         p, s = C.c_void_p(), C.c_int64()

@@ -1,0 +1,104 @@
+// elmk_common.h - shared definitions of the column-physics core.
+//
+// The physics core (phys_*.h) is single-source: the CUDA kernels in k_*.cu instantiate it for
+// sm_100a; oracle/port compiles the same headers with g++ as a CPU checker of the source itself
+// (test infrastructure only - the product library has no host path).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ELMK_HD __host__ __device__ __forceinline__
+#define ELMK_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define ELMK_HD inline
+#define ELMK_HD_NOINLINE inline
+#endif
+
+namespace elmk {
+
+// ---- dimensions (reference src/data/elm_constants.h:84-98) ----
+constexpr int NLEVSNO = 5;       // snow layer slots
+constexpr int NLEVGRND = 15;     // soil layers
+constexpr int NLEVTOT = 20;      // snow + soil
+constexpr int NLEVSOI = 10;      // hydrologically active soil layers
+constexpr int NLEVBED = 15;      // layers to bedrock
+constexpr int NUMRAD = 2;        // VIS, NIR
+constexpr int NBND_SNW = 5;      // SNICAR spectral bands
+constexpr int NAER = 8;          // aerosol species in snow
+constexpr int NROWS = 21;        // unknowns of the temperature system: 5 snow + surface water + 15 soil
+
+// ---- physical constants (reference src/data/elm_constants.h:18-52) ----
+constexpr double TFRZ = 273.15;
+constexpr double PI = 3.14159265358979323846;
+constexpr double BOLTZ = 1.38065e-23;
+constexpr double AVOGAD = 6.02214e26;
+constexpr double MWWV = 18.016;
+constexpr double RGAS = AVOGAD * BOLTZ;
+constexpr double RWV = RGAS / MWWV;
+constexpr double STEBOL = 5.67e-8;
+constexpr double MWDAIR = 28.966;
+constexpr double RAIR = RGAS / MWDAIR;
+constexpr double GRAV = 9.80616;
+constexpr double ROVERG = RWV / GRAV * 1000.;
+constexpr double O2_MOLAR_CONST = 0.209;
+constexpr double CO2_PPMV = 355.0;
+constexpr double DENICE = 0.917e3;
+constexpr double DENH2O = 1.000e3;
+constexpr double HVAP = 2.501e6;
+constexpr double HFUS = 3.337e5;
+constexpr double HSUB = HVAP + HFUS;
+constexpr double VKC = 0.4;
+constexpr double CPAIR = 1.00464e3;
+constexpr double CPICE = 2.11727e3;
+constexpr double CPWAT = 4.188e3;
+constexpr double CSOILC = 0.004;
+constexpr double ZLND = 0.01;
+constexpr double ZSNO = 0.0024;
+constexpr double SNW_RDS_MIN = 54.526;
+constexpr double H2OSNO_MAX = 1000.0;
+
+// land-unit keys (reference src/data/land_data.h:7-20)
+constexpr int ISTSOIL = 1;
+constexpr int ISTCROP = 2;
+// PFT keys used by the hot path (elm_constants.h:56-80)
+constexpr int PFT_SOYBEAN = 23;
+constexpr int PFT_SOYBEAN_IRRIG = 24;
+
+// ---- per-column error bits (values mirror include/elmk_b200.h) ----
+constexpr uint32_t ERR_CANOPY_LAYER = 1u << 0;
+constexpr uint32_t ERR_SNICAR_RADIUS = 1u << 1;
+constexpr uint32_t ERR_SNICAR_NEGABS = 1u << 2;
+constexpr uint32_t ERR_SNICAR_ENERGY = 1u << 3;
+constexpr uint32_t ERR_SNICAR_ALBEDO = 1u << 4;
+constexpr uint32_t ERR_SABG_LAYERS = 1u << 5;
+constexpr uint32_t ERR_FORC_HEIGHT = 1u << 6;
+constexpr uint32_t ERR_QUADRATIC = 1u << 7;
+constexpr uint32_t ERR_BRENT_BRACKET = 1u << 8;
+constexpr uint32_t ERR_NEG_STOMATAL = 1u << 9;
+constexpr uint32_t ERR_SNOWAGE_DR = 1u << 10;
+constexpr uint32_t ERR_DIVIDE_RADIUS = 1u << 11;
+
+// ---- arithmetic helpers ----
+// The reference is written with std::min/std::max; their NaN and signed-zero behaviour
+// ((b < a) ? b : a and (a < b) ? b : a) differs from fmin/fmax, so it is spelled out.
+ELMK_HD double dmin(double a, double b) { return (b < a) ? b : a; }
+ELMK_HD double dmax(double a, double b) { return (a < b) ? b : a; }
+ELMK_HD int imin(int a, int b) { return (b < a) ? b : a; }
+ELMK_HD int imax(int a, int b) { return (a < b) ? b : a; }
+
+// Integer powers.  The reference calls pow(x, 2.0|3.0|4.0); glibc's pow is correctly rounded in
+// practice, so x*x is bit-identical to pow(x, 2.0), while products for the cube and the fourth
+// power can differ from it in the last bit.  ELMK_EXACT_POW (set by the CPU checker build) keeps
+// the libm call so that the checker can be compared bit-for-bit with the reference; the CUDA
+// build uses multiplications (3 DMUL instead of a ~100-instruction pow), inside the 1e-12 bar.
+ELMK_HD double sq(double x) { return x * x; }
+#ifdef ELMK_EXACT_POW
+ELMK_HD double cube(double x) { return pow(x, 3.0); }
+ELMK_HD double pow4(double x) { return pow(x, 4.0); }
+#else
+ELMK_HD double cube(double x) { return x * x * x; }
+ELMK_HD double pow4(double x) { const double x2 = x * x; return x2 * x2; }
+#endif
+
+} // namespace elmk

@@ -1,0 +1,765 @@
+// elmk_lib.cu - libelmk_b200.so: the C ABI of include/elmk_b200.h over hand-written FP64 CUDA kernels
+// for sm_100a.  One handle = one device, one stream, one contiguous range of land columns resident in
+// HBM as structure-of-arrays with the column index innermost (elmk_state.h).
+//
+// Kernels: one thread per column.  A launch runs a compile-time set of kernel groups (a bit mask of
+// ELMK_G_*) back to back for its column, in the chain order of the reference's
+// ELMInterface::advance (driver/kokkos/elm_kokkos_interface.cc:289-318); elmk_step covers the requested
+// mask with the launches of the active plan (see kPlans).  The reference issues 23 parallel_for
+// dispatches and 107 scratch allocations per step for the same work.
+//
+// There is no host fallback: every entry point that computes needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/elmk_b200.h"
+#include "elmk_state.h"
+#include "phys_albedo.h"
+#include "phys_bareground.h"
+#include "phys_canflux.h"
+#include "phys_cantemp.h"
+#include "phys_hydrology.h"
+#include "phys_radiation.h"
+#include "phys_snow.h"
+#include "phys_soiltemp.h"
+#include "phys_surfflux.h"
+
+namespace {
+using namespace elmk;
+
+// ------------------------------------------------------------------------------------------------
+// field table
+// ------------------------------------------------------------------------------------------------
+struct Spec { const char* name; int dtype; int nlev; };
+const Spec kSpecs[] = {
+#define F64 ELMK_F64
+#define I32 ELMK_I32
+#define U8 ELMK_U8
+#define ELMK_FIELD(name, type, nlev, cls) {#name, type, nlev},
+#include "../../include/elmk_fields.def"
+#undef ELMK_FIELD
+#undef F64
+#undef I32
+#undef U8
+};
+constexpr int kNumFields = sizeof(kSpecs) / sizeof(kSpecs[0]);
+inline size_t esize(int dt) { return dt == ELMK_F64 ? 8 : dt == ELMK_I32 ? 4 : 1; }
+
+constexpr int kBlock = 128;              // threads per block of the column kernels
+constexpr int kColAlign = 128;           // columns are padded to a multiple of this
+constexpr size_t kStageBytes = 64u << 20; // device staging buffer for layout conversion (per slot)
+
+// ------------------------------------------------------------------------------------------------
+// column kernels
+// ------------------------------------------------------------------------------------------------
+template <uint32_t MASK>
+__global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
+{
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  if (c >= S.ncols) return;
+  const Tables& T = *Tp;
+  if (MASK & ELMK_G_FRAC_WET) column_frac_wet(S, T, c);
+  if (MASK & ELMK_G_ALBEDO) column_albedo(S, T, c);
+  if (MASK & ELMK_G_CANOPY_HYDROLOGY) column_canopy_hydrology(S, T, A.dtime, c);
+  if (MASK & ELMK_G_SURFACE_RADIATION) column_surface_radiation(S, T, c);
+  if (MASK & ELMK_G_CANOPY_TEMPERATURE) column_canopy_temperature(S, T, c);
+  if (MASK & ELMK_G_BAREGROUND_FLUXES) column_bareground_fluxes(S, T, c);
+  if (MASK & ELMK_G_CANOPY_FLUXES) column_canopy_fluxes(S, T, A, c);
+  if (MASK & ELMK_G_SOIL_TEMPERATURE) column_soil_temperature(S, T, A.dtime, c);
+  if (MASK & ELMK_G_SNOW_HYDROLOGY) column_snow_hydrology(S, T, A.dtime, c);
+  if (MASK & ELMK_G_SURFACE_FLUXES) column_surface_fluxes(S, T, A.dtime, c);
+  if (MASK & ELMK_G_CONSERVATION) column_conservation(S, T, A.dtime, c);
+}
+
+__global__ void __launch_bounds__(kBlock) k_init_timestep(const Cols S, const Tables* __restrict__ Tp, const int reset)
+{
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  if (c >= S.ncols) return;
+  column_init_timestep(S, *Tp, reset, c);
+}
+
+typedef void (*GroupKernel)(const Cols, const Tables*, const StepArgs);
+struct Launch { uint32_t mask; GroupKernel fn; const char* name; };
+#define ELMK_LAUNCH(M, NAME) {(M), k_groups<(M)>, NAME}
+
+// plan "split": one launch per kernel group (the reference's wrapper granularity)
+const Launch kSplit[] = {
+    ELMK_LAUNCH(ELMK_G_FRAC_WET, "frac_wet"),
+    ELMK_LAUNCH(ELMK_G_ALBEDO, "albedo_snicar"),
+    ELMK_LAUNCH(ELMK_G_CANOPY_HYDROLOGY, "canopy_hydrology"),
+    ELMK_LAUNCH(ELMK_G_SURFACE_RADIATION, "surface_radiation"),
+    ELMK_LAUNCH(ELMK_G_CANOPY_TEMPERATURE, "canopy_temperature"),
+    ELMK_LAUNCH(ELMK_G_BAREGROUND_FLUXES, "bareground_fluxes"),
+    ELMK_LAUNCH(ELMK_G_CANOPY_FLUXES, "canopy_fluxes"),
+    ELMK_LAUNCH(ELMK_G_SOIL_TEMPERATURE, "soil_temperature"),
+    ELMK_LAUNCH(ELMK_G_SNOW_HYDROLOGY, "snow_hydrology"),
+    ELMK_LAUNCH(ELMK_G_SURFACE_FLUXES, "surface_fluxes"),
+    ELMK_LAUNCH(ELMK_G_CONSERVATION, "conservation"),
+};
+// plan "fused": the chain cut where register pressure changes character -
+//   radiative transfer | closed-form hydrology/radiation/temperature + bare-ground fluxes |
+//   canopy-flux iteration | banded solve | snow state machine + flux update + diagnostics
+constexpr uint32_t M_RAD = ELMK_G_FRAC_WET | ELMK_G_ALBEDO;
+constexpr uint32_t M_SFC = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | ELMK_G_CANOPY_TEMPERATURE |
+                           ELMK_G_BAREGROUND_FLUXES;
+constexpr uint32_t M_END = ELMK_G_SNOW_HYDROLOGY | ELMK_G_SURFACE_FLUXES | ELMK_G_CONSERVATION;
+const Launch kFused[] = {
+    ELMK_LAUNCH(M_RAD, "fracwet+albedo"),
+    ELMK_LAUNCH(M_SFC, "hydrology+radiation+temperature+bareground"),
+    ELMK_LAUNCH(ELMK_G_CANOPY_FLUXES, "canopy_fluxes"),
+    ELMK_LAUNCH(ELMK_G_SOIL_TEMPERATURE, "soil_temperature"),
+    ELMK_LAUNCH(M_END, "snow+surface_fluxes+conservation"),
+};
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion between the reference's host layout (column outer) and the device layout
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileCols = 64;
+// src: staged host rows [n][nlev]; dst: field base [nlev][np], columns col0..col0+n
+template <typename T>
+__global__ void __launch_bounds__(256) k_outer_to_inner(const T* __restrict__ src, T* __restrict__ dst, const long long n,
+                                                         const int nlev, const long long np, const long long col0)
+{
+  extern __shared__ unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  const long long c0 = (long long)blockIdx.x * kTileCols;
+  const int cols = (int)((n - c0 < kTileCols) ? (n - c0) : kTileCols);
+  const int count = cols * nlev;
+  const int pitch = nlev | 1;   // odd pitch: conflict-free shared-memory transposition
+  for (int e = threadIdx.x; e < count; e += blockDim.x) {
+    const int cl = e / nlev, lev = e - cl * nlev;
+    tile[cl * pitch + lev] = src[c0 * nlev + e];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kTileCols * nlev; e += blockDim.x) {
+    const int lev = e / kTileCols, cl = e - lev * kTileCols;
+    if (cl < cols) dst[(long long)lev * np + col0 + c0 + cl] = tile[cl * pitch + lev];
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_inner_to_outer(const T* __restrict__ src, T* __restrict__ dst, const long long n,
+                                                         const int nlev, const long long np, const long long col0)
+{
+  extern __shared__ unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  const long long c0 = (long long)blockIdx.x * kTileCols;
+  const int cols = (int)((n - c0 < kTileCols) ? (n - c0) : kTileCols);
+  const int pitch = nlev | 1;
+  for (int e = threadIdx.x; e < kTileCols * nlev; e += blockDim.x) {
+    const int lev = e / kTileCols, cl = e - lev * kTileCols;
+    if (cl < cols) tile[cl * pitch + lev] = src[(long long)lev * np + col0 + c0 + cl];
+  }
+  __syncthreads();
+  const int count = cols * nlev;
+  for (int e = threadIdx.x; e < count; e += blockDim.x) {
+    const int cl = e / nlev, lev = e - cl * nlev;
+    dst[c0 * nlev + e] = tile[cl * pitch + lev];
+  }
+}
+
+template <typename T> __global__ void k_fill(T* __restrict__ p, const long long count, const T v)
+{
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions: error words and the balance diagnostics
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_errors(const int* __restrict__ errmask, const int n, unsigned int* any,
+                                                long long* first)
+{
+  unsigned int acc = 0;
+  long long lo = 0x7fffffffffffffffLL;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned int w = (unsigned int)errmask[i];
+    if (w) {
+      acc |= w;
+      if (i < lo) lo = i;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc |= __shfl_xor_sync(0xffffffffu, acc, o);
+    const long long other = __shfl_xor_sync(0xffffffffu, lo, o);
+    lo = (other < lo) ? other : lo;
+  }
+  if ((threadIdx.x & 31) == 0 && acc) {
+    atomicOr(any, acc);
+    atomicMin(first, lo);
+  }
+}
+
+// out[k] = sum, out[8+k] = min, out[16+k] = max of diagnostic k; one block per (diagnostic, slice),
+// per-block partials combined by the host in a fixed order (deterministic result)
+constexpr int kDiagSlices = 64;
+__global__ void __launch_bounds__(256) k_diag(const Cols S, double* __restrict__ partial)
+{
+  const double* d;
+  switch (blockIdx.y) {
+    case 0: d = S.dtend_column_h2o; break;
+    case 1: d = S.errh2o; break;
+    case 2: d = S.errh2osno; break;
+    case 3: d = S.dwb; break;
+    case 4: d = S.errsol; break;
+    case 5: d = S.errlon; break;
+    case 6: d = S.errseb; break;
+    default: d = S.netrad; break;
+  }
+  const int n = S.ncols;
+  const int per = (n + kDiagSlices - 1) / kDiagSlices;
+  const int lo_i = blockIdx.x * per;
+  const int hi_i = (lo_i + per < n) ? lo_i + per : n;
+  double s = 0.0, lo = INFINITY, hi = -INFINITY;
+  for (int i = lo_i + threadIdx.x; i < hi_i; i += blockDim.x) {
+    const double v = d[i];
+    s += v;
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+  }
+  __shared__ double sh[3][256];
+  sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = lo; sh[2][threadIdx.x] = hi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] = fmin(sh[1][threadIdx.x], sh[1][threadIdx.x + o]);
+      sh[2][threadIdx.x] = fmax(sh[2][threadIdx.x], sh[2][threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double* p = partial + ((size_t)blockIdx.y * kDiagSlices + blockIdx.x) * 3;
+    p[0] = sh[0][0]; p[1] = sh[1][0]; p[2] = sh[2][0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  int64_t ncols = 0, np = 0;
+  cudaStream_t stream = nullptr;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<void*> base;
+  Cols cols;
+  Tables* d_tables = nullptr;
+  double* d_table_data = nullptr;
+  char* stage[2] = {nullptr, nullptr};
+  int stage_next = 0;
+  unsigned int* d_err = nullptr;   // [0] any, then long long first at +8
+  double* d_diag = nullptr;
+  void* h_pinned = nullptr;        // small pinned buffer for scalar read-backs
+  bool tables_set = false;
+  int64_t launches = 0;
+  // optional per-launch timing
+  bool timing = false;
+  struct Timed { const char* name; uint32_t mask; cudaEvent_t t0, t1; };
+  std::vector<Timed> timed;          // recorded, not yet accumulated
+  std::vector<cudaEvent_t> ev_pool;  // recycled events
+  struct Acc { const char* name; uint32_t mask; double ms; int64_t n; };
+  std::vector<Acc> acc;
+  const Launch* plan = kFused;
+  int plan_len = sizeof(kFused) / sizeof(kFused[0]);
+  std::string last_error;
+};
+Ctx* ctx(elmk_handle h) { return reinterpret_cast<Ctx*>(h); }
+
+int fail(Ctx* c, cudaError_t e, const char* what) {
+  if (c) c->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return ELMK_ECUDA;
+}
+#define CU(call)                                        \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return fail(c, e_, #call);   \
+  } while (0)
+
+cudaEvent_t take_event(Ctx* c) {
+  if (!c->ev_pool.empty()) {
+    cudaEvent_t e = c->ev_pool.back();
+    c->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+// brackets one kernel launch with events when timing is on
+struct TimedScope {
+  Ctx* c;
+  Ctx::Timed t;
+  TimedScope(Ctx* c_, const char* name, uint32_t mask) : c(c_) {
+    if (!c->timing) return;
+    t = {name, mask, take_event(c), take_event(c)};
+    cudaEventRecord(t.t0, c->stream);
+  }
+  ~TimedScope() {
+    if (!c->timing) return;
+    cudaEventRecord(t.t1, c->stream);
+    c->timed.push_back(t);
+  }
+};
+int drain_timing(Ctx* c) {
+  if (c->timed.empty()) return ELMK_OK;
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) { c->last_error = cudaGetErrorString(e); return ELMK_ECUDA; }
+  for (auto& t : c->timed) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.t0, t.t1);
+    bool found = false;
+    for (auto& a : c->acc)
+      if (a.name == t.name) { a.ms += ms; a.n += 1; found = true; break; }
+    if (!found) c->acc.push_back({t.name, t.mask, (double)ms, 1});
+    c->ev_pool.push_back(t.t0);
+    c->ev_pool.push_back(t.t1);
+  }
+  c->timed.clear();
+  return ELMK_OK;
+}
+
+int bind(Ctx* c) {
+  cudaError_t e = cudaSetDevice(c->device);
+  return e == cudaSuccess ? ELMK_OK : fail(c, e, "cudaSetDevice");
+}
+
+template <typename T>
+int convert(Ctx* c, bool up, const T* staged_or_field, T* dst, int64_t n, int nlev, int64_t col0) {
+  const unsigned grid = (unsigned)((n + kTileCols - 1) / kTileCols);
+  const size_t sh = (size_t)kTileCols * (nlev | 1) * sizeof(T);
+  if (up) k_outer_to_inner<T><<<grid, 256, sh, c->stream>>>(staged_or_field, dst, n, nlev, c->np, col0);
+  else k_inner_to_outer<T><<<grid, 256, sh, c->stream>>>(staged_or_field, dst, n, nlev, c->np, col0);
+  c->launches += 1;
+  CU(cudaGetLastError());
+  return ELMK_OK;
+}
+
+// host <-> device movement of one field; asynchronous on the stream when the host buffer is pinned
+int move_field(Ctx* c, int field, void* host, int64_t col0, int64_t n, int layout, bool up) {
+  if (field < 0 || field >= kNumFields || col0 < 0 || n < 0 || col0 + n > c->ncols || !host) {
+    c->last_error = "bad field / column range";
+    return ELMK_EINVAL;
+  }
+  if (n == 0) return ELMK_OK;
+  const int nlev = kSpecs[field].nlev;
+  const int dt = kSpecs[field].dtype;
+  const size_t es = esize(dt);
+  char* dev = static_cast<char*>(c->base[field]);
+  char* hb = static_cast<char*>(host);
+  const cudaMemcpyKind kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  if (nlev == 1) {
+    if (up) CU(cudaMemcpyAsync(dev + col0 * es, hb, n * es, kind, c->stream));
+    else CU(cudaMemcpyAsync(hb, dev + col0 * es, n * es, kind, c->stream));
+    return ELMK_OK;
+  }
+  if (layout == ELMK_COL_INNER) {
+    // host[(lev)*n + col]: one strided 2-D copy
+    if (up) CU(cudaMemcpy2DAsync(dev + col0 * es, c->np * es, hb, n * es, n * es, nlev, kind, c->stream));
+    else CU(cudaMemcpy2DAsync(hb, n * es, dev + col0 * es, c->np * es, n * es, nlev, kind, c->stream));
+    return ELMK_OK;
+  }
+  // reference layout host[(col)*nlev + lev]: stage the rows on the device, transpose there
+  const int64_t chunk_cols = std::max<int64_t>(kTileCols, (int64_t)(kStageBytes / (es * nlev)) / kTileCols * kTileCols);
+  for (int64_t done = 0; done < n; done += chunk_cols) {
+    const int64_t m = std::min(chunk_cols, n - done);
+    const int slot = c->stage_next;
+    c->stage_next ^= 1;
+    char* st = c->stage[slot];
+    char* hchunk = hb + (size_t)done * nlev * es;
+    if (up) {
+      CU(cudaMemcpyAsync(st, hchunk, (size_t)m * nlev * es, kind, c->stream));
+      int rc;
+      if (dt == ELMK_F64) rc = convert<double>(c, true, (const double*)st, (double*)dev, m, nlev, col0 + done);
+      else if (dt == ELMK_I32) rc = convert<int>(c, true, (const int*)st, (int*)dev, m, nlev, col0 + done);
+      else rc = convert<unsigned char>(c, true, (const unsigned char*)st, (unsigned char*)dev, m, nlev, col0 + done);
+      if (rc) return rc;
+    } else {
+      int rc;
+      if (dt == ELMK_F64) rc = convert<double>(c, false, (const double*)dev, (double*)st, m, nlev, col0 + done);
+      else if (dt == ELMK_I32) rc = convert<int>(c, false, (const int*)dev, (int*)st, m, nlev, col0 + done);
+      else rc = convert<unsigned char>(c, false, (const unsigned char*)dev, (unsigned char*)st, m, nlev, col0 + done);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(hchunk, st, (size_t)m * nlev * es, kind, c->stream));
+    }
+  }
+  return ELMK_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int elmk_abi_version(void) { return ELMK_ABI_VERSION; }
+const char* elmk_backend(void) { return "cuda-sm100a"; }
+int elmk_field_count(void) { return kNumFields; }
+int elmk_field_id(const char* name) {
+  if (!name) return -1;
+  for (int i = 0; i < kNumFields; ++i)
+    if (std::strcmp(kSpecs[i].name, name) == 0) return i;
+  return -1;
+}
+int elmk_field_info(int field, const char** name, int* dtype, int* nlev) {
+  if (field < 0 || field >= kNumFields) return ELMK_EINVAL;
+  if (name) *name = kSpecs[field].name;
+  if (dtype) *dtype = kSpecs[field].dtype;
+  if (nlev) *nlev = kSpecs[field].nlev;
+  return ELMK_OK;
+}
+
+int elmk_create(elmk_handle* out, int device, int64_t ncols) {
+  if (!out || ncols <= 0 || ncols > INT32_MAX - kColAlign) return ELMK_EINVAL;
+  *out = nullptr;
+  Ctx* c = new Ctx;
+  c->device = device;
+  c->ncols = ncols;
+  c->np = (ncols + kColAlign - 1) / kColAlign * kColAlign;
+  auto bail = [&](int rc) {
+    std::fprintf(stderr, "elmk_create: %s\n", c->last_error.c_str());
+    elmk_destroy(reinterpret_cast<elmk_handle>(c));
+    return rc;
+  };
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(fail(c, e, "cudaSetDevice"));
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail(fail(c, e, "cudaStreamCreate"));
+  // one arena for all per-column fields; every field starts on a 256-byte boundary and, because np is
+  // a multiple of 128 columns, so does every level row of every field
+  std::vector<size_t> offset(kNumFields);
+  size_t total = 0;
+  for (int f = 0; f < kNumFields; ++f) {
+    offset[f] = total;
+    total += ((size_t)c->np * kSpecs[f].nlev * esize(kSpecs[f].dtype) + 255) / 256 * 256;
+  }
+  c->arena_bytes = total;
+  if ((e = cudaMalloc(&c->arena, total)) != cudaSuccess) return bail(fail(c, e, "cudaMalloc(column state)"));
+  if ((e = cudaMemsetAsync(c->arena, 0, total, c->stream)) != cudaSuccess) return bail(fail(c, e, "cudaMemset"));
+  c->base.resize(kNumFields);
+  for (int f = 0; f < kNumFields; ++f) c->base[f] = c->arena + offset[f];
+  c->cols.np = c->np;
+  c->cols.ncols = (int)ncols;
+  c->cols.pad_ = 0;
+  {
+    int f = 0;
+#define ELMK_FIELD(name, type, nlev, cls) c->cols.name = static_cast<elmk_##type*>(c->base[f++]);
+#include "../../include/elmk_fields.def"
+#undef ELMK_FIELD
+  }
+  for (int s = 0; s < 2; ++s) {
+    if ((e = cudaMalloc(&c->stage[s], kStageBytes)) != cudaSuccess) return bail(fail(c, e, "cudaMalloc(stage)"));
+  }
+  if ((e = cudaMalloc(&c->d_tables, sizeof(Tables))) != cudaSuccess) return bail(fail(c, e, "cudaMalloc(tables)"));
+  const size_t table_doubles = (size_t)6 * NBND_SNW * ELMK_MIE_SNW + (size_t)3 * 11 * 31 * 8;
+  if ((e = cudaMalloc(&c->d_table_data, table_doubles * sizeof(double))) != cudaSuccess)
+    return bail(fail(c, e, "cudaMalloc(table data)"));
+  if ((e = cudaMalloc(&c->d_err, 16)) != cudaSuccess) return bail(fail(c, e, "cudaMalloc(err)"));
+  if ((e = cudaMalloc(&c->d_diag, sizeof(double) * 8 * kDiagSlices * 3)) != cudaSuccess)
+    return bail(fail(c, e, "cudaMalloc(diag)"));
+  if ((e = cudaMallocHost(&c->h_pinned, sizeof(double) * 8 * kDiagSlices * 3)) != cudaSuccess)
+    return bail(fail(c, e, "cudaMallocHost"));
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail(fail(c, e, "cudaStreamSynchronize"));
+  const char* plan = std::getenv("ELMK_PLAN");
+  if (plan && std::strcmp(plan, "split") == 0) {
+    c->plan = kSplit;
+    c->plan_len = sizeof(kSplit) / sizeof(kSplit[0]);
+  }
+  *out = reinterpret_cast<elmk_handle>(c);
+  return ELMK_OK;
+}
+
+int elmk_destroy(elmk_handle h) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->arena);
+  cudaFree(c->stage[0]);
+  cudaFree(c->stage[1]);
+  cudaFree(c->d_tables);
+  cudaFree(c->d_table_data);
+  cudaFree(c->d_err);
+  cudaFree(c->d_diag);
+  for (auto& t : c->timed) { cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return ELMK_OK;
+}
+
+const char* elmk_last_error(elmk_handle h) { return h ? ctx(h)->last_error.c_str() : "null handle"; }
+int64_t elmk_ncols(elmk_handle h) { return h ? ctx(h)->ncols : 0; }
+
+int elmk_set_tables(elmk_handle h, const elmk_tables* t) {
+  Ctx* c = ctx(h);
+  if (!c || !t) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (!(t->ltype == ISTSOIL || t->ltype == ISTCROP) || t->urbpoi || t->lakpoi) {
+    c->last_error = "only soil/crop land units without lake or urban points are on the hot path";
+    return ELMK_EUNSUPPORTED;
+  }
+  if (t->vtype < 0 || t->vtype >= ELMK_NUMPFT) return ELMK_EINVAL;
+  Tables T;
+  std::memset(&T, 0, sizeof(T));
+  T.ltype = t->ltype; T.ctype = t->ctype; T.vtype = t->vtype; T.urbpoi = t->urbpoi; T.lakpoi = t->lakpoi;
+  T.oldfflag = t->oldfflag; T.dewmx = t->dewmx;
+  for (int v = 0; v < ELMK_NUMPFT; ++v) {
+    T.z0mr[v] = t->pft[27][v]; T.displar[v] = t->pft[28][v]; T.xl[v] = t->pft[29][v];
+    T.rhol[v][0] = t->pft[32][v]; T.rhol[v][1] = t->pft[33][v];
+    T.rhos[v][0] = t->pft[34][v]; T.rhos[v][1] = t->pft[35][v];
+    T.taul[v][0] = t->pft[36][v]; T.taul[v][1] = t->pft[37][v];
+    T.taus[v][0] = t->pft[38][v]; T.taus[v][1] = t->pft[39][v];
+  }
+  std::memcpy(T.albsat, t->albsat, sizeof(T.albsat));
+  std::memcpy(T.albdry, t->albdry, sizeof(T.albdry));
+  for (int s = 0; s < 6; ++s)
+    for (int k = 0; k < 3; ++k) std::memcpy(T.aer_band[s][k], t->snicar_band[s * 3 + k], sizeof(double) * NBND_SNW);
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < 3; ++k) std::memcpy(T.bc[s][k], t->snicar_bc[s * 3 + k], sizeof(double) * 10 * NBND_SNW);
+  std::memcpy(T.bcenh, t->bcenh, sizeof(T.bcenh));
+  const size_t snw_n = (size_t)NBND_SNW * ELMK_MIE_SNW, age_n = (size_t)11 * 31 * 8;
+  double* p = c->d_table_data;
+  for (int d = 0; d < 2; ++d)
+    for (int k = 0; k < 3; ++k) {
+      CU(cudaMemcpyAsync(p, t->snicar_snow[d * 3 + k], snw_n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      T.snw[d][k] = p;
+      p += snw_n;
+    }
+  for (int k = 0; k < 3; ++k) {
+    CU(cudaMemcpyAsync(p, t->snowage[k], age_n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    T.snowage[k] = p;
+    p += age_n;
+  }
+  CU(cudaMemcpyAsync(c->d_tables, &T, sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));   // T and the caller's arrays may go out of scope
+  c->tables_set = true;
+  return ELMK_OK;
+}
+
+int elmk_upload(elmk_handle h, int field, const void* host, int64_t col0, int64_t n, int layout) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  return move_field(c, field, const_cast<void*>(host), col0, n, layout, true);
+}
+int elmk_download(elmk_handle h, int field, void* host, int64_t col0, int64_t n, int layout) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (int rc = move_field(c, field, host, col0, n, layout, false)) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return ELMK_OK;
+}
+int elmk_upload_many(elmk_handle h, int nf, const int* fields, const void* const* hosts, int64_t col0, int64_t n,
+                     int layout) {
+  Ctx* c = ctx(h);
+  if (!c || nf < 0 || (nf && (!fields || !hosts))) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  for (int i = 0; i < nf; ++i)
+    if (int rc = move_field(c, fields[i], const_cast<void*>(hosts[i]), col0, n, layout, true)) return rc;
+  return ELMK_OK;
+}
+int elmk_download_many(elmk_handle h, int nf, const int* fields, void* const* hosts, int64_t col0, int64_t n,
+                       int layout) {
+  Ctx* c = ctx(h);
+  if (!c || nf < 0 || (nf && (!fields || !hosts))) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  for (int i = 0; i < nf; ++i)
+    if (int rc = move_field(c, fields[i], hosts[i], col0, n, layout, false)) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return ELMK_OK;
+}
+
+int elmk_fill(elmk_handle h, int field, double value) {
+  Ctx* c = ctx(h);
+  if (!c || field < 0 || field >= kNumFields) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  const long long count = (long long)c->np * kSpecs[field].nlev;
+  const unsigned grid = (unsigned)std::min<long long>((count + 255) / 256, 148 * 16);
+  if (kSpecs[field].dtype == ELMK_F64) k_fill<double><<<grid, 256, 0, c->stream>>>((double*)c->base[field], count, value);
+  else if (kSpecs[field].dtype == ELMK_I32) k_fill<int><<<grid, 256, 0, c->stream>>>((int*)c->base[field], count, (int)value);
+  else k_fill<unsigned char><<<grid, 256, 0, c->stream>>>((unsigned char*)c->base[field], count, (unsigned char)(value != 0.0));
+  c->launches += 1;
+  CU(cudaGetLastError());
+  return ELMK_OK;
+}
+
+int elmk_init_timestep(elmk_handle h, int reset_forc_hgt) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (!c->tables_set) return ELMK_ENOTABLES;
+  const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
+  {
+    TimedScope ts(c, "init_timestep", 0u);
+    k_init_timestep<<<grid, kBlock, 0, c->stream>>>(c->cols, c->d_tables, reset_forc_hgt);
+  }
+  c->launches += 1;
+  CU(cudaGetLastError());
+  return ELMK_OK;
+}
+
+int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_t mask) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (!c->tables_set) {
+    c->last_error = "elmk_step before elmk_set_tables";
+    return ELMK_ENOTABLES;
+  }
+  mask &= ELMK_G_ALL;
+  const StepArgs A{dtime, dayl, max_dayl};
+  const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
+  // cover the requested groups, in chain order, with the launches of the plan; a launch whose group
+  // set is only partly requested falls back to one launch per requested group
+  for (int i = 0; i < c->plan_len; ++i) {
+    const Launch& L = c->plan[i];
+    const uint32_t want = L.mask & mask;
+    if (!want) continue;
+    if (want == L.mask) {
+      TimedScope ts(c, L.name, L.mask);
+      L.fn<<<grid, kBlock, 0, c->stream>>>(c->cols, c->d_tables, A);
+      c->launches += 1;
+    } else {
+      for (const Launch& G : kSplit) {
+        if (G.mask & want) {
+          TimedScope ts(c, G.name, G.mask);
+          G.fn<<<grid, kBlock, 0, c->stream>>>(c->cols, c->d_tables, A);
+          c->launches += 1;
+        }
+      }
+    }
+    if (c->timed.size() > 4096) {
+      if (int rc = drain_timing(c)) return rc;
+    }
+  }
+  CU(cudaGetLastError());
+  return ELMK_OK;
+}
+
+int elmk_sync(elmk_handle h) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return ELMK_OK;
+}
+int64_t elmk_launch_count(elmk_handle h) { return h ? ctx(h)->launches : 0; }
+
+int elmk_timing_enable(elmk_handle h, int on) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (int rc = drain_timing(c)) return rc;
+  c->acc.clear();
+  c->timing = on != 0;
+  return ELMK_OK;
+}
+int elmk_timing_read(elmk_handle h, int max, const char** names, double* total_ms, int64_t* launches,
+                     uint32_t* group_masks) {
+  Ctx* c = ctx(h);
+  if (!c || max < 0) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (int rc = drain_timing(c)) return rc;
+  const int n = std::min<int>(max, (int)c->acc.size());
+  for (int i = 0; i < n; ++i) {
+    if (names) names[i] = c->acc[i].name;
+    if (total_ms) total_ms[i] = c->acc[i].ms;
+    if (launches) launches[i] = c->acc[i].n;
+    if (group_masks) group_masks[i] = c->acc[i].mask;
+  }
+  return (int)c->acc.size();
+}
+
+int elmk_errors(elmk_handle h, uint32_t* any, int64_t* first_col) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  struct { unsigned int any; unsigned int pad; long long first; } init = {0u, 0u, 0x7fffffffffffffffLL}, *res;
+  res = static_cast<decltype(res)>(c->h_pinned);
+  *res = init;
+  CU(cudaMemcpyAsync(c->d_err, res, 16, cudaMemcpyHostToDevice, c->stream));
+  const unsigned grid = (unsigned)std::min<int64_t>((c->ncols + 255) / 256, 148 * 8);
+  k_errors<<<grid, 256, 0, c->stream>>>(c->cols.errmask, (int)c->ncols, c->d_err, reinterpret_cast<long long*>(c->d_err + 2));
+  c->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(res, c->d_err, 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (any) *any = res->any;
+  if (first_col) *first_col = res->any ? res->first : -1;
+  return ELMK_OK;
+}
+int elmk_clear_errors(elmk_handle h) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  CU(cudaMemsetAsync(c->cols.errmask, 0, (size_t)c->np * sizeof(int), c->stream));
+  return ELMK_OK;
+}
+const char* elmk_error_text(uint32_t bit) {
+  switch (bit) {
+    case ELMK_ERR_CANOPY_LAYER: return "ELM ERROR: multi-layer canopy not implemented";
+    case ELMK_ERR_SNICAR_RADIUS: return "ELM ERROR: SNICAR snow grain radius out of bounds";
+    case ELMK_ERR_SNICAR_NEGABS: return "ELM ERROR: SNICAR negative absoption";
+    case ELMK_ERR_SNICAR_ENERGY: return "ELM ERROR: SNICAR Energy conservation error";
+    case ELMK_ERR_SNICAR_ALBEDO: return "ELM ERROR: SNICAR Albedo > 1.0";
+    case ELMK_ERR_SABG_LAYERS: return "surface_radiation: absorbed solar radiation of the snow layers does not sum to sabg_snow";
+    case ELMK_ERR_FORC_HEIGHT: return "canopy_fluxes: forcing height is below the canopy displacement height";
+    case ELMK_ERR_QUADRATIC: return "ELM ERROR: quadratic solution a == 0";
+    case ELMK_ERR_BRENT_BRACKET: return "ELM ERROR: root must be bracketed for brent";
+    case ELMK_ERR_NEG_STOMATAL: return "ELM ERROR: Negative stomatal conductance";
+    case ELMK_ERR_SNOWAGE_DR: return "ELM ERROR: SnowAge dr_fresh < 0.0.";
+    case ELMK_ERR_DIVIDE_RADIUS: return "ELM ERROR: snow radius out of bounds in snow::divide_layers.";
+    default: return "unknown error bit";
+  }
+}
+
+int elmk_diag_reduce(elmk_handle h, double out[24]) {
+  Ctx* c = ctx(h);
+  if (!c || !out) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  k_diag<<<dim3(kDiagSlices, 8), 256, 0, c->stream>>>(c->cols, c->d_diag);
+  c->launches += 1;
+  CU(cudaGetLastError());
+  double* hp = static_cast<double*>(c->h_pinned);
+  CU(cudaMemcpyAsync(hp, c->d_diag, sizeof(double) * 8 * kDiagSlices * 3, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 8; ++k) {
+    double s = 0.0, lo = INFINITY, hi = -INFINITY;
+    for (int b = 0; b < kDiagSlices; ++b) {
+      const double* p = hp + ((size_t)k * kDiagSlices + b) * 3;
+      s += p[0];
+      lo = std::min(lo, p[1]);
+      hi = std::max(hi, p[2]);
+    }
+    out[k] = s; out[8 + k] = lo; out[16 + k] = hi;
+  }
+  return ELMK_OK;
+}
+
+int elmk_device_ptr(elmk_handle h, int field, void** ptr, int64_t* level_stride) {
+  Ctx* c = ctx(h);
+  if (!c || field < 0 || field >= kNumFields) return ELMK_EINVAL;
+  if (ptr) *ptr = c->base[field];
+  if (level_stride) *level_stride = c->np;
+  return ELMK_OK;
+}
+
+int elmk_stream(elmk_handle h, void** stream) {
+  Ctx* c = ctx(h);
+  if (!c || !stream) return ELMK_EINVAL;
+  *stream = static_cast<void*>(c->stream);
+  return ELMK_OK;
+}
+
+} // extern "C"

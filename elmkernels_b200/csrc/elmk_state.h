@@ -1,0 +1,53 @@
+// elmk_state.h - the column state as the kernels see it.
+//
+// Layout in HBM: structure of arrays, COLUMN INNERMOST.  A field with nlev elements per column
+// is stored as base[lev * np + col], np = padded column count.  Thirty-two consecutive threads of a
+// warp (32 consecutive columns) therefore read one level of a field as one contiguous 256-byte
+// segment, whatever the number of levels - the transpose of the reference's host layout
+// d_[lev + col*nlev] (reference src/utils/array.hh:176-183), which would make every warp load a
+// stride-nlev gather.
+#pragma once
+#include "elmk_common.h"
+
+namespace elmk {
+
+typedef double elmk_F64;
+typedef int elmk_I32;
+typedef unsigned char elmk_U8;
+
+// one pointer per field of include/elmk_fields.def
+struct Cols {
+  long long np;   // distance (in elements) between consecutive levels of a field
+  int ncols;      // number of valid columns
+  int pad_;
+#define ELMK_FIELD(name, type, nlev, cls) elmk_##type* name;
+#include "../../include/elmk_fields.def"
+#undef ELMK_FIELD
+};
+
+// global tables (device copies of struct elmk_tables, include/elmk_b200.h)
+struct Tables {
+  int ltype, ctype, vtype, urbpoi, lakpoi, oldfflag;
+  double dewmx;
+  // PFT constants used on the path (pft_data.h:38-77)
+  double z0mr[17], displar[17];
+  double xl[17], rhol[17][2], rhos[17][2], taul[17][2], taus[17][2];
+  double albsat[20][2], albdry[20][2];
+  // SNICAR optics (snicar_data.h:40-70)
+  double aer_band[6][3][NBND_SNW];       // [oc1,oc2,dst1..dst4][ss_alb,asm_prm,ext_cff_mss][band]
+  double bc[2][3][10][NBND_SNW];         // [bc1,bc2][ss_alb,asm_prm,ext_cff_mss][nclrds][band]
+  double bcenh[8][10][NBND_SNW];
+  const double* snw[2][3];               // [drc,dfs][ss_alb,asm_prm,ext_cff_mss] -> [band][1471] in HBM
+  const double* snowage[3];              // tau, kappa, drdt0 -> [11][31][8] in HBM
+};
+
+// per-step scalars
+struct StepArgs {
+  double dtime, dayl, max_dayl;
+};
+
+// field accessors used by the physics bodies: S is a `const Cols&`, c the column index
+#define C1(field) S.field[c]
+#define C2(field, lev) S.field[(long long)(lev) * S.np + c]
+
+} // namespace elmk

@@ -1,0 +1,655 @@
+// phys_canflux.h - canopy fluxes group (a7): root-zone moisture stress, the leaf-temperature Newton
+// iteration coupled to Monin-Obukhov stability and to sunlit/shaded Farquhar-Collatz photosynthesis
+// with Ball-Berry stomatal conductance (secant -> Brent root find on ci), canopy and ground fluxes.
+//
+// Parity target: kokkos_canopy_fluxes, reference
+// driver/kokkos/canopy_fluxes_kokkos.cc:6-265 ->
+//   canopy_fluxes::initialize_flux :95, stability_iteration :187, compute_flux :456
+//                                                        (src/physics/canopy_fluxes_impl.hh)
+//   photosynthesis::photosynthesis :9, hybrid :517, brent :396, ci_func :308, quadratic :286,
+//   ft :623, fth :628, fth25 :633                        (src/physics/photosynthesis_impl.hh)
+//   soil_moist_stress::calc_effective_soilporosity :62, calc_volumetric_h2oliq :77,
+//   calc_root_moist_stress :89                           (src/physics/soil_moist_stress_impl.hh)
+// The branch structure of the solvers is kept identical: the order of comparisons decides which
+// iterate is returned, hence the bits of every downstream flux.  The 30 scratch Views of the wrapper
+// (:11-40) are registers.
+#pragma once
+#include "elmk_state.h"
+#include "phys_bareground.h"
+#include "phys_cantemp.h"
+#include "phys_friction.h"
+
+namespace elmk {
+
+// per-PFT photosynthesis constants of one column (the reference's struct PFTDataPSN, pft_data.h:20-24)
+struct PsnPft {
+  double fnr, act25, kcha, koha, cpha, vcmaxha, jmaxha, tpuha, lmrha;
+  double vcmaxhd, jmaxhd, tpuhd, lmrhd, lmrse, qe, theta_cj, bbbopt, mbbopt;
+  double c3psn, slatop, leafcn, flnr, fnitr, dleaf, smpso, smpsc, tc_stress;
+};
+
+ELMK_HD PsnPft load_psn_pft(const Cols& S, const int c)
+{
+  PsnPft p;
+  p.fnr = C2(psn_pft, 0); p.act25 = C2(psn_pft, 1); p.kcha = C2(psn_pft, 2); p.koha = C2(psn_pft, 3);
+  p.cpha = C2(psn_pft, 4); p.vcmaxha = C2(psn_pft, 5); p.jmaxha = C2(psn_pft, 6); p.tpuha = C2(psn_pft, 7);
+  p.lmrha = C2(psn_pft, 8); p.vcmaxhd = C2(psn_pft, 9); p.jmaxhd = C2(psn_pft, 10); p.tpuhd = C2(psn_pft, 11);
+  p.lmrhd = C2(psn_pft, 12); p.lmrse = C2(psn_pft, 13); p.qe = C2(psn_pft, 14); p.theta_cj = C2(psn_pft, 15);
+  p.bbbopt = C2(psn_pft, 16); p.mbbopt = C2(psn_pft, 17); p.c3psn = C2(psn_pft, 18); p.slatop = C2(psn_pft, 19);
+  p.leafcn = C2(psn_pft, 20); p.flnr = C2(psn_pft, 21); p.fnitr = C2(psn_pft, 22); p.dleaf = C2(psn_pft, 23);
+  p.smpso = C2(psn_pft, 24); p.smpsc = C2(psn_pft, 25); p.tc_stress = C2(psn_pft, 26);
+  return p;
+}
+
+// ---- photosynthesis -------------------------------------------------------------------------
+
+// temperature response functions
+ELMK_HD double psn_ft(const double tl, const double ha)
+{
+  return exp(ha / (RGAS * 1.0e-3 * (TFRZ + 25.0)) * (1.0 - (TFRZ + 25.0) / tl));
+}
+ELMK_HD double psn_fth(const double tl, const double hd, const double se, const double scale)
+{
+  return scale / (1.0 + exp((-hd + se * tl) / (RGAS * 1.0e-3 * tl)));
+}
+ELMK_HD double psn_fth25(const double hd, const double se)
+{
+  return 1.0 + exp((-hd + se * (TFRZ + 25.0)) / (RGAS * 1.0e-3 * (TFRZ + 25.0)));
+}
+
+// roots of a x^2 + b x + c, numerically stable form; a == 0 is an error in the reference
+ELMK_HD void psn_quadratic(const double a, const double b, const double cc, double& r1, double& r2, uint32_t& err)
+{
+  if (a == 0.0) err |= ERR_QUADRATIC;
+  double q;
+  if (b >= 0.0) {
+    q = -0.5 * (b + sqrt(b * b - 4.0 * a * cc));
+  } else {
+    q = -0.5 * (b - sqrt(b * b - 4.0 * a * cc));
+  }
+  r1 = q / a;
+  if (q != 0.0) {
+    r2 = cc / q;
+  } else {
+    r2 = 1.0e36;
+  }
+}
+
+// everything ci_func needs besides ci; gs_mol and the assimilation rates are its side outputs
+struct LeafPsn {
+  // inputs
+  double gb_mol, je, cair, oair, lmr, par, rh_can, vcmax, pbot, cp, kc, ko, qe, tpu, kp, theta_cj, bbb, mbb;
+  bool c3;
+  // outputs of the last evaluation
+  double gs_mol, ac, aj, ap, ag, an;
+};
+
+// f(ci) = ci - (ca - (1.4/gb + 1.6/gs) p an)
+ELMK_HD double psn_ci_func(const double ci, LeafPsn& L, uint32_t& err)
+{
+  constexpr double theta_ip = 0.95;
+  if (L.c3) {
+    L.ac = L.vcmax * dmax(ci - L.cp, 0.0) / (ci + L.kc * (1.0 + L.oair / L.ko));
+    L.aj = L.je * dmax(ci - L.cp, 0.0) / (4.0 * ci + 8.0 * L.cp);
+    L.ap = 3.0 * L.tpu;
+  } else {
+    L.ac = L.vcmax;
+    L.aj = L.qe * L.par * 4.6;
+    L.ap = L.kp * dmax(ci, 0.0) / L.pbot;
+  }
+  double r1, r2;
+  psn_quadratic(L.theta_cj, -(L.ac + L.aj), L.ac * L.aj, r1, r2, err);
+  const double ai = dmin(r1, r2);
+  psn_quadratic(theta_ip, -(ai + L.ap), ai * L.ap, r1, r2, err);
+  L.ag = dmin(r1, r2);
+  L.an = L.ag - L.lmr;
+  if (L.an < 0.0) return 0.0;
+  double cs = L.cair - 1.4 / L.gb_mol * L.an * L.pbot;
+  cs = dmax(cs, 1.e-6);
+  const double aquad = cs;
+  const double bquad = cs * (L.gb_mol - L.bbb) - L.mbb * L.an * L.pbot;
+  const double cquad = -L.gb_mol * (cs * L.bbb + L.mbb * L.an * L.pbot * L.rh_can);
+  psn_quadratic(aquad, bquad, cquad, r1, r2, err);
+  L.gs_mol = dmax(r1, r2);
+  return ci - L.cair + L.an * L.pbot * (1.4 * L.gs_mol + 1.6 * L.gb_mol) / (L.gb_mol * L.gs_mol);
+}
+
+// Brent's method on [x1, x2] (Numerical Recipes form used by the reference)
+ELMK_HD double psn_brent(const double x1, const double x2, const double f1, const double f2, const double tol,
+                         LeafPsn& L, uint32_t& err)
+{
+  constexpr int ITMAX = 20;
+  constexpr double EPS = 1.0e-2;
+  double a = x1, b = x2, fa = f1, fb = f2;
+  if ((fa > 0.0 && fb > 0.0) || (fa < 0.0 && fb < 0.0)) err |= ERR_BRENT_BRACKET;
+  double cc = b, fc = fb;
+  double d = 0.0, e = 0.0;
+  int iter = 0;
+  while (iter != ITMAX) {
+    iter += 1;
+    if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) {
+      cc = a;
+      fc = fa;
+      d = b - a;
+      e = d;
+    }
+    if (fabs(fc) < fabs(fb)) {
+      a = b;
+      b = cc;
+      cc = a;
+      fa = fb;
+      fb = fc;
+      fc = fa;
+    }
+    const double tol1 = 2.0 * EPS * fabs(b) + 0.5 * tol;
+    const double xm = 0.5 * (cc - b);
+    if (fabs(xm) <= tol1 || fb == 0.0) return b;
+    if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
+      const double s = fb / fa;
+      double p, q;
+      if (a == cc) {
+        p = 2.0 * xm * s;
+        q = 1.0 - s;
+      } else {
+        q = fa / fc;
+        const double r = fb / fc;
+        p = s * (2.0 * xm * q * (q - r) - (b - a) * (r - 1.0));
+        q = (q - 1.0) * (r - 1.0) * (s - 1.0);
+      }
+      if (p > 0.0) q *= -1.0;
+      p = fabs(p);
+      if (2.0 * p < dmin(3.0 * xm * q - fabs(tol1 * q), fabs(e * q))) {
+        e = d;
+        d = p / q;
+      } else {
+        d = xm;
+        e = d;
+      }
+    } else {
+      d = xm;
+      e = d;
+    }
+    a = b;
+    fa = fb;
+    if (fabs(d) > tol1) {
+      b = b + d;
+    } else {
+      b = b + copysign(tol1, xm);
+    }
+    fb = psn_ci_func(b, L, err);
+    if (fb == 0.0) break;
+  }
+  return b;
+}
+
+// secant search for a sign change, Brent once bracketed; leaves the side outputs of the last
+// ci_func evaluation in L
+ELMK_HD void psn_hybrid(double x0, LeafPsn& L, uint32_t& err)
+{
+  constexpr double eps = 1.0e-2;
+  constexpr double eps1 = 1.0e-4;
+  constexpr int itmax = 40;
+  double f0 = psn_ci_func(x0, L, err);
+  if (f0 == 0.0) return;
+  double minx = x0, minf = f0;
+  double x1 = x0 * 0.99;
+  double f1 = psn_ci_func(x1, L, err);
+  if (f1 == 0.0) return;
+  if (f1 < minf) {
+    minx = x1;
+    minf = f1;
+  }
+  int iter = 0;
+  while (true) {
+    iter += 1;
+    const double dx = -f1 * (x1 - x0) / (f1 - f0);
+    const double x = x1 + dx;
+    const double tol = fabs(x) * eps;
+    if (fabs(dx) < tol) break;
+    x0 = x1;
+    f0 = f1;
+    x1 = x;
+    f1 = psn_ci_func(x1, L, err);
+    if (f1 < minf) {
+      minx = x1;
+      minf = f1;
+    }
+    if (fabs(f1) <= eps1) break;
+    if (f1 * f0 < 0.0) {
+      psn_brent(x0, x1, f0, f1, tol, L, err);
+      break;
+    }
+    if (iter > itmax) {
+      // not converged: fall back to the evaluation with the smallest residual
+      f1 = psn_ci_func(minx, L, err);
+      break;
+    }
+  }
+}
+
+// stomatal resistance of the sunlit or the shaded canopy fraction (nlevcan == 1, nrad == 1)
+ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const int nrad, const double pbot, const double t_veg,
+                                       const double t10, const double esat_tv, const double eair, const double oair,
+                                       const double cair, const double rb, const double btran,
+                                       const double dayl_factor, const double thm, const double vcmaxcint,
+                                       const double par, const double lai, uint32_t& err)
+{
+  constexpr double fnps = 0.15;
+  constexpr double theta_psii = 0.7;
+  constexpr double sco = 0.5 * 0.209 / (42.75 / 1.e06);
+  const bool c3 = (round(P.c3psn) == 1);   // anything else is treated as C4, as in the reference (:22-27)
+  if (nrad < 1) return 0.0;
+
+  const double lnc = 1.0 / (P.slatop * P.leafcn);
+  const double act25 = P.act25 * 1000.0 / 60.0;
+  double vcmax25top = lnc * P.flnr * P.fnr * act25 * dayl_factor;
+  vcmax25top *= P.fnitr;
+  const double t10c = dmin(dmax((t10 - TFRZ), 11.0), 35.0);
+  const double jmax25top = (2.59 - 0.035 * t10c) * vcmax25top;
+  const double tpu25top = 0.167 * vcmax25top;
+  const double kp25top = 20000.0 * vcmax25top;
+  const double lmr25top = c3 ? vcmax25top * 0.015 : vcmax25top * 0.025;
+  const double nscaler = vcmaxcint;
+
+  // leaf maintenance respiration (always) and the carboxylation capacities (daytime only)
+  double lmr_z;
+  const double lmr25 = lmr25top * nscaler;
+  if (c3) {
+    const double lmrc = psn_fth25(P.lmrhd, P.lmrse);
+    lmr_z = lmr25 * psn_ft(t_veg, P.lmrha) * psn_fth(t_veg, P.lmrhd, P.lmrse, lmrc);
+  } else {
+    lmr_z = lmr25 * pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
+    lmr_z /= (1.0 + exp(1.3 * (t_veg - (TFRZ + 55.0))));
+  }
+  double vcmax_z, jmax_z, tpu_z, kp_z;
+  if (par <= 0.0) {
+    vcmax_z = 0.0; jmax_z = 0.0; tpu_z = 0.0; kp_z = 0.0;
+  } else {
+    const double vcmax25 = vcmax25top * nscaler;
+    const double jmax25 = jmax25top * nscaler;
+    const double tpu25 = tpu25top * nscaler;
+    const double kp25 = kp25top * nscaler;
+    const double vcmaxse = 668.39 - 1.07 * t10c;
+    const double jmaxse = 659.70 - 0.75 * t10c;
+    const double tpuse = vcmaxse;
+    const double vcmaxc = psn_fth25(P.vcmaxhd, vcmaxse);
+    const double jmaxc = psn_fth25(P.jmaxhd, jmaxse);
+    const double tpuc = psn_fth25(P.tpuhd, tpuse);
+    vcmax_z = vcmax25 * psn_ft(t_veg, P.vcmaxha) * psn_fth(t_veg, P.vcmaxhd, vcmaxse, vcmaxc);
+    jmax_z = jmax25 * psn_ft(t_veg, P.jmaxha) * psn_fth(t_veg, P.jmaxhd, jmaxse, jmaxc);
+    tpu_z = tpu25 * psn_ft(t_veg, P.tpuha) * psn_fth(t_veg, P.tpuhd, tpuse, tpuc);
+    if (!c3) {
+      vcmax_z = vcmax25 * pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
+      vcmax_z /= (1.0 + exp(0.2 * ((TFRZ + 15.0) - t_veg)));
+      vcmax_z /= (1.0 + exp(0.3 * (t_veg - (TFRZ + 40.0))));
+    }
+    kp_z = kp25 * pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
+  }
+  vcmax_z *= btran;
+  lmr_z *= btran;
+
+  const double cf = pbot / (RGAS * 1.0e-3 * thm) * 1.e06;
+  const double gb = 1.0 / rb;
+  const double gb_mol = gb * cf;
+  const double bbb = dmax(P.bbbopt * btran, 1.0);
+  constexpr double rsmax0 = 2.0e4;
+  const double kc25 = (404.9 / 1.e06) * pbot;
+  const double ko25 = (278.4 / 1.e03) * pbot;
+  const double cp25 = 0.5 * oair / sco;
+  const double kc = kc25 * psn_ft(t_veg, P.kcha);
+  const double ko = ko25 * psn_ft(t_veg, P.koha);
+  const double cp = cp25 * psn_ft(t_veg, P.cpha);
+
+  double rs_z;
+  if (par <= 0.0) {
+    rs_z = dmin(rsmax0, 1.0 / bbb * cf);
+  } else {
+    const double ceair = dmin(eair, esat_tv);
+    const double rh_can = ceair / esat_tv;
+    const double qabs = 0.5 * (1.0 - fnps) * par * 4.6;
+    double r1, r2;
+    psn_quadratic(theta_psii, -(qabs + jmax_z), qabs * jmax_z, r1, r2, err);
+    LeafPsn L;
+    L.gb_mol = gb_mol; L.je = dmin(r1, r2); L.cair = cair; L.oair = oair; L.lmr = lmr_z; L.par = par;
+    L.rh_can = rh_can; L.vcmax = vcmax_z; L.pbot = pbot; L.cp = cp; L.kc = kc; L.ko = ko; L.qe = P.qe;
+    L.tpu = tpu_z; L.kp = kp_z; L.theta_cj = P.theta_cj; L.bbb = bbb; L.mbb = P.mbbopt; L.c3 = c3;
+    L.gs_mol = 0.0; L.ac = 0.0; L.aj = 0.0; L.ap = 0.0; L.ag = 0.0; L.an = 0.0;
+    // every call restarts from the atmospheric CO2 guess: iterations do not inherit the previous root
+    psn_hybrid(c3 ? 0.7 * cair : 0.4 * cair, L, err);
+    if (L.an < 0.0) L.gs_mol = bbb;
+    const double gs = L.gs_mol / cf;
+    rs_z = dmin(1.0 / gs, rsmax0);
+    if (L.gs_mol < 0.0) err |= ERR_NEG_STOMATAL;
+  }
+  // canopy integration over the single layer
+  const double gscan = lai / (rb + rs_z);
+  const double laican = lai;
+  return (laican > 0.0) ? laican / gscan - rb : 0.0;
+}
+
+// ---- canopy fluxes --------------------------------------------------------------------------
+
+ELMK_HD void column_canopy_fluxes(const Cols& S, const Tables& T, const StepArgs& A, const int c)
+{
+  // canopy_fluxes::compute_flux zeroes these for every column (:475-480) - including the bare
+  // columns whose values kokkos_bareground_fluxes has just computed
+  C1(cgrnd) = 0.0;
+  C1(cgrnds) = 0.0;
+  C1(cgrndl) = 0.0;
+
+  const int veg = C1(frac_veg_nosno);
+  const double forc_t = C1(forc_tbot);
+  if (veg == 0) {
+    // initialize_flux for non-vegetated columns (:121-131)
+    C1(btran) = 0.0;
+    C1(t_veg) = forc_t;
+#pragma unroll
+    for (int i = 0; i < NLEVGRND; ++i) C2(rootr, i) = 0.0;
+    return;
+  }
+
+  uint32_t err = 0;
+  const double dtime = A.dtime;
+  const PsnPft P = load_psn_pft(S, c);
+  const int snl = C1(snl);
+  const double pbot = C1(forc_pbot), forc_q = C1(forc_qbot), forc_th = C1(forc_thbot);
+  const double forc_lwrad = C1(forc_lwrad);
+  const double thm = C1(thm), thv = C1(thv), tg = C1(t_grnd), qg = C1(qg);
+  const double elai = C1(elai), esai = C1(esai), emv = C1(emv), emg = C1(emg);
+  const double z0mg = C1(z0mg);
+  const double hgt_u = C1(forc_hgt_u_patch), hgt_t = C1(forc_hgt_t_patch), hgt_q = C1(forc_hgt_q_patch);
+  const double forc_po2 = O2_MOLAR_CONST * pbot;
+  const double forc_pco2 = CO2_PPMV * 1.0e-6 * pbot;
+  const double forc_rho = air_density(pbot, forc_q, forc_t);
+
+  // ---- initialize_flux (:133-181) ----
+  const double dayl_factor = dmin(1.0, dmax(0.01, (A.dayl * A.dayl) / (A.max_dayl * A.max_dayl)));
+  // root-zone moisture stress: effective porosity, liquid volume, per-layer resistance
+  double btran = 0.0;
+  double rootr[NLEVGRND];
+#pragma unroll
+  for (int i = 0; i < NLEVGRND; ++i) {
+    const int k = NLEVSNO + i;
+    const double watsat = C2(watsat, i), dzk = C2(dz, k);
+    const double vol_ice = dmin(watsat, (C2(h2osoi_ice, k) / (DENICE * dzk)));
+    const double eff_por = watsat - vol_ice;
+    C2(eff_porosity, i) = eff_por;
+    const double liqvol = dmin(eff_por, (C2(h2osoi_liq, k) / (dzk * DENH2O)));
+    if (liqvol <= 0.0 || C2(t_soisno, k) <= TFRZ + P.tc_stress) {
+      rootr[i] = 0.0;
+    } else {
+      const double s_node = dmax(liqvol / eff_por, 0.01);
+      double smp_node = -C2(sucsat, i) * pow(s_node, (-C2(bsw, i)));
+      smp_node = dmax(P.smpsc, smp_node);
+      const double rresis = dmin((eff_por / watsat) * (smp_node - P.smpsc) / (P.smpso - P.smpsc), 1.0);
+      rootr[i] = C2(rootfr, i) * rresis;
+      btran += dmax(rootr[i], 0.0);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NLEVGRND; ++i) {
+    if (btran > 0.0) rootr[i] /= btran; else rootr[i] = 0.0;
+    C2(rootr, i) = rootr[i];
+  }
+
+  // sparse/dense canopy aerodynamic parameters
+  double displa = C1(displa), z0mv = C1(z0mv);
+  const double lt = dmin(elai + esai, 2.0);
+  const double egvf = (1.0 - exp(-lt)) / (1.0 - exp(-2.0));
+  displa *= egvf;
+  z0mv = exp(egvf * log(z0mv) + (1.0 - egvf) * log(z0mg));
+  const double z0hv = z0mv, z0qv = z0mv;
+  C1(displa) = displa;
+  C1(z0mv) = z0mv;
+  C1(z0hv) = z0hv;
+  C1(z0qv) = z0qv;
+
+  // net absorbed longwave coefficients
+  const double air = emv * (1.0 + (1.0 - emv) * (1.0 - emg)) * forc_lwrad;
+  const double bir = -(2.0 - emv * (1.0 - emg)) * emv * STEBOL;
+  const double cir = emv * emg * STEBOL;
+
+  double t_veg = C1(t_veg);
+  double el, deldT, qsatl, qsatldT;
+  qsat(t_veg, pbot, el, deldT, qsatl, qsatldT);
+  double taf = (tg + thm) / 2.0;
+  double qaf = (forc_q + qg) / 2.0;
+  const double fu = C1(forc_u), fv = C1(forc_v);
+  const double ur = dmax(1.0, sqrt(fu * fu + fv * fv));
+  double dth = thm - taf;
+  double dqh = forc_q - qaf;
+  double delq = qg - qaf;
+  const double dthv = dth * (1.0 + 0.61 * forc_q) + 0.61 * forc_th * dqh;
+  const double zldis = hgt_u - displa;
+  if (!(zldis >= 0.0)) err |= ERR_FORC_HEIGHT;
+  double um, obu;
+  mo_initial_length(ur, thv, dthv, zldis, z0mv, um, obu);
+
+  // ---- stability_iteration (:215-451) ----
+  const double fwet = C1(fwet), fdry = C1(fdry), laisun = C1(laisun), laisha = C1(laisha);
+  const double snow_depth = C1(snow_depth), soilbeta = C1(soilbeta);
+  const double fsno = C1(frac_sno), fsfc = C1(frac_h2osfc), t_sfc = C1(t_h2osfc);
+  const double sabv = C1(sabv), htop = C1(htop), t10 = C1(t10);
+  const double h2ocan0 = C1(h2ocan);
+  const int nrad = C1(nrad);
+  const double vcsha = C1(vcmaxcintsha), vcsun = C1(vcmaxcintsun);
+  const double parsha = C2(parsha_z, 0), parsun = C2(parsun_z, 0);
+  const double laisha_z = C2(laisha_z, 0), laisun_z = C2(laisun_z, 0);
+  const double t_snotop = C2(t_soisno, NLEVSNO - snl), t_soil1 = C2(t_soisno, NLEVSNO);
+  const bool soybean = (T.vtype == PFT_SOYBEAN || T.vtype == PFT_SOYBEAN_IRRIG);
+  // ground-emitted longwave does not change during the iteration
+  const double lw_grnd = (fsno * pow4(t_snotop) + (1.0 - fsno - fsfc) * pow4(t_soil1) + fsfc * pow4(t_sfc));
+
+  constexpr double ria = 0.5, dlemin = 0.1, dtmin = 0.01;
+  constexpr int itmax = 40, itmin = 2;
+  bool stop = false;
+  int itlef = 0, nmozsgn = 0;
+  double del = 0.0, efeb = 0.0, obuold = 0.0;
+  double qflx_tran_veg = C1(qflx_tran_veg), qflx_evap_veg = C1(qflx_evap_veg), eflx_sh_veg = C1(eflx_sh_veg);
+  double wtg = 0.0, wtl0 = 0.0, wta0 = 0.0, wtal = 0.0, wtgq = 0.0, wtalq = 0.0, wtlq0 = 0.0, wtaq0 = 0.0;
+  double tlbef = 0.0, dt_veg = 0.0;
+  MoProfiles p;
+  p.ustar = 0.0; p.temp1 = 0.0; p.temp2 = 0.0; p.temp12m = 0.0; p.temp22m = 0.0;
+
+#pragma unroll 1
+  while (itlef <= itmax && !stop) {
+    p = mo_profiles(hgt_u, hgt_t, hgt_q, displa, um, obu, z0mv, z0hv, z0qv);
+    tlbef = t_veg;
+    const double del2 = del;
+    const double ram = 1.0 / (p.ustar * p.ustar / um);
+    const double rah0 = 1.0 / (p.temp1 * p.ustar);
+    const double raw0 = 1.0 / (p.temp2 * p.ustar);
+    const double uaf = um * sqrt(1.0 / (ram * um));
+    const double cf = 0.01 / (sqrt(uaf) * sqrt(P.dleaf));
+    const double rb = 1.0 / (cf * uaf);
+    const double w = exp(-(elai + esai));
+    const double csoilb = (VKC / (0.13 * pow((z0mg * uaf / 1.5e-5), 0.45)));
+    const double ri = (GRAV * htop * (taf - tg)) / (taf * sq(uaf));
+    double csoilcn;
+    if ((taf - tg) > 0.0) {
+      const double ricsoilc = CSOILC / (1.0 + ria * dmin(ri, 10.0));
+      csoilcn = csoilb * w + ricsoilc * (1.0 - w);
+    } else {
+      csoilcn = csoilb * w + CSOILC * (1.0 - w);
+    }
+    const double rah1 = 1.0 / (csoilcn * uaf);
+    const double raw1 = rah1;
+    const double svpts = el;
+    const double eah = pbot * qaf / 0.622;
+
+    if (soybean) btran = dmin(1.0, btran * 1.25);
+    const double rssun = psn_stomatal_resistance(P, nrad, pbot, t_veg, t10, svpts, eah, forc_po2, forc_pco2, rb, btran,
+                                                 dayl_factor, thm, vcsun, parsun, laisun_z, err);
+    if (soybean) btran = dmin(1.0, btran * 1.25);
+    const double rssha = psn_stomatal_resistance(P, nrad, pbot, t_veg, t10, svpts, eah, forc_po2, forc_pco2, rb, btran,
+                                                 dayl_factor, thm, vcsha, parsha, laisha_z, err);
+
+    // sensible-heat conductances: air, leaf, ground
+    const double wta = 1.0 / rah0;
+    const double wtl = (elai + esai) / rb;
+    wtg = 1.0 / rah1;
+    const double wtshi = 1.0 / (wta + wtl + wtg);
+    wtl0 = wtl * wtshi;
+    const double wtg0 = wtg * wtshi;
+    wta0 = wta * wtshi;
+    const double wtga = wta0 + wtg0;
+    wtal = wta0 + wtl0;
+
+    // fraction of potential evaporation from the leaf
+    double rppdry;
+    if (fdry > 0.0) {
+      rppdry = fdry * rb * (laisun / (rb + rssun) + laisha / (rb + rssha)) / elai;
+    } else {
+      rppdry = 0.0;
+    }
+    double efpot = forc_rho * wtl * (qsatl - qaf);
+    double rpp;
+    if (efpot > 0.0) {
+      if (btran > 0.0) {
+        qflx_tran_veg = efpot * rppdry;
+        rpp = rppdry + fwet;
+      } else {
+        rpp = fwet;
+        qflx_tran_veg = 0.0;
+      }
+      rpp = dmin(rpp, (qflx_tran_veg + h2ocan0 / dtime) / efpot);
+    } else {
+      rpp = 1.0;
+      qflx_tran_veg = 0.0;
+    }
+
+    // latent-heat conductances, with the dry-litter layer resistance
+    const double wtaq = veg / raw0;
+    const double wtlq = veg * (elai + esai) / rb * rpp;
+    const double fsno_dl = snow_depth / 0.05;
+    const double elai_dl = 0.5 * (1.0 - dmin(fsno_dl, 1.0));
+    const double rdl = (1.0 - exp(-elai_dl)) / (0.004 * uaf);
+    if (delq < 0.0) {
+      wtgq = veg / (raw1 + rdl);
+    } else {
+      wtgq = soilbeta * veg / (raw1 + rdl);
+    }
+    const double wtsqi = 1.0 / (wtaq + wtlq + wtgq);
+    const double wtgq0 = wtgq * wtsqi;
+    wtlq0 = wtlq * wtsqi;
+    wtaq0 = wtaq * wtsqi;
+    const double wtgaq = wtaq0 + wtgq0;
+    wtalq = wtaq0 + wtlq0;
+    const double dc1 = forc_rho * CPAIR * wtl;
+    const double dc2 = HVAP * forc_rho * wtlq;
+    const double efsh = dc1 * (wtga * t_veg - wtg0 * tg - wta0 * thm);
+    double efe = dc2 * (wtgaq * qsatl - wtgq0 * qg - wtaq0 * forc_q);
+    double erre = 0.0;
+    if ((efe * efeb) < 0.0) {
+      const double efeold = efe;
+      efe = 0.1 * efeold;
+      erre = efe - efeold;
+    }
+
+    // leaf energy balance: Newton step on t_veg, limited to 1 K per iteration
+    dt_veg = (sabv + air + bir * pow4(t_veg) + cir * lw_grnd - efsh - efe) /
+             (-4.0 * bir * cube(t_veg) + dc1 * wtga + dc2 * wtgaq * qsatldT);
+    t_veg = tlbef + dt_veg;
+    const double dels = dt_veg;
+    del = fabs(dels);
+    double errb = 0.0;
+    if (del > 1.0) {
+      dt_veg = dels / del;
+      t_veg = tlbef + dt_veg;
+      errb = sabv + air + bir * cube(tlbef) * (tlbef + 4.0 * dt_veg) + cir * lw_grnd - (efsh + dc1 * wtga * dt_veg) -
+             (efe + dc2 * wtgaq * qsatldT * dt_veg);
+    }
+
+    // fluxes from leaves to canopy air
+    efpot = forc_rho * wtl * (wtgaq * (qsatl + qsatldT * dt_veg) - wtgq0 * qg - wtaq0 * forc_q);
+    qflx_evap_veg = rpp * efpot;
+    if (efpot > 0.0 && btran > 0.0) {
+      qflx_tran_veg = efpot * rppdry;
+    } else {
+      qflx_tran_veg = 0.0;
+    }
+    const double ecidif = dmax(0.0, qflx_evap_veg - qflx_tran_veg - h2ocan0 / dtime);
+    qflx_evap_veg = dmin(qflx_evap_veg, qflx_tran_veg + h2ocan0 / dtime);
+    eflx_sh_veg = efsh + dc1 * wtga * dt_veg + errb + erre + HVAP * ecidif;
+    qsat(t_veg, pbot, el, deldT, qsatl, qsatldT);
+
+    // canopy air state and Monin-Obukhov length for the next pass
+    taf = wtg0 * tg + wta0 * thm + wtl0 * t_veg;
+    qaf = wtlq0 * qsatl + wtgq0 * qg + forc_q * wtaq0;
+    dth = thm - taf;
+    dqh = forc_q - qaf;
+    delq = wtalq * qg - wtlq0 * qsatl - wtaq0 * forc_q;
+    const double tstar = p.temp1 * dth;
+    const double qstar = p.temp2 * dqh;
+    const double thvstar = tstar * (1.0 + 0.61 * forc_q) + 0.61 * forc_th * qstar;
+    double zeta = zldis * VKC * GRAV * thvstar / (sq(p.ustar) * thv);
+    if (zeta >= 0.0) {
+      zeta = dmin(2.0, dmax(zeta, 0.01));
+      um = dmax(ur, 0.1);
+    } else {
+      zeta = dmax(-100.0, dmin(zeta, -0.01));
+      const double wc = 1.0 * pow((-GRAV * p.ustar * thvstar * 1000.0 / thv), 0.333);
+      um = sqrt(ur * ur + wc * wc);
+    }
+    obu = zldis / zeta;
+    if (obuold * obu < 0.0) nmozsgn += 1;
+    if (nmozsgn >= 4) obu = zldis / (-0.01);
+    obuold = obu;
+
+    // convergence: at least three passes, leaf temperature within 0.01 K twice in a row and the
+    // latent heat flux within 0.1 W/m2
+    itlef += 1;
+    if (itlef > itmin) {
+      const double dele = fabs(efe - efeb);
+      efeb = efe;
+      const double det = dmax(del, del2);
+      if ((det < dtmin) && (dele < dlemin)) stop = true;
+    }
+  }
+
+  C1(btran) = btran;
+  C1(t_veg) = t_veg;
+  C1(qflx_tran_veg) = qflx_tran_veg;
+  C1(qflx_evap_veg) = qflx_evap_veg;
+  C1(eflx_sh_veg) = eflx_sh_veg;
+
+  // ---- compute_flux (:482-539) ----
+  const double htvp = C1(htvp);
+  const double delt = wtal * tg - wtl0 * t_veg - wta0 * thm;
+  C1(eflx_sh_grnd) = CPAIR * forc_rho * wtg * delt;
+  const double delt_snow = wtal * t_snotop - wtl0 * t_veg - wta0 * thm;
+  C1(eflx_sh_snow) = CPAIR * forc_rho * wtg * delt_snow;
+  const double delt_soil = wtal * t_soil1 - wtl0 * t_veg - wta0 * thm;
+  C1(eflx_sh_soil) = CPAIR * forc_rho * wtg * delt_soil;
+  const double delt_h2osfc = wtal * t_sfc - wtl0 * t_veg - wta0 * thm;
+  C1(eflx_sh_h2osfc) = CPAIR * forc_rho * wtg * delt_h2osfc;
+  C1(qflx_evap_soi) = forc_rho * wtgq * delq;
+  const double delq_snow = wtalq * C1(qg_snow) - wtlq0 * qsatl - wtaq0 * forc_q;
+  C1(qflx_ev_snow) = forc_rho * wtgq * delq_snow;
+  const double delq_soil = wtalq * C1(qg_soil) - wtlq0 * qsatl - wtaq0 * forc_q;
+  C1(qflx_ev_soil) = forc_rho * wtgq * delq_soil;
+  const double delq_h2osfc = wtalq * C1(qg_h2osfc) - wtlq0 * qsatl - wtaq0 * forc_q;
+  C1(qflx_ev_h2osfc) = forc_rho * wtgq * delq_h2osfc;
+  const double t_ref2m = thm + p.temp1 * dth * (1.0 / p.temp12m - 1.0 / p.temp1);
+  const double q_ref2m = forc_q + p.temp2 * dqh * (1.0 / p.temp22m - 1.0 / p.temp2);
+  double e2m, de2m, qsat2m, dqsat2m;
+  qsat(t_ref2m, pbot, e2m, de2m, qsat2m, dqsat2m);
+  C1(t_ref2m) = t_ref2m;
+  C1(q_ref2m) = q_ref2m;
+  C1(rh_ref2m) = dmin(100.0, (q_ref2m / qsat2m) * 100.0);
+  // (products kept in the reference's left-to-right association)
+  C1(dlrad) = (1.0 - emv) * emg * forc_lwrad + emv * emg * STEBOL * cube(tlbef) * (tlbef + 4.0 * dt_veg);
+  C1(ulrad) = ((1.0 - emg) * (1.0 - emv) * (1.0 - emv) * forc_lwrad +
+               emv * (1.0 + (1.0 - emg) * (1.0 - emv)) * STEBOL * cube(tlbef) * (tlbef + 4.0 * dt_veg) +
+               emg * (1.0 - emv) * STEBOL * lw_grnd);
+  double cgrnds = 0.0, cgrndl = 0.0;
+  cgrnds += CPAIR * forc_rho * wtg * wtal;
+  cgrndl += forc_rho * wtgq * wtalq * C1(dqgdT);
+  C1(cgrnds) = cgrnds;
+  C1(cgrndl) = cgrndl;
+  C1(cgrnd) = cgrnds + cgrndl * htvp;
+  C1(h2ocan) = dmax(0.0, h2ocan0 + (qflx_tran_veg - qflx_evap_veg) * dtime);
+  if (err) C1(errmask) |= (int)err;
+}
+
+} // namespace elmk

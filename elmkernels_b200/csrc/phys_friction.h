@@ -1,0 +1,104 @@
+// phys_friction.h - Monin-Obukhov surface-layer similarity (Zeng et al. 1998): friction velocity and
+// the temperature / humidity profile relations, shared by the bare-ground (a6) and canopy (a7) fluxes.
+//
+// Parity target: reference src/physics/friction_velocity_impl.hh:17-173
+//   StabilityFunc1 :17, StabilityFunc2 :26, monin_obukhov_length :35, friction_velocity_wind :62,
+//   friction_velocity_temp :84, friction_velocity_humidity :105, friction_velocity_temp2m :133,
+//   friction_velocity_humidity2m :152.
+// The literal exponent 0.333 (not 1/3) is the reference's.
+#pragma once
+#include "elmk_common.h"
+
+namespace elmk {
+
+ELMK_HD double mo_psi_m(const double zeta)   // wind-profile stability correction, unstable branch
+{
+  const double chik2 = sqrt(1.0 - 16.0 * zeta);
+  const double chik = sqrt(chik2);
+  return 2.0 * log((1.0 + chik) * 0.5) + log((1.0 + chik2) * 0.5) - 2.0 * atan(chik) + PI * 0.5;
+}
+
+ELMK_HD double mo_psi_h(const double zeta)   // scalar-profile stability correction, unstable branch
+{
+  const double chik2 = sqrt(1.0 - 16.0 * zeta);
+  return 2.0 * log((1.0 + chik2) * 0.5);
+}
+
+// initial Monin-Obukhov length and wind speed from the bulk Richardson number
+ELMK_HD void mo_initial_length(const double ur, const double thv, const double dthv, const double zldis,
+                               const double z0m, double& um, double& obu)
+{
+  constexpr double wc = 0.5;
+  if (dthv >= 0.0) {
+    um = dmax(ur, 0.1);
+  } else {
+    um = sqrt(ur * ur + wc * wc);
+  }
+  const double rib = GRAV * zldis * dthv / (thv * um * um);
+  double zeta;
+  if (rib >= 0.0) {
+    zeta = rib * log(zldis / z0m) / (1.0 - 5.0 * dmin(rib, 0.19));
+    zeta = dmin(2.0, dmax(zeta, 0.01));
+  } else {
+    zeta = rib * log(zldis / z0m);
+    zeta = dmax(-100.0, dmin(zeta, -0.01));
+  }
+  obu = zldis / zeta;
+}
+
+ELMK_HD double mo_ustar(const double forc_hgt_u, const double displa, const double um, const double obu,
+                        const double z0m)
+{
+  constexpr double zetam = 1.574;
+  const double zldis = forc_hgt_u - displa;
+  const double zeta = zldis / obu;
+  if (zeta < (-zetam)) {
+    return VKC * um / (log(-zetam * obu / z0m) - mo_psi_m(-zetam) + mo_psi_m(z0m / obu) +
+                       1.14 * (pow((-zeta), 0.333) - pow(zetam, 0.333)));
+  } else if (zeta < 0.0) {
+    return VKC * um / (log(zldis / z0m) - mo_psi_m(zeta) + mo_psi_m(z0m / obu));
+  } else if (zeta <= 1.0) {
+    return VKC * um / (log(zldis / z0m) + 5.0 * zeta - 5.0 * z0m / obu);
+  }
+  return VKC * um / (log(obu / z0m) + 5.0 - 5.0 * z0m / obu + (5.0 * log(zeta) + zeta - 1.0));
+}
+
+// scalar (temperature or humidity) profile relation for a reference height `zldis` above the
+// displacement height and roughness length z0
+// `grouped`: friction_velocity_temp2m writes the very-stable branch as 5 (z0/L) instead of (5 z0)/L
+// (:147), which can differ in the last bit; the other four callers use the ungrouped product.
+ELMK_HD double mo_scalar_profile(const double zldis, const double obu, const double z0, const bool grouped = false)
+{
+  constexpr double zetat = 0.465;
+  const double zeta = zldis / obu;
+  if (zeta < (-zetat)) {
+    return VKC / (log(-zetat * obu / z0) - mo_psi_h(-zetat) + mo_psi_h(z0 / obu) +
+                  0.8 * (pow(zetat, -0.333) - pow((-zeta), -0.333)));
+  } else if (zeta < 0.0) {
+    return VKC / (log(zldis / z0) - mo_psi_h(zeta) + mo_psi_h(z0 / obu));
+  } else if (zeta <= 1.0) {
+    return VKC / (log(zldis / z0) + 5.0 * zeta - 5.0 * z0 / obu);
+  }
+  const double stable = grouped ? 5.0 * (z0 / obu) : 5.0 * z0 / obu;
+  return VKC / (log(obu / z0) + 5.0 - stable + (5.0 * log(zeta) + zeta - 1.0));
+}
+
+// the five profile quantities of one stability iteration
+struct MoProfiles {
+  double ustar, temp1, temp2, temp12m, temp22m;
+};
+
+ELMK_HD MoProfiles mo_profiles(const double hgt_u, const double hgt_t, const double hgt_q, const double displa,
+                               const double um, const double obu, const double z0m, const double z0h,
+                               const double z0q)
+{
+  MoProfiles p;
+  p.ustar = mo_ustar(hgt_u, displa, um, obu, z0m);
+  p.temp1 = mo_scalar_profile(hgt_t - displa, obu, z0h);
+  p.temp2 = (hgt_q == hgt_t && z0q == z0h) ? p.temp1 : mo_scalar_profile(hgt_q - displa, obu, z0q);
+  p.temp12m = mo_scalar_profile(2.0 + z0h, obu, z0h, true);
+  p.temp22m = (z0q == z0h) ? p.temp12m : mo_scalar_profile(2.0 + z0q, obu, z0q);
+  return p;
+}
+
+} // namespace elmk

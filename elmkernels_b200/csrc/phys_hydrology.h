@@ -1,0 +1,220 @@
+// phys_hydrology.h - canopy water: wetted fraction (group a1) and interception / snow
+// initialisation / surface-water fraction (group a3).
+//
+// Parity targets:
+//   kokkos_frac_wet          reference driver/kokkos/canopy_hydrology_kokkos.cc:98-112
+//     -> canopy_hydrology::fraction_wet      src/physics/canopy_hydrology_impl.hh:123-142
+//   kokkos_canopy_hydrology  canopy_hydrology_kokkos.cc:7-96
+//     -> interception :8-66, ground_flux :83-119, snow_init :146-308, fraction_h2osfc :312-357
+// Scope: soil/crop land units, no lake, no urban (elmk_set_tables rejects anything else), so the
+// reference's LandType branches are resolved at compile time here.
+#pragma once
+#include "elmk_state.h"
+
+namespace elmk {
+
+// ---- a1 -------------------------------------------------------------------------------------
+ELMK_HD void column_frac_wet(const Cols& S, const Tables& T, const int c)
+{
+  const int veg = C1(frac_veg_nosno);
+  double wet = 0.0, dry = 0.0;
+  if (veg == 1) {
+    const double lai = C1(elai), sai = C1(esai), canwat = C1(h2ocan);
+    if (canwat > 0.0) {
+      const double vegt = veg * (lai + sai);
+      const double dewmxi = 1.0 / T.dewmx;
+      // exponent literal as in the reference, not 2/3
+      wet = dmin(pow((dewmxi / vegt) * canwat, 0.666666666666), 1.0);
+    }
+    dry = (1.0 - wet) * lai / (lai + sai);
+  }
+  C1(fwet) = wet;
+  C1(fdry) = dry;
+}
+
+// ---- a3 -------------------------------------------------------------------------------------
+// density of newly fallen snow [kg/m3] as a function of air temperature (Alta relationship)
+ELMK_HD double fresh_snow_density(const double forc_t)
+{
+  if (forc_t > TFRZ + 2.0) return 50.0 + 1.7 * pow(17.0, 1.5);
+  if (forc_t > TFRZ - 15.0) return 50.0 + 1.7 * pow((forc_t - TFRZ + 15.0), 1.5);
+  return 50.0;
+}
+
+// Niu & Yang (2007) snow-cover fraction used when oldfflag == 1
+ELMK_HD double fsca_niu_yang(const double snow_depth, const double swe)
+{
+  // pow(x, 1.0) == x exactly, kept out
+  return tanh(snow_depth / (2.5 * ZLND * dmin(800.0, (swe / snow_depth / 100.0))));
+}
+
+ELMK_HD void column_canopy_hydrology(const Cols& S, const Tables& T, const double dtime, const int c)
+{
+  const int veg = C1(frac_veg_nosno);
+  const int capsnow = C1(do_capsnow);
+  const double rain = C1(forc_rain), snow = C1(forc_snow);
+  const double forc_t = C1(forc_tbot);
+
+  // -- interception: throughfall and canopy drip --
+  double candrip = 0.0, thru_snow = 0.0, thru_rain = 0.0, fracsnow = 0.0, fracrain = 0.0;
+  if (veg == 1 && (rain + snow) > 0.0) {
+    const double lsai = C1(elai) + C1(esai);
+    double canwat = C1(h2ocan);
+    fracsnow = snow / (snow + rain);
+    fracrain = rain / (snow + rain);
+    const double canmax = T.dewmx * lsai;
+    const double fpi = 0.25 * (1.0 - exp(-0.5 * lsai));
+    thru_snow = snow * (1.0 - fpi);
+    thru_rain = rain * (1.0 - fpi);
+    const double intr = (snow + rain) * fpi;
+    canwat = dmax(0.0, (canwat + dtime * intr));
+    const double xrun = (canwat - canmax) / dtime;
+    if (xrun > 0.0) {
+      candrip = xrun;
+      canwat = canmax;
+    }
+    C1(h2ocan) = canwat;
+  }
+
+  // -- precipitation reaching the ground (qflx_irrig is hard-wired 0.0 in the wrapper) --
+  double grnd_snow, grnd_rain;
+  if (veg == 0) {
+    grnd_snow = snow;
+    grnd_rain = rain;
+  } else {
+    grnd_snow = thru_snow + (candrip * fracsnow);
+    grnd_rain = thru_rain + (candrip * fracrain);
+  }
+  grnd_rain = grnd_rain + 0.0;
+  double snow_grnd, rain_grnd;
+  if (capsnow) {
+    C1(qflx_snwcp_liq) = grnd_rain;
+    C1(qflx_snwcp_ice) = grnd_snow;
+    snow_grnd = 0.0;
+    rain_grnd = 0.0;
+  } else {
+    C1(qflx_snwcp_liq) = 0.0;
+    C1(qflx_snwcp_ice) = 0.0;
+    snow_grnd = grnd_snow;
+    rain_grnd = grnd_rain;
+  }
+  C1(qflx_snow_grnd) = snow_grnd;
+  C1(qflx_rain_grnd) = rain_grnd;
+
+  // -- snow depth, snow-cover fraction, birth of the first snow layer --
+  int snl = C1(snl);
+  double depth = C1(snow_depth), swe = C1(h2osno), intsnow = C1(int_snow), fsno = C1(frac_sno);
+  const double depth_before = depth;
+  const double nmelt = C1(n_melt);
+  constexpr double accum_factor = 0.1;
+  for (int j = 0; j < NLEVSNO; ++j)
+    C2(swe_old, j) = (j < NLEVSNO - snl) ? 0.0 : C2(h2osoi_liq, j) + C2(h2osoi_ice, j);
+
+  double dz_snowf, newsnow;
+  if (capsnow) {
+    dz_snowf = 0.0;
+    newsnow = snow_grnd * dtime;
+    fsno = 1.0;
+    intsnow = 5.e2;
+  } else {
+    const double bifall = fresh_snow_density(forc_t);
+    newsnow = snow_grnd * dtime;
+    intsnow = dmax(intsnow, swe);
+    const double snowmelt = C1(qflx_snow_melt) * dtime;
+    if (swe > 0.0) {
+      if (snowmelt > 0.0) {
+        const double smr = dmin(1.0, (swe / intsnow));
+        fsno = 1.0 - pow((acos(dmin(1.0, (2.0 * smr - 1.0))) / PI), nmelt);
+      }
+      if (newsnow > 0.0) {
+        fsno = 1.0 - (1.0 - tanh(accum_factor * newsnow)) * (1.0 - fsno);
+        const double t = (swe + newsnow) / (0.5 * (cos(PI * pow((1.0 - dmax(fsno, 1.e-6)), (1.0 / nmelt))) + 1.0));
+        intsnow = dmin(1.e8, t);
+      }
+      if (fsno > 0.0) {
+        depth = depth + newsnow / (bifall * fsno);
+      } else {
+        depth = 0.0;
+      }
+      if (T.oldfflag == 1) {
+        if (depth > 0.0) fsno = fsca_niu_yang(depth, swe + newsnow);
+        if (swe < 1.0) fsno = dmin(fsno, swe);
+      }
+    } else {
+      if (newsnow > 0.0) {
+        const double z_avg = newsnow / bifall;
+        fsno = tanh(accum_factor * newsnow);
+        const double t = (swe + newsnow) / (0.5 * (cos(PI * pow((1.0 - dmax(fsno, 1.e-6)), (1.0 / nmelt))) + 1.0));
+        intsnow = dmin(1.e8, t);
+        depth = z_avg / fsno;
+        if (T.oldfflag == 1 && depth > 0.0) fsno = fsca_niu_yang(depth, swe + newsnow);
+      } else {
+        depth = 0.0;
+        fsno = 0.0;
+      }
+    }
+    swe = swe + newsnow;
+    intsnow = intsnow + newsnow;
+    dz_snowf = (depth - depth_before);
+  }
+  double fsno_eff = fsno;   // soil/crop land unit with subgridflag == 1
+
+  const int bot = NLEVSNO - 1;
+  bool newnode = false;
+  if (snl == 0 && snow_grnd > 0.0 && (fsno * depth) >= 0.01) {
+    newnode = true;
+    snl = 1;
+    C2(dz, bot) = depth;
+    C2(zsoi, bot) = -0.5 * depth;
+    C2(zisoi, bot) = -depth;
+    C2(t_soisno, bot) = dmin(TFRZ, forc_t);
+    C2(h2osoi_ice, bot) = swe;
+    C2(h2osoi_liq, bot) = 0.0;
+    C2(frac_iceold, bot) = 1.0;
+    C2(snw_rds, bot) = SNW_RDS_MIN;
+  }
+  if (snl > 0 && !newnode) {
+    const int top = NLEVSNO - snl;
+    C2(h2osoi_ice, top) = C2(h2osoi_ice, top) + newsnow;
+    C2(dz, top) = C2(dz, top) + dz_snowf;
+  }
+
+  // -- fraction of the column covered by standing surface water: 10 fixed Newton steps --
+  double sfc = C1(h2osfc), fsfc;
+  constexpr double min_h2osfc = 1.e-8;
+  if (sfc > min_h2osfc) {
+    double d = 0.0;
+    const double sigma = 1.0e3 * C1(micro_sigma);
+    for (int l = 0; l < 10; ++l) {
+      const double fd = 0.5 * d * (1.0 + erf(d / (sigma * sqrt(2.0)))) +
+                        sigma / sqrt(2.0 * PI) * exp(-sq(d) / (2.0 * sq(sigma))) - sfc;
+      const double dfdd = 0.5 * (1.0 + erf(d / (sigma * sqrt(2.0))));
+      d = d - fd / dfdd;
+    }
+    fsfc = 0.5 * (1.0 + erf(d / (sigma * sqrt(2.0))));
+  } else {
+    fsfc = 0.0;
+    C2(h2osoi_liq, NLEVSNO) = C2(h2osoi_liq, NLEVSNO) + sfc;
+    sfc = 0.0;
+  }
+  if (fsno > (1.0 - fsfc) && swe > 0.0) {
+    if (fsfc > 0.01) {
+      fsfc = dmax((1.0 - fsno), 0.01);
+      fsno = 1.0 - fsfc;
+    } else {
+      fsno = 1.0 - fsfc;
+    }
+    fsno_eff = fsno;
+  }
+
+  C1(snl) = snl;
+  C1(snow_depth) = depth;
+  C1(h2osno) = swe;
+  C1(int_snow) = intsnow;
+  C1(frac_sno) = fsno;
+  C1(frac_sno_eff) = fsno_eff;
+  C1(h2osfc) = sfc;
+  C1(frac_h2osfc) = fsfc;
+}
+
+} // namespace elmk

@@ -1,7 +1,7 @@
 /* elmk_b200.h - C ABI of the B200-native ELM column-timestep library (libelmk_b200.so).
  *
  * This is the drop-in boundary below the reference's kernel-group wrappers
- * (reference driver/kokkos/*_kokkos.{hh,cc}, called from ELMInterface::advance,
+ * (reference driver/kokkos/<group>_kokkos.{hh,cc}, called from ELMInterface::advance,
  * driver/kokkos/elm_kokkos_interface.cc:269-322).  Plain pointers and sizes only.
  *
  * Every entry point returns 0 on success or a negative ELMK_E* code; the text of the
@@ -168,6 +168,16 @@ int elmk_sync(elmk_handle h);
 /* number of kernel launches issued by this handle since creation (for bench accounting) */
 int64_t elmk_launch_count(elmk_handle h);
 
+/* ---- per-launch device timing (CUDA events on the handle's stream around every kernel of elmk_step
+ *      and elmk_init_timestep).  Counterpart of the kernel name strings the reference passes to
+ *      Kokkos::parallel_for (e.g. canopy_fluxes_kokkos.cc:264) for the Kokkos profiling tools.
+ *      elmk_timing_read synchronises, accumulates the recorded intervals and returns, for up to `max`
+ *      distinct launch names, the name, the total milliseconds and the number of launches; the return
+ *      value is the number of names (or a negative error).  elmk_timing_enable(h, 0|1) also resets. ---- */
+int elmk_timing_enable(elmk_handle h, int on);
+int elmk_timing_read(elmk_handle h, int max, const char** names, double* total_ms, int64_t* launches,
+                     uint32_t* group_masks);
+
 /* ---- error convention: replaces C++ exceptions thrown inside kernels.  any = OR of all
  *      columns' errmask words, first_col = lowest column index with a non-zero word (-1 if none).
  *      Synchronises the stream. ---- */
@@ -184,6 +194,9 @@ int elmk_diag_reduce(elmk_handle h, double out[24]);
 
 /* raw device pointer + level stride of a field (for zero-copy interop with torch tensors) */
 int elmk_device_ptr(elmk_handle h, int field, void** ptr, int64_t* level_stride);
+/* the handle's CUDA stream (a cudaStream_t), so that a caller can record its own events on it or make
+ * other streams wait for the step */
+int elmk_stream(elmk_handle h, void** stream);
 
 #ifdef __cplusplus
 }

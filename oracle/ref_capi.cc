@@ -449,6 +449,9 @@ int elmk_diag_reduce(elmk_handle h, double out[24]) {
   return ELMK_OK;
 }
 int elmk_device_ptr(elmk_handle, int, void**, int64_t*) { return ELMK_EUNSUPPORTED; }
+int elmk_stream(elmk_handle, void** stream) { if (stream) *stream = nullptr; return ELMK_OK; }
+int elmk_timing_enable(elmk_handle, int) { return ELMK_OK; }
+int elmk_timing_read(elmk_handle, int, const char**, double*, int64_t*, uint32_t*) { return 0; }
 
 // ---- oracle-only extra: the reference's one-time column initialisation, per column exactly as
 //      initialize_elm_kokkos.cc:374-431, used to check the product's ensemble generator ----

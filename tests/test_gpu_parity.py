@@ -1,0 +1,182 @@
+"""GPU parity tests: the CUDA library (through the C ABI) against the oracle on the same seeded inputs.
+
+Checker = oracle/_ref (the reference's own code) when its prebuilt library is present, else oracle/port.
+Tolerances (BASELINE.json): 1e-12 relative for closed-form kernel groups, 1e-8 relative on the outputs of
+the iterative CanopyFluxes and SoilTemperature paths and on everything computed from them."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from elmkernels_b200 import abi, ensemble
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CLOSED_FORM = [abi.G_FRAC_WET, abi.G_ALBEDO, abi.G_CANOPY_HYDROLOGY, abi.G_SURFACE_RADIATION,
+               abi.G_CANOPY_TEMPERATURE, abi.G_BAREGROUND_FLUXES, abi.G_SNOW_HYDROLOGY, abi.G_SURFACE_FLUXES,
+               abi.G_CONSERVATION]
+
+
+@pytest.fixture(scope="module")
+def checker(request):
+    path = os.path.join(ROOT, "oracle", "_ref", "libelmref.so")
+    if os.path.exists(path):
+        return abi.Library(path)
+    return request.getfixturevalue("port_lib")
+
+
+def test_backend_is_cuda(cuda_lib):
+    assert cuda_lib.backend == "cuda-sm100a"
+
+
+def test_upload_download_round_trip(cuda_lib):
+    """Layout conversion (reference host layout <-> column-innermost HBM layout), ragged sizes."""
+    rng = np.random.default_rng(1)
+    for n in (1, 63, 64, 65, 1000, 4097):
+        cols = cuda_lib.columns(n)
+        for name in ("t_soisno", "zisoi", "psn_pft", "forc_tbot", "snl", "imelt", "veg_active", "forc_solad"):
+            _, dt, nl = cuda_lib.fields[name]
+            shape = (n,) if nl == 1 else (n, nl)
+            a = (rng.uniform(-1e3, 1e3, shape) if dt == abi.F64 else rng.integers(0, 100, shape)).astype(abi._NP[dt])
+            cols.upload(name, a)
+            assert np.array_equal(cols.download(name), a), (n, name)
+        # partial ranges
+        if n > 10:
+            a = rng.uniform(size=(5, 20))
+            cols.upload("dz", a, col0=3)
+            assert np.array_equal(cols.download("dz", col0=3, n=5), a)
+        cols.close()
+
+
+def test_fill_and_errors(cuda_lib):
+    cols = cuda_lib.columns(777)
+    cols.fill("t_grnd", 271.5)
+    assert np.all(cols.download("t_grnd") == 271.5)
+    assert cols.errors() == (0, -1)
+    e = np.zeros(777, np.int32)
+    e[500] = 4
+    e[123] = 2
+    cols.upload("errmask", e)
+    assert cols.errors() == (6, 123)
+    cols.clear_errors()
+    assert cols.errors() == (0, -1)
+
+
+def test_step_requires_tables(cuda_lib):
+    cols = cuda_lib.columns(64)
+    with pytest.raises(abi.ElmkError):
+        cols.step()
+
+
+def test_unsupported_land_unit_is_rejected(cuda_lib, params):
+    cols = cuda_lib.columns(64)
+    with pytest.raises(abi.ElmkError):
+        cols.set_tables(params, land=dict(ltype=3))
+
+
+@pytest.mark.parametrize("seed,h2osfc,tspread", [(20240005, 0.0, 0.0), (20240003, 0.2, 8.0)])
+def test_each_group_in_isolation(cuda_lib, checker, params, seed, h2osfc, tspread):
+    """Every kernel group on inputs identical to the checker's (state re-synchronised before each group)."""
+    cfg = ensemble.EnsembleConfig(ncols=4096, seed=seed, h2osfc_fraction=h2osfc, soil_temp_spread=tspread)
+    pair = parity.Pair(checker, cuda_lib, params, cfg)
+    for step in range(4):
+        pair.begin_step()
+        bad = pair.compare(0.0, names=["h2osno_old", "dtbegin_column_h2o", "do_capsnow", "frac_veg_nosno", "frac_iceold"])
+        assert not bad, f"init_timestep step {step}\n{parity.fmt(bad)}"
+        for g in range(abi.G_ALL.bit_length()):
+            pair.resync()
+            pair.run(groups=1 << g)
+            rtol = parity.RTOL_CLOSED if (1 << g) in CLOSED_FORM else parity.RTOL_ITER
+            bad = pair.compare(rtol)
+            assert not bad, f"step {step} group {abi.GROUP_NAMES[g]} (rtol {rtol})\n{parity.fmt(bad)}"
+    assert pair.b.errors() == pair.a.errors()
+
+
+def test_full_chain_free_running(cuda_lib, checker, params):
+    """48 steps (one day) of the full chain with state persistent on the device, never re-synchronised."""
+    cfg = ensemble.EnsembleConfig(ncols=8192, seed=20240005, soil_temp_spread=6.0)
+    pair = parity.Pair(checker, cuda_lib, params, cfg)
+    diag = ["dtend_column_h2o", "errh2o", "errh2osno", "dwb", "errsol", "errlon", "errseb", "netrad"]
+    for step in range(48):
+        pair.begin_step()
+        pair.run()
+        if step % 8 == 7 or step < 2:
+            bad = pair.compare(parity.RTOL_ITER)
+            assert not bad, f"step {step}\n{parity.fmt(bad)}"
+    assert pair.b.errors() == pair.a.errors() == (0, -1)
+    assert not pair.compare(parity.RTOL_ITER, names=diag)
+    # the optional global diagnostic (sum/min/max over columns)
+    ra, rb = pair.a.diag_reduce(), pair.b.diag_reduce()
+    assert np.allclose(ra, rb, rtol=1e-8, atol=1e-8 * np.max(np.abs(ra)))
+
+
+def test_split_and_fused_plans_agree(cuda_lib, params, monkeypatch):
+    """The fused launch plan and one-launch-per-group give identical bits."""
+    cfg = ensemble.EnsembleConfig(ncols=2048, seed=3, h2osfc_fraction=0.1, soil_temp_spread=5.0)
+    monkeypatch.setenv("ELMK_PLAN", "split")
+    pair = parity.Pair(cuda_lib, cuda_lib, params, cfg)   # a: split plan
+    monkeypatch.delenv("ELMK_PLAN")
+    pair.b.close()
+    pair.b = cuda_lib.columns(cfg.ncols)                   # b: default (fused) plan
+    pair.b.set_tables(params)
+    pair.b.upload_state(pair.state0)
+    for _ in range(6):
+        pair.begin_step()
+        pair.run()
+    assert not pair.compare(0.0)
+    assert pair.b.launch_count < pair.a.launch_count
+
+
+def test_golden_vectors(cuda_lib, params):
+    """The committed vectors produced by the reference itself (tests/golden/chain_64col.npz)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "chain_64col.npz"))
+    n = int(z["ncols"])
+    cols = cuda_lib.columns(n)
+    cols.set_tables(params)
+    cols.upload_state({k[3:]: z[k] for k in z.files if k.startswith("s0_")})
+    for s in range(int(z["nsteps"])):
+        cols.upload_state({k[len(f"f{s}_"):]: z[k] for k in z.files if k.startswith(f"f{s}_")})
+        cols.init_timestep(True)
+        cols.step()
+    assert cols.errors() == (0, -1)
+    bad = {}
+    for k in z.files:
+        if k.startswith("out_"):
+            m = parity.mismatch(z[k], cols.download(k[4:]), parity.RTOL_ITER)
+            if m.any():
+                bad[k[4:]] = int(m.sum())
+    assert not bad, bad
+
+
+def test_large_ensemble_properties(cuda_lib, params):
+    """Size-independent properties at a bench-like size (no oracle): column independence (a column's result
+    does not depend on which other columns share the launch) and the shortwave/longwave identities."""
+    n = 1 << 18
+    cfg = ensemble.EnsembleConfig(ncols=n, seed=77, soil_temp_spread=6.0)
+    st = ensemble.make_state(cfg, params, cuda_lib.fields)
+    F = ensemble.Forcing(n, seed=5)
+    big = cuda_lib.columns(n)
+    big.set_tables(params)
+    big.upload_state(st)
+    lo, m = 100_003, 4096
+    sub = cuda_lib.columns(m)
+    sub.set_tables(params)
+    sub.upload_state({k: v[lo:lo + m] for k, v in st.items()})
+    for step in range(4):
+        f = F.at(step, {k: big.download(k) for k in parity.FORCING_STATE})
+        big.upload_state(f)
+        sub.upload_state({k: v[lo:lo + m] for k, v in f.items()})
+        for c in (big, sub):
+            c.init_timestep(True)
+            c.step()
+    assert big.errors() == (0, -1)
+    for k in cuda_lib.field_names:
+        assert np.array_equal(big.download(k, col0=lo, n=m), sub.download(k), equal_nan=True), k
+    assert np.max(np.abs(big.download("errsol"))) < 1e-9
+    assert np.max(np.abs(big.download("errlon"))) < 1e-9
+    snl = big.download("snl")
+    assert snl.min() >= 0 and snl.max() <= 5
+    t = big.download("t_soisno")
+    assert np.isfinite(t).all() and t[:, 5:].min() > 150.0 and t.max() < 350.0

@@ -1,0 +1,82 @@
+"""The oracle is pinned: oracle/port (host build of the physics core) must reproduce oracle/_ref (the
+reference's own code, compiled unmodified) bit for bit on seeded ensembles that exercise snow layers 0..5,
+bare and vegetated columns, all PFTs incl. C4, night and day, standing water, and against the committed
+golden vectors generated from the reference (tests/golden, tools/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from elmkernels_b200 import abi, ensemble
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden", "chain_64col.npz")
+
+
+def _assert_identical(pair, what):
+    bad = pair.compare(0.0)
+    assert not bad, f"{what}: port differs from the reference\n{parity.fmt(bad)}"
+
+
+@pytest.mark.parametrize("seed,h2osfc,tspread", [(20240005, 0.0, 0.0), (20240003, 0.2, 8.0)])
+def test_port_equals_reference_free_running(ref_lib, port_lib, params, seed, h2osfc, tspread):
+    cfg = ensemble.EnsembleConfig(ncols=768, seed=seed, h2osfc_fraction=h2osfc, soil_temp_spread=tspread)
+    pair = parity.Pair(ref_lib, port_lib, params, cfg)
+    for step in range(12):
+        pair.begin_step()
+        pair.run()
+        if step in (0, 5, 11):
+            _assert_identical(pair, f"step {step}")
+    assert pair.a.errors() == pair.b.errors() == (0, -1)
+    snl = pair.a.download("snl")
+    assert set(np.unique(snl)) == {0, 1, 2, 3, 4, 5}
+
+
+def test_port_equals_reference_group_by_group(ref_lib, port_lib, params):
+    cfg = ensemble.EnsembleConfig(ncols=512, seed=5, h2osfc_fraction=0.2, soil_temp_spread=8.0)
+    pair = parity.Pair(ref_lib, port_lib, params, cfg)
+    for step in range(3):
+        pair.begin_step()
+        for g in range(abi.G_ALL.bit_length()):
+            pair.run(groups=1 << g)
+            _assert_identical(pair, f"step {step} group {abi.GROUP_NAMES[g]}")
+
+
+def test_port_reproduces_golden_vectors(port_lib, params):
+    """Golden vectors: inputs and outputs of the reference itself (oracle/_ref) on 64 columns x 6 steps,
+    committed so that the check also runs where /root/reference is absent."""
+    z = np.load(GOLDEN)
+    n = int(z["ncols"])
+    cols = port_lib.columns(n)
+    cols.set_tables(params)
+    names = [k[3:] for k in z.files if k.startswith("s0_")]
+    cols.upload_state({k: z["s0_" + k] for k in names})
+    nsteps = int(z["nsteps"])
+    for s in range(nsteps):
+        cols.upload_state({k[len(f"f{s}_"):]: z[k] for k in z.files if k.startswith(f"f{s}_")})
+        cols.init_timestep(True)
+        cols.step()
+    for k in z.files:
+        if k.startswith("out_"):
+            got = cols.download(k[4:])
+            ref = z[k]
+            same = (got == ref) | (np.isnan(got.astype(float)) & np.isnan(ref.astype(float)))
+            assert same.all(), f"{k[4:]}: {int((~same).sum())} elements differ from the golden vector"
+
+
+def test_golden_vectors_match_reference(ref_lib, params):
+    """The committed golden file is what the reference produces today (guards against a stale file)."""
+    z = np.load(GOLDEN)
+    n = int(z["ncols"])
+    cols = ref_lib.columns(n)
+    cols.set_tables(params)
+    cols.upload_state({k[3:]: z[k] for k in z.files if k.startswith("s0_")})
+    for s in range(int(z["nsteps"])):
+        cols.upload_state({k[len(f"f{s}_"):]: z[k] for k in z.files if k.startswith(f"f{s}_")})
+        cols.init_timestep(True)
+        cols.step()
+    for k in z.files:
+        if k.startswith("out_"):
+            got = cols.download(k[4:])
+            assert np.array_equal(got, z[k], equal_nan=True), k
