@@ -155,7 +155,7 @@ class Columns:
     def set_tables(self, params: Mapping[str, np.ndarray], land: Optional[Mapping[str, int]] = None,
                    dewmx: float = 0.1, oldfflag: int = 1):
         """params: arrays keyed pft_<name>, snicar_<name>, albsat, albdry, snowage_{tau,kappa,drdt0}."""
-        land = dict(ltype=1, ctype=1, vtype=12, urbpoi=0, lakpoi=0, **(land or {}))
+        land = {**dict(ltype=1, ctype=1, vtype=12, urbpoi=0, lakpoi=0), **(land or {})}
         t = Tables()
         keep = []
 

@@ -15,6 +15,24 @@
 #define ELMK_HD_NOINLINE inline
 #endif
 
+// Transcendentals are CALLED, not inlined, on the device: CUDA's double-precision pow/exp/log expand to
+// 60-350 SASS instructions per call site, and the column kernels have ~70 call sites inside divergent
+// loops.  Inlined, the CanopyFluxes iteration body was 390 KB of SASS against a 32 KB L1.5 instruction
+// cache and the kernel spent >20 issue slots per instruction waiting for instruction fetch (ncu
+// "no_instruction" stall, profiles/r1_baseline_raw.csv).  One shared copy per function keeps the loop
+// bodies cache-resident.
+namespace elmk {
+ELMK_HD_NOINLINE double m_exp(double x) { return exp(x); }
+ELMK_HD_NOINLINE double m_log(double x) { return log(x); }
+ELMK_HD_NOINLINE double m_log10(double x) { return log10(x); }
+ELMK_HD_NOINLINE double m_pow(double x, double y) { return pow(x, y); }
+ELMK_HD_NOINLINE double m_atan(double x) { return atan(x); }
+ELMK_HD_NOINLINE double m_acos(double x) { return acos(x); }
+ELMK_HD_NOINLINE double m_tanh(double x) { return tanh(x); }
+ELMK_HD_NOINLINE double m_erf(double x) { return erf(x); }
+ELMK_HD_NOINLINE double m_cos(double x) { return cos(x); }
+} // namespace elmk
+
 namespace elmk {
 
 // ---- dimensions (reference src/data/elm_constants.h:84-98) ----
@@ -94,8 +112,8 @@ ELMK_HD int imax(int a, int b) { return (a < b) ? b : a; }
 // build uses multiplications (3 DMUL instead of a ~100-instruction pow), inside the 1e-12 bar.
 ELMK_HD double sq(double x) { return x * x; }
 #ifdef ELMK_EXACT_POW
-ELMK_HD double cube(double x) { return pow(x, 3.0); }
-ELMK_HD double pow4(double x) { return pow(x, 4.0); }
+ELMK_HD double cube(double x) { return m_pow(x, 3.0); }
+ELMK_HD double pow4(double x) { return m_pow(x, 4.0); }
 #else
 ELMK_HD double cube(double x) { return x * x * x; }
 ELMK_HD double pow4(double x) { const double x2 = x * x; return x2 * x2; }

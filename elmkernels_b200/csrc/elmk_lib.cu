@@ -78,6 +78,213 @@ __global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* _
   if (MASK & ELMK_G_CONSERVATION) column_conservation(S, T, A.dtime, c);
 }
 
+// ---- work-class sorted variant ------------------------------------------------------------------
+// The heavy groups branch on column type: CanopyFluxes does nothing for bare columns, skips the
+// photosynthesis root-find at night; SNICAR runs only for sunlit snow and costs in proportion to the number
+// of snow layers.  With one thread per consecutive column, a warp holds every type and executes the union of
+// their paths (ncu: 5-6 active lanes per instruction, profiles/r1_baseline_raw.csv).  Here a block owns a
+// window of kWindow consecutive columns, orders them by a cheap work-class key in shared memory (counting
+// sort, heaviest class first) and its warps pull 32-column chunks of the ordered list from a shared counter,
+// so that a warp sees one class (except at the few class boundaries) and the warps of a block stay
+// balanced.  The window keeps the scattered 8-byte accesses of a warp inside 8 KB per field row.
+constexpr int kWindow = 1024;
+constexpr int kClasses = 8;
+
+template <uint32_t MASK> __device__ __forceinline__ int work_class(const Cols& S, const int c)
+{
+  if (MASK & ELMK_G_CANOPY_FLUXES) {
+    if (S.frac_veg_nosno[c] == 0) return 0;                       // bare: initialise and leave
+    return (S.parsun_z[c] > 0.0 || S.parsha_z[c] > 0.0) ? 2 : 1;  // day: stomatal root-find; night: none
+  }
+  if (MASK & ELMK_G_ALBEDO) {
+    if (!(S.coszen[c] > 0.0)) return 0;                           // night: initial values only
+    if (!(S.h2osno[c] > 1.0e-30)) return 1;                       // sunlit, no snow: two-stream only
+    const int snl = S.snl[c];
+    return 1 + (snl > 0 ? snl : 1);                               // SNICAR over 1..5 layers
+  }
+  if (MASK & ELMK_G_SOIL_TEMPERATURE) return S.snl[c];
+  return 0;
+}
+
+template <uint32_t MASK>
+__global__ void __launch_bounds__(kBlock) k_groups_sorted(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
+{
+  __shared__ unsigned short order[kWindow];
+  __shared__ int count[kClasses], start[kClasses], next_chunk;
+  const int base = blockIdx.x * kWindow;
+  const int nvalid = (S.ncols - base < kWindow) ? (S.ncols - base) : kWindow;
+  if (threadIdx.x < kClasses) count[threadIdx.x] = 0;
+  if (threadIdx.x == 0) next_chunk = 0;
+  __syncthreads();
+  int key[kWindow / kBlock], rank[kWindow / kBlock];
+#pragma unroll
+  for (int r = 0; r < kWindow / kBlock; ++r) {
+    const int i = r * kBlock + threadIdx.x;
+    key[r] = -1;
+    if (i < nvalid) {
+      key[r] = work_class<MASK>(S, base + i);
+      rank[r] = atomicAdd(&count[key[r]], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = kClasses - 1; k >= 0; --k) {   // heaviest class first
+      start[k] = acc;
+      acc += count[k];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kWindow / kBlock; ++r)
+    if (key[r] >= 0) order[start[key[r]] + rank[r]] = (unsigned short)(r * kBlock + threadIdx.x);
+  __syncthreads();
+  const Tables& T = *Tp;
+  const int lane = threadIdx.x & 31;
+  while (true) {
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(&next_chunk, 1);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    const int i = chunk * 32 + lane;
+    if (chunk * 32 >= nvalid) break;
+    if (i < nvalid) {
+      const int c = base + order[i];
+      if (MASK & ELMK_G_FRAC_WET) column_frac_wet(S, T, c);
+      if (MASK & ELMK_G_ALBEDO) column_albedo(S, T, c);
+      if (MASK & ELMK_G_CANOPY_FLUXES) column_canopy_fluxes(S, T, A, c);
+      if (MASK & ELMK_G_SOIL_TEMPERATURE) column_soil_temperature(S, T, A.dtime, c);
+    }
+  }
+}
+
+// ---- CanopyFluxes with warp-level re-packing of the stability iteration ---------------------------
+// The number of passes of the leaf-temperature / stability loop is data dependent: 3..41, mean ~6, and a
+// warp of 32 consecutive (or even class-sorted) columns runs as long as its slowest lane - measured mean
+// of the per-warp maximum ~15, i.e. ~40 % lane utilisation.  The loop is therefore taken out of the
+// column kernel:
+//   k_canflux_begin    one thread per column: initialize_flux (moisture stress = 15 pow per column, first
+//                      guess), iteration state -> scratch (column-innermost, coalesced), column appended to
+//                      the day list (stomatal root-find every pass) or the night list
+//   k_canflux_iterate  persistent warps; every lane owns one column of the queue and runs ONE pass per
+//                      round; a lane whose column has converged stores its state and takes the next
+//                      queue entry (warp-aggregated atomic), so lanes stay busy whatever the pass counts
+//   k_canflux_end      one thread per column: compute_flux from the stored state
+// The arithmetic is canflux_begin / canflux_iterate / canflux_end of phys_canflux.h, the same functions
+// the one-launch column_canopy_fluxes chains, so the result is bit-identical to the plain kernel.
+constexpr int kCanfluxDoubles = 0
+#define X(n) +1
+    ELMK_CANFLUX_CONST(X) ELMK_CANFLUX_CARRIED(X) ELMK_CANFLUX_INT(X)
+#undef X
+    ;
+
+struct CanfluxQueue {
+  double* scratch;   // [kCanfluxDoubles][np]
+  int* list;         // [np]: day columns from the front, night columns from the back
+  int* counters;     // [0] day count, [1] night count, [2] queue head
+  long long np;
+};
+
+__device__ __forceinline__ void canflux_store(const CanfluxQueue& Q, const int c, const CanopyIter& I, const bool all)
+{
+  double* p = Q.scratch + c;
+  long long k = 0;
+#define X(n) if (all) p[k * Q.np] = I.n; ++k;
+  ELMK_CANFLUX_CONST(X)
+#undef X
+#define X(n) p[k * Q.np] = I.n; ++k;
+  ELMK_CANFLUX_CARRIED(X)
+#undef X
+#define X(n) p[k * Q.np] = (double)I.n; ++k;
+  ELMK_CANFLUX_INT(X)
+#undef X
+}
+__device__ __forceinline__ void canflux_load(const CanfluxQueue& Q, const int c, CanopyIter& I)
+{
+  const double* p = Q.scratch + c;
+  long long k = 0;
+#define X(n) I.n = p[k * Q.np]; ++k;
+  ELMK_CANFLUX_CONST(X)
+  ELMK_CANFLUX_CARRIED(X)
+#undef X
+#define X(n) I.n = (int)p[k * Q.np]; ++k;
+  ELMK_CANFLUX_INT(X)
+#undef X
+}
+
+__global__ void __launch_bounds__(kBlock) k_canflux_begin(const Cols S, const Tables* __restrict__ Tp, const StepArgs A,
+                                                          const CanfluxQueue Q)
+{
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  int cls = 0;   // 0: nothing to iterate, 1: night, 2: day
+  if (c < S.ncols) {
+    const PsnPft P = load_psn_pft(S, c);
+    CanopyIter I;
+    if (canflux_begin(S, *Tp, A, P, c, I)) {
+      canflux_store(Q, c, I, true);
+      cls = (I.parsun > 0.0 || I.parsha > 0.0) ? 2 : 1;
+    }
+  }
+  // warp-aggregated append: one atomic per warp and list
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned day = __ballot_sync(0xffffffffu, cls == 2), night = __ballot_sync(0xffffffffu, cls == 1);
+  int base_day = 0, base_night = 0;
+  if (lane == 0) {
+    if (day) base_day = atomicAdd(&Q.counters[0], __popc(day));
+    if (night) base_night = atomicAdd(&Q.counters[1], __popc(night));
+  }
+  base_day = __shfl_sync(0xffffffffu, base_day, 0);
+  base_night = __shfl_sync(0xffffffffu, base_night, 0);
+  const unsigned below = (1u << lane) - 1u;
+  if (cls == 2) Q.list[base_day + __popc(day & below)] = c;
+  if (cls == 1) Q.list[Q.np - 1 - (base_night + __popc(night & below))] = c;
+}
+
+__global__ void __launch_bounds__(kBlock) k_canflux_iterate(const Cols S, const CanfluxQueue Q)
+{
+  const int nday = Q.counters[0], total = nday + Q.counters[1];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned below = (1u << lane) - 1u;
+  bool have = false;
+  int c = 0;
+  PsnPft P;
+  CanopyIter I;
+  while (true) {
+    // ---- refill idle lanes from the queue ----
+    const unsigned need = __ballot_sync(0xffffffffu, !have);
+    if (need) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&Q.counters[2], __popc(need));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (!have) {
+        const int q = base + __popc(need & below);
+        if (q < total) {
+          c = (q < nday) ? Q.list[q] : Q.list[Q.np - 1 - (q - nday)];
+          canflux_load(Q, c, I);
+          P = load_psn_pft(S, c);
+          have = true;
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    // ---- one pass for every lane that owns a column ----
+    if (have) {
+      if (canflux_iterate(P, I)) {
+        canflux_store(Q, c, I, false);
+        have = false;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_canflux_end(const Cols S, const CanfluxQueue Q)
+{
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  if (c >= S.ncols || S.frac_veg_nosno[c] == 0) return;
+  CanopyIter I;
+  canflux_load(Q, c, I);
+  canflux_end(S, c, I);
+}
+
 __global__ void __launch_bounds__(kBlock) k_init_timestep(const Cols S, const Tables* __restrict__ Tp, const int reset)
 {
   const int c = blockIdx.x * kBlock + threadIdx.x;
@@ -86,8 +293,9 @@ __global__ void __launch_bounds__(kBlock) k_init_timestep(const Cols S, const Ta
 }
 
 typedef void (*GroupKernel)(const Cols, const Tables*, const StepArgs);
-struct Launch { uint32_t mask; GroupKernel fn; const char* name; };
-#define ELMK_LAUNCH(M, NAME) {(M), k_groups<(M)>, NAME}
+struct Launch { uint32_t mask; GroupKernel fn; const char* name; int cols_per_block; };
+#define ELMK_LAUNCH(M, NAME) {(M), k_groups<(M)>, NAME, kBlock}
+#define ELMK_LAUNCH_SORTED(M, NAME) {(M), k_groups_sorted<(M)>, NAME, kWindow}
 
 // plan "split": one launch per kernel group (the reference's wrapper granularity)
 const Launch kSplit[] = {
@@ -111,6 +319,14 @@ constexpr uint32_t M_SFC = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | 
                            ELMK_G_BAREGROUND_FLUXES;
 constexpr uint32_t M_END = ELMK_G_SNOW_HYDROLOGY | ELMK_G_SURFACE_FLUXES | ELMK_G_CONSERVATION;
 const Launch kFused[] = {
+    ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo"),
+    ELMK_LAUNCH(M_SFC, "hydrology+radiation+temperature+bareground"),
+    ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes"),
+    ELMK_LAUNCH(ELMK_G_SOIL_TEMPERATURE, "soil_temperature"),
+    ELMK_LAUNCH(M_END, "snow+surface_fluxes+conservation"),
+};
+// plan "unsorted": the fused cut without work-class ordering (for A/B measurements)
+const Launch kFusedUnsorted[] = {
     ELMK_LAUNCH(M_RAD, "fracwet+albedo"),
     ELMK_LAUNCH(M_SFC, "hydrology+radiation+temperature+bareground"),
     ELMK_LAUNCH(ELMK_G_CANOPY_FLUXES, "canopy_fluxes"),
@@ -255,6 +471,9 @@ struct Ctx {
   double* d_table_data = nullptr;
   char* stage[2] = {nullptr, nullptr};
   int stage_next = 0;
+  CanfluxQueue cq = {nullptr, nullptr, nullptr, 0};   // CanopyFluxes re-packing scratch (allocated on first use)
+  int iterate_blocks = 0;
+  bool repack = true;
   unsigned int* d_err = nullptr;   // [0] any, then long long first at +8
   double* d_diag = nullptr;
   void* h_pinned = nullptr;        // small pinned buffer for scalar read-backs
@@ -393,6 +612,29 @@ int move_field(Ctx* c, int field, void* host, int64_t col0, int64_t n, int layou
   return ELMK_OK;
 }
 
+// CanopyFluxes as begin / re-packed iterate / end (three launches)
+int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
+  if (!c->cq.scratch) {
+    CU(cudaMalloc(&c->cq.scratch, sizeof(double) * (size_t)kCanfluxDoubles * c->np));
+    CU(cudaMalloc(&c->cq.list, sizeof(int) * (size_t)c->np));
+    CU(cudaMalloc(&c->cq.counters, sizeof(int) * 4));
+    c->cq.np = c->np;
+    int per_sm = 0, sms = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate, kBlock, 0));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    c->iterate_blocks = std::max(1, per_sm) * std::max(1, sms);
+  }
+  const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
+  CU(cudaMemsetAsync(c->cq.counters, 0, sizeof(int) * 4, c->stream));
+  k_canflux_begin<<<grid, kBlock, 0, c->stream>>>(c->cols, c->d_tables, A, c->cq);
+  const unsigned persistent = (unsigned)std::min<int64_t>(c->iterate_blocks, (c->ncols + kBlock - 1) / kBlock);
+  k_canflux_iterate<<<persistent, kBlock, 0, c->stream>>>(c->cols, c->cq);
+  k_canflux_end<<<grid, kBlock, 0, c->stream>>>(c->cols, c->cq);
+  c->launches += 3;
+  CU(cudaGetLastError());
+  return ELMK_OK;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -472,7 +714,12 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
   if (plan && std::strcmp(plan, "split") == 0) {
     c->plan = kSplit;
     c->plan_len = sizeof(kSplit) / sizeof(kSplit[0]);
+  } else if (plan && std::strcmp(plan, "unsorted") == 0) {
+    c->plan = kFusedUnsorted;
+    c->plan_len = sizeof(kFusedUnsorted) / sizeof(kFusedUnsorted[0]);
   }
+  const char* rp = std::getenv("ELMK_CANFLUX_REPACK");
+  if (rp && rp[0] == '0') c->repack = false;
   *out = reinterpret_cast<elmk_handle>(c);
   return ELMK_OK;
 }
@@ -489,6 +736,9 @@ int elmk_destroy(elmk_handle h) {
   cudaFree(c->d_table_data);
   cudaFree(c->d_err);
   cudaFree(c->d_diag);
+  cudaFree(c->cq.scratch);
+  cudaFree(c->cq.list);
+  cudaFree(c->cq.counters);
   for (auto& t : c->timed) { cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -619,22 +869,25 @@ int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_
   }
   mask &= ELMK_G_ALL;
   const StepArgs A{dtime, dayl, max_dayl};
-  const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
+  auto grid_for = [&](const Launch& L) { return (unsigned)((c->ncols + L.cols_per_block - 1) / L.cols_per_block); };
   // cover the requested groups, in chain order, with the launches of the plan; a launch whose group
   // set is only partly requested falls back to one launch per requested group
   for (int i = 0; i < c->plan_len; ++i) {
     const Launch& L = c->plan[i];
     const uint32_t want = L.mask & mask;
     if (!want) continue;
-    if (want == L.mask) {
+    if (want == L.mask && L.mask == ELMK_G_CANOPY_FLUXES && c->repack && c->plan == kFused) {
       TimedScope ts(c, L.name, L.mask);
-      L.fn<<<grid, kBlock, 0, c->stream>>>(c->cols, c->d_tables, A);
+      if (int rc = launch_canflux_repacked(c, A)) return rc;
+    } else if (want == L.mask) {
+      TimedScope ts(c, L.name, L.mask);
+      L.fn<<<grid_for(L), kBlock, 0, c->stream>>>(c->cols, c->d_tables, A);
       c->launches += 1;
     } else {
       for (const Launch& G : kSplit) {
         if (G.mask & want) {
           TimedScope ts(c, G.name, G.mask);
-          G.fn<<<grid, kBlock, 0, c->stream>>>(c->cols, c->d_tables, A);
+          G.fn<<<grid_for(G), kBlock, 0, c->stream>>>(c->cols, c->d_tables, A);
           c->launches += 1;
         }
       }

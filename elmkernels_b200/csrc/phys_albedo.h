@@ -31,7 +31,7 @@ constexpr int MIE_N = 1471;
 // SNICAR for one incident-flux type.  flg = 1 direct beam, 2 diffuse.
 // cnc[i][j]: aerosol mass concentrations per snow slot.  Outputs: alb_out[2] (VIS, NIR) and
 // flx_abs[6][2] (five snow slots + ground, VIS/NIR), both already zero on entry.
-ELMK_HD void snicar_solve(const Cols& S, const Tables& T, const int c, const int flg, const double coszen,
+ELMK_HD_NOINLINE void snicar_solve(const Cols& S, const Tables& T, const int c, const int flg, const double coszen,
                           const double h2osno, const int snl, const double (&albsoi)[NUMRAD],
                           const double (&cnc)[NLEVSNO][NAER], double (&alb_out)[NUMRAD],
                           double (&flx_abs)[NLEVSNO + 1][NUMRAD], uint32_t& err)
@@ -165,11 +165,11 @@ ELMK_HD void snicar_solve(const Cols& S, const Tables& T, const int c, const int
           const double ts = ts_[i], ws = ws_[i], gs = gs_[i];
           const double lm = sqrt(3.0 * (1.0 - ws) * (1.0 - ws * gs));
           const double ue = 1.5 * (1.0 - ws * gs) / lm;
-          const double extins = dmax(exp_min, exp(-lm * ts));
+          const double extins = dmax(exp_min, m_exp(-lm * ts));
           const double ne = ((ue + 1.0) * (ue + 1.0) / extins) - ((ue - 1.0) * (ue - 1.0) * extins);
           rdif_a[i] = (sq(ue) - 1.0) * (1.0 / extins - extins) / ne;
           tdif_a[i] = 4.0 * ue / ne;
-          trnlay[i] = dmax(exp_min, exp(-ts / mu_not));
+          trnlay[i] = dmax(exp_min, m_exp(-ts / mu_not));
           double alp = 0.75 * ws * mu_not * ((1.0 + gs * (1.0 - ws)) / (1.0 - lm * lm * mu_not * mu_not));
           double gam = 0.5 * ws * ((1.0 + 3.0 * gs * (1.0 - ws) * mu_not * mu_not) / (1.0 - lm * lm * mu_not * mu_not));
           double apg = alp + gam;
@@ -184,7 +184,7 @@ ELMK_HD void snicar_solve(const Cols& S, const Tables& T, const int c, const int
             const double mu = gauspt[ng];
             const double gwt = gauswt[ng];
             swt = swt + mu * gwt;
-            const double trn = dmax(exp_min, exp(-ts / mu));
+            const double trn = dmax(exp_min, m_exp(-ts / mu));
             alp = 0.75 * ws * mu * ((1.0 + gs * (1.0 - ws)) / (1.0 - lm * lm * mu * mu));
             gam = 0.5 * ws * ((1.0 + 3.0 * gs * (1.0 - ws) * mu * mu) / (1.0 - lm * lm * mu * mu));
             apg = alp + gam;
@@ -302,7 +302,7 @@ ELMK_HD void snicar_solve(const Cols& S, const Tables& T, const int c, const int
     int rds_top = 0;
 #pragma unroll
     for (int i = 0; i < NLEVSNO; ++i) if (i == top) rds_top = rds[i];
-    const double sza_factor = sza_c1 * (log10(rds_top * 1.0) - 6.0) + sza_c0;
+    const double sza_factor = sza_c1 * (m_log10(rds_top * 1.0) - 6.0) + sza_c0;
     const double adjust = alb_out[1] * (sza_factor - 1.0) * wgt_sum;
     alb_out[1] *= sza_factor;
 #pragma unroll
@@ -333,7 +333,7 @@ ELMK_HD void column_albedo(const Cols& S, const Tables& T, const int c)
 #pragma unroll
   for (int i = 0; i <= NLEVSNO; ++i) { absdv[i] = 0.0; absdn[i] = 0.0; absiv[i] = 0.0; absin[i] = 0.0; }
   double vcsun = 0.0;
-  double vcsha = (1.0 - exp(-EXTKN * elai)) / EXTKN;
+  double vcsha = (1.0 - m_exp(-EXTKN * elai)) / EXTKN;
   if (elai > 0.0) vcsha /= elai; else vcsha = 0.0;
 
   double albsnd[NUMRAD] = {0.0, 0.0}, albsni[NUMRAD] = {0.0, 0.0};
@@ -411,10 +411,10 @@ ELMK_HD void column_albedo(const Cols& S, const Tables& T, const int c)
     const double phi2 = 0.877 * (1.0 - 2.0 * phi1);
     const double gdir = phi1 + phi2 * cosz;
     const double twostext = gdir / cosz;
-    const double avmu = (1.0 - phi1 / phi2 * log((phi1 + phi2) / phi1)) / phi2;
+    const double avmu = (1.0 - phi1 / phi2 * m_log((phi1 + phi2) / phi1)) / phi2;
     const double temp0 = gdir + phi2 * cosz;
     const double temp1 = phi1 * cosz;
-    const double temp2 = (1.0 - temp1 / temp0 * log((temp1 + temp0) / temp1));
+    const double temp2 = (1.0 - temp1 / temp0 * m_log((temp1 + temp0) / temp1));
     const double t_veg = C1(t_veg), fwet = C1(fwet);
     const double omegas[NUMRAD] = {0.8, 0.4};
     constexpr double betads = 0.5, betais = 0.5;
@@ -453,9 +453,9 @@ ELMK_HD void column_albedo(const Cols& S, const Tables& T, const int c)
       const double p3 = bb + tmp0;
       const double p4 = bb - tmp0;
       double t1 = dmin(h * (elai + esai), 40.0);
-      const double s1 = exp(-t1);
+      const double s1 = m_exp(-t1);
       t1 = dmin(twostext * (elai + esai), 40.0);
-      const double s2 = exp(-t1);
+      const double s2 = m_exp(-t1);
 
       // direct beam
       double u1 = bb - c1 / albgrd[ib];
@@ -518,8 +518,8 @@ ELMK_HD void column_albedo(const Cols& S, const Tables& T, const int c)
         fabd_sha_z = fabd_sha[ib] / ((1.0 - fsun) * laisum);
         fabi_sha_z = fabi_sha[ib] / ((1.0 - fsun) * laisum);
         const double extkb = twostext;
-        vcsun = (1.0 - exp(-(EXTKN + extkb) * elai)) / (EXTKN + extkb);
-        vcsha = (1.0 - exp(-EXTKN * elai)) / EXTKN - vcsun;
+        vcsun = (1.0 - m_exp(-(EXTKN + extkb) * elai)) / (EXTKN + extkb);
+        vcsha = (1.0 - m_exp(-EXTKN * elai)) / EXTKN - vcsun;
         if (elai > 0.0) {
           vcsun = vcsun / (fsun * elai);
           vcsha = vcsha / ((1.0 - fsun) * elai);

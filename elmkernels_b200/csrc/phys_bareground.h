@@ -56,7 +56,7 @@ ELMK_HD void column_bareground_fluxes(const Cols& S, const Tables&, const int c)
     const double tstar = p.temp1 * dth;
     const double qstar = p.temp2 * dqh;
     const double thvstar = tstar * (1.0 + 0.61 * forc_q) + 0.61 * forc_th * qstar;
-    z0hg = z0mg / exp(0.13 * pow((p.ustar * z0mg / 1.5e-5), 0.45));
+    z0hg = z0mg / m_exp(0.13 * m_pow((p.ustar * z0mg / 1.5e-5), 0.45));
     z0qg = z0hg;
     double zeta = zldis * VKC * GRAV * thvstar / (sq(p.ustar) * thv);
     if (zeta >= 0.0) {
@@ -64,7 +64,7 @@ ELMK_HD void column_bareground_fluxes(const Cols& S, const Tables&, const int c)
       um = dmax(ur, 0.1);
     } else {
       zeta = dmax(-100.0, dmin(zeta, -0.01));
-      const double wc = 1.0 * pow((-GRAV * p.ustar * thvstar * 1000.0 / thv), 0.333);
+      const double wc = 1.0 * m_pow((-GRAV * p.ustar * thvstar * 1000.0 / thv), 0.333);
       um = sqrt(ur * ur + wc * wc);
     }
     obu = zldis / zeta;

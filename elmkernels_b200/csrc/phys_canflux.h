@@ -46,15 +46,15 @@ ELMK_HD PsnPft load_psn_pft(const Cols& S, const int c)
 // temperature response functions
 ELMK_HD double psn_ft(const double tl, const double ha)
 {
-  return exp(ha / (RGAS * 1.0e-3 * (TFRZ + 25.0)) * (1.0 - (TFRZ + 25.0) / tl));
+  return m_exp(ha / (RGAS * 1.0e-3 * (TFRZ + 25.0)) * (1.0 - (TFRZ + 25.0) / tl));
 }
 ELMK_HD double psn_fth(const double tl, const double hd, const double se, const double scale)
 {
-  return scale / (1.0 + exp((-hd + se * tl) / (RGAS * 1.0e-3 * tl)));
+  return scale / (1.0 + m_exp((-hd + se * tl) / (RGAS * 1.0e-3 * tl)));
 }
 ELMK_HD double psn_fth25(const double hd, const double se)
 {
-  return 1.0 + exp((-hd + se * (TFRZ + 25.0)) / (RGAS * 1.0e-3 * (TFRZ + 25.0)));
+  return 1.0 + m_exp((-hd + se * (TFRZ + 25.0)) / (RGAS * 1.0e-3 * (TFRZ + 25.0)));
 }
 
 // roots of a x^2 + b x + c, numerically stable form; a == 0 is an error in the reference
@@ -85,7 +85,7 @@ struct LeafPsn {
 };
 
 // f(ci) = ci - (ca - (1.4/gb + 1.6/gs) p an)
-ELMK_HD double psn_ci_func(const double ci, LeafPsn& L, uint32_t& err)
+ELMK_HD_NOINLINE double psn_ci_func(const double ci, LeafPsn& L, uint32_t& err)
 {
   constexpr double theta_ip = 0.95;
   if (L.c3) {
@@ -228,7 +228,7 @@ ELMK_HD void psn_hybrid(double x0, LeafPsn& L, uint32_t& err)
 }
 
 // stomatal resistance of the sunlit or the shaded canopy fraction (nlevcan == 1, nrad == 1)
-ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const int nrad, const double pbot, const double t_veg,
+ELMK_HD_NOINLINE double psn_stomatal_resistance(const PsnPft& P, const int nrad, const double pbot, const double t_veg,
                                        const double t10, const double esat_tv, const double eair, const double oair,
                                        const double cair, const double rb, const double btran,
                                        const double dayl_factor, const double thm, const double vcmaxcint,
@@ -258,8 +258,8 @@ ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const int nrad, const do
     const double lmrc = psn_fth25(P.lmrhd, P.lmrse);
     lmr_z = lmr25 * psn_ft(t_veg, P.lmrha) * psn_fth(t_veg, P.lmrhd, P.lmrse, lmrc);
   } else {
-    lmr_z = lmr25 * pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
-    lmr_z /= (1.0 + exp(1.3 * (t_veg - (TFRZ + 55.0))));
+    lmr_z = lmr25 * m_pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
+    lmr_z /= (1.0 + m_exp(1.3 * (t_veg - (TFRZ + 55.0))));
   }
   double vcmax_z, jmax_z, tpu_z, kp_z;
   if (par <= 0.0) {
@@ -279,11 +279,11 @@ ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const int nrad, const do
     jmax_z = jmax25 * psn_ft(t_veg, P.jmaxha) * psn_fth(t_veg, P.jmaxhd, jmaxse, jmaxc);
     tpu_z = tpu25 * psn_ft(t_veg, P.tpuha) * psn_fth(t_veg, P.tpuhd, tpuse, tpuc);
     if (!c3) {
-      vcmax_z = vcmax25 * pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
-      vcmax_z /= (1.0 + exp(0.2 * ((TFRZ + 15.0) - t_veg)));
-      vcmax_z /= (1.0 + exp(0.3 * (t_veg - (TFRZ + 40.0))));
+      vcmax_z = vcmax25 * m_pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
+      vcmax_z /= (1.0 + m_exp(0.2 * ((TFRZ + 15.0) - t_veg)));
+      vcmax_z /= (1.0 + m_exp(0.3 * (t_veg - (TFRZ + 40.0))));
     }
-    kp_z = kp25 * pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
+    kp_z = kp25 * m_pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
   }
   vcmax_z *= btran;
   lmr_z *= btran;
@@ -328,8 +328,41 @@ ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const int nrad, const do
 }
 
 // ---- canopy fluxes --------------------------------------------------------------------------
+//
+// The group is written as three pieces around one explicit state object so that the CUDA library can
+// run the data-dependent stability iteration with warp-level re-packing (elmk_lib.cu, k_canflux_iterate):
+//   canflux_begin    initialize_flux (:95-181): moisture stress, canopy aerodynamics, first guess
+//   canflux_iterate  ONE pass of the stability_iteration loop body (:215-451); returns true when done
+//   canflux_end      compute_flux (:456-539) and the write-back
+// column_canopy_fluxes = begin; while (!iterate) ; end  - the reference's control flow, used by the host
+// port and by the one-launch-per-group plan.
 
-ELMK_HD void column_canopy_fluxes(const Cols& S, const Tables& T, const StepArgs& A, const int c)
+// doubles of the iteration state: per-column constants first, then the loop-carried values
+#define ELMK_CANFLUX_CONST(X)                                                                                     \
+  X(pbot) X(forc_q) X(forc_th) X(forc_lwrad) X(thm) X(thv) X(tg) X(qg) X(elai) X(esai) X(emv) X(emg) X(z0mg)     \
+  X(hgt_u) X(hgt_t) X(hgt_q) X(forc_po2) X(forc_pco2) X(forc_rho) X(dayl_factor) X(displa) X(z0mv) X(air) X(bir) \
+  X(cir) X(ur) X(zldis) X(fwet) X(fdry) X(laisun) X(laisha) X(snow_depth) X(soilbeta) X(fsno) X(fsfc) X(sabv)    \
+  X(htop) X(t10) X(h2ocan0) X(vcsha) X(vcsun) X(parsha) X(parsun) X(laisha_z) X(laisun_z) X(lw_grnd)             \
+  X(t_snotop) X(t_soil1) X(t_sfc) X(dtime)
+#define ELMK_CANFLUX_CARRIED(X)                                                                                   \
+  X(btran) X(t_veg) X(el) X(qsatl) X(qsatldT) X(taf) X(qaf) X(dth) X(dqh) X(delq) X(um) X(obu) X(obuold) X(del)  \
+  X(efeb) X(qflx_tran_veg) X(qflx_evap_veg) X(eflx_sh_veg) X(wtg) X(wtl0) X(wta0) X(wtal) X(wtgq) X(wtalq)       \
+  X(wtlq0) X(wtaq0) X(tlbef) X(dt_veg) X(p_ustar) X(p_temp1) X(p_temp2) X(p_temp12m) X(p_temp22m)
+#define ELMK_CANFLUX_INT(X) X(nrad) X(veg) X(soybean) X(itlef) X(nmozsgn) X(err)
+
+struct CanopyIter {
+#define X(n) double n;
+  ELMK_CANFLUX_CONST(X)
+  ELMK_CANFLUX_CARRIED(X)
+#undef X
+#define X(n) int n;
+  ELMK_CANFLUX_INT(X)
+#undef X
+};
+
+// Non-vegetated columns: initialize_flux (:121-131) and the unconditional zeroing of compute_flux.
+// Returns false when the column has no exposed vegetation (nothing else to do).
+ELMK_HD bool canflux_begin(const Cols& S, const Tables& T, const StepArgs& A, const PsnPft& P, const int c, CanopyIter& I)
 {
   // canopy_fluxes::compute_flux zeroes these for every column (:475-480) - including the bare
   // columns whose values kokkos_bareground_fluxes has just computed
@@ -340,34 +373,33 @@ ELMK_HD void column_canopy_fluxes(const Cols& S, const Tables& T, const StepArgs
   const int veg = C1(frac_veg_nosno);
   const double forc_t = C1(forc_tbot);
   if (veg == 0) {
-    // initialize_flux for non-vegetated columns (:121-131)
     C1(btran) = 0.0;
     C1(t_veg) = forc_t;
 #pragma unroll
     for (int i = 0; i < NLEVGRND; ++i) C2(rootr, i) = 0.0;
-    return;
+    return false;
   }
 
-  uint32_t err = 0;
-  const double dtime = A.dtime;
-  const PsnPft P = load_psn_pft(S, c);
+  I.err = 0;
+  I.veg = veg;
+  I.dtime = A.dtime;
   const int snl = C1(snl);
-  const double pbot = C1(forc_pbot), forc_q = C1(forc_qbot), forc_th = C1(forc_thbot);
-  const double forc_lwrad = C1(forc_lwrad);
-  const double thm = C1(thm), thv = C1(thv), tg = C1(t_grnd), qg = C1(qg);
-  const double elai = C1(elai), esai = C1(esai), emv = C1(emv), emg = C1(emg);
-  const double z0mg = C1(z0mg);
-  const double hgt_u = C1(forc_hgt_u_patch), hgt_t = C1(forc_hgt_t_patch), hgt_q = C1(forc_hgt_q_patch);
-  const double forc_po2 = O2_MOLAR_CONST * pbot;
-  const double forc_pco2 = CO2_PPMV * 1.0e-6 * pbot;
-  const double forc_rho = air_density(pbot, forc_q, forc_t);
+  I.pbot = C1(forc_pbot); I.forc_q = C1(forc_qbot); I.forc_th = C1(forc_thbot);
+  I.forc_lwrad = C1(forc_lwrad);
+  I.thm = C1(thm); I.thv = C1(thv); I.tg = C1(t_grnd); I.qg = C1(qg);
+  I.elai = C1(elai); I.esai = C1(esai); I.emv = C1(emv); I.emg = C1(emg);
+  I.z0mg = C1(z0mg);
+  I.hgt_u = C1(forc_hgt_u_patch); I.hgt_t = C1(forc_hgt_t_patch); I.hgt_q = C1(forc_hgt_q_patch);
+  I.forc_po2 = O2_MOLAR_CONST * I.pbot;
+  I.forc_pco2 = CO2_PPMV * 1.0e-6 * I.pbot;
+  I.forc_rho = air_density(I.pbot, I.forc_q, forc_t);
 
   // ---- initialize_flux (:133-181) ----
-  const double dayl_factor = dmin(1.0, dmax(0.01, (A.dayl * A.dayl) / (A.max_dayl * A.max_dayl)));
+  I.dayl_factor = dmin(1.0, dmax(0.01, (A.dayl * A.dayl) / (A.max_dayl * A.max_dayl)));
   // root-zone moisture stress: effective porosity, liquid volume, per-layer resistance
   double btran = 0.0;
   double rootr[NLEVGRND];
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < NLEVGRND; ++i) {
     const int k = NLEVSNO + i;
     const double watsat = C2(watsat, i), dzk = C2(dz, k);
@@ -379,261 +411,297 @@ ELMK_HD void column_canopy_fluxes(const Cols& S, const Tables& T, const StepArgs
       rootr[i] = 0.0;
     } else {
       const double s_node = dmax(liqvol / eff_por, 0.01);
-      double smp_node = -C2(sucsat, i) * pow(s_node, (-C2(bsw, i)));
+      double smp_node = -C2(sucsat, i) * m_pow(s_node, (-C2(bsw, i)));
       smp_node = dmax(P.smpsc, smp_node);
       const double rresis = dmin((eff_por / watsat) * (smp_node - P.smpsc) / (P.smpso - P.smpsc), 1.0);
       rootr[i] = C2(rootfr, i) * rresis;
       btran += dmax(rootr[i], 0.0);
     }
   }
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < NLEVGRND; ++i) {
     if (btran > 0.0) rootr[i] /= btran; else rootr[i] = 0.0;
     C2(rootr, i) = rootr[i];
   }
+  I.btran = btran;
 
   // sparse/dense canopy aerodynamic parameters
   double displa = C1(displa), z0mv = C1(z0mv);
-  const double lt = dmin(elai + esai, 2.0);
-  const double egvf = (1.0 - exp(-lt)) / (1.0 - exp(-2.0));
+  const double lt = dmin(I.elai + I.esai, 2.0);
+  const double egvf = (1.0 - m_exp(-lt)) / (1.0 - m_exp(-2.0));
   displa *= egvf;
-  z0mv = exp(egvf * log(z0mv) + (1.0 - egvf) * log(z0mg));
-  const double z0hv = z0mv, z0qv = z0mv;
+  z0mv = m_exp(egvf * m_log(z0mv) + (1.0 - egvf) * m_log(I.z0mg));
   C1(displa) = displa;
   C1(z0mv) = z0mv;
-  C1(z0hv) = z0hv;
-  C1(z0qv) = z0qv;
+  C1(z0hv) = z0mv;
+  C1(z0qv) = z0mv;
+  I.displa = displa;
+  I.z0mv = z0mv;
 
   // net absorbed longwave coefficients
-  const double air = emv * (1.0 + (1.0 - emv) * (1.0 - emg)) * forc_lwrad;
-  const double bir = -(2.0 - emv * (1.0 - emg)) * emv * STEBOL;
-  const double cir = emv * emg * STEBOL;
+  I.air = I.emv * (1.0 + (1.0 - I.emv) * (1.0 - I.emg)) * I.forc_lwrad;
+  I.bir = -(2.0 - I.emv * (1.0 - I.emg)) * I.emv * STEBOL;
+  I.cir = I.emv * I.emg * STEBOL;
 
-  double t_veg = C1(t_veg);
-  double el, deldT, qsatl, qsatldT;
-  qsat(t_veg, pbot, el, deldT, qsatl, qsatldT);
-  double taf = (tg + thm) / 2.0;
-  double qaf = (forc_q + qg) / 2.0;
+  I.t_veg = C1(t_veg);
+  double deldT;
+  qsat(I.t_veg, I.pbot, I.el, deldT, I.qsatl, I.qsatldT);
+  I.taf = (I.tg + I.thm) / 2.0;
+  I.qaf = (I.forc_q + I.qg) / 2.0;
   const double fu = C1(forc_u), fv = C1(forc_v);
-  const double ur = dmax(1.0, sqrt(fu * fu + fv * fv));
-  double dth = thm - taf;
-  double dqh = forc_q - qaf;
-  double delq = qg - qaf;
-  const double dthv = dth * (1.0 + 0.61 * forc_q) + 0.61 * forc_th * dqh;
-  const double zldis = hgt_u - displa;
-  if (!(zldis >= 0.0)) err |= ERR_FORC_HEIGHT;
-  double um, obu;
-  mo_initial_length(ur, thv, dthv, zldis, z0mv, um, obu);
+  I.ur = dmax(1.0, sqrt(fu * fu + fv * fv));
+  I.dth = I.thm - I.taf;
+  I.dqh = I.forc_q - I.qaf;
+  I.delq = I.qg - I.qaf;
+  const double dthv = I.dth * (1.0 + 0.61 * I.forc_q) + 0.61 * I.forc_th * I.dqh;
+  I.zldis = I.hgt_u - displa;
+  if (!(I.zldis >= 0.0)) I.err |= ERR_FORC_HEIGHT;
+  mo_initial_length(I.ur, I.thv, dthv, I.zldis, z0mv, I.um, I.obu);
 
-  // ---- stability_iteration (:215-451) ----
-  const double fwet = C1(fwet), fdry = C1(fdry), laisun = C1(laisun), laisha = C1(laisha);
-  const double snow_depth = C1(snow_depth), soilbeta = C1(soilbeta);
-  const double fsno = C1(frac_sno), fsfc = C1(frac_h2osfc), t_sfc = C1(t_h2osfc);
-  const double sabv = C1(sabv), htop = C1(htop), t10 = C1(t10);
-  const double h2ocan0 = C1(h2ocan);
-  const int nrad = C1(nrad);
-  const double vcsha = C1(vcmaxcintsha), vcsun = C1(vcmaxcintsun);
-  const double parsha = C2(parsha_z, 0), parsun = C2(parsun_z, 0);
-  const double laisha_z = C2(laisha_z, 0), laisun_z = C2(laisun_z, 0);
-  const double t_snotop = C2(t_soisno, NLEVSNO - snl), t_soil1 = C2(t_soisno, NLEVSNO);
-  const bool soybean = (T.vtype == PFT_SOYBEAN || T.vtype == PFT_SOYBEAN_IRRIG);
+  // ---- loop-invariant inputs of stability_iteration (:215-451) ----
+  I.fwet = C1(fwet); I.fdry = C1(fdry); I.laisun = C1(laisun); I.laisha = C1(laisha);
+  I.snow_depth = C1(snow_depth); I.soilbeta = C1(soilbeta);
+  I.fsno = C1(frac_sno); I.fsfc = C1(frac_h2osfc); I.t_sfc = C1(t_h2osfc);
+  I.sabv = C1(sabv); I.htop = C1(htop); I.t10 = C1(t10);
+  I.h2ocan0 = C1(h2ocan);
+  I.nrad = C1(nrad);
+  I.vcsha = C1(vcmaxcintsha); I.vcsun = C1(vcmaxcintsun);
+  I.parsha = C2(parsha_z, 0); I.parsun = C2(parsun_z, 0);
+  I.laisha_z = C2(laisha_z, 0); I.laisun_z = C2(laisun_z, 0);
+  I.t_snotop = C2(t_soisno, NLEVSNO - snl); I.t_soil1 = C2(t_soisno, NLEVSNO);
+  I.soybean = (T.vtype == PFT_SOYBEAN || T.vtype == PFT_SOYBEAN_IRRIG) ? 1 : 0;
   // ground-emitted longwave does not change during the iteration
-  const double lw_grnd = (fsno * pow4(t_snotop) + (1.0 - fsno - fsfc) * pow4(t_soil1) + fsfc * pow4(t_sfc));
+  I.lw_grnd = (I.fsno * pow4(I.t_snotop) + (1.0 - I.fsno - I.fsfc) * pow4(I.t_soil1) + I.fsfc * pow4(I.t_sfc));
 
+  I.itlef = 0; I.nmozsgn = 0;
+  I.del = 0.0; I.efeb = 0.0; I.obuold = 0.0;
+  I.qflx_tran_veg = C1(qflx_tran_veg); I.qflx_evap_veg = C1(qflx_evap_veg); I.eflx_sh_veg = C1(eflx_sh_veg);
+  I.wtg = 0.0; I.wtl0 = 0.0; I.wta0 = 0.0; I.wtal = 0.0; I.wtgq = 0.0; I.wtalq = 0.0; I.wtlq0 = 0.0; I.wtaq0 = 0.0;
+  I.tlbef = 0.0; I.dt_veg = 0.0;
+  I.p_ustar = 0.0; I.p_temp1 = 0.0; I.p_temp2 = 0.0; I.p_temp12m = 0.0; I.p_temp22m = 0.0;
+  return true;
+}
+
+// One pass of the stability iteration.  Returns true when the loop of the reference would end
+// (converged, or 41 passes done).
+ELMK_HD bool canflux_iterate(const PsnPft& P, CanopyIter& I)
+{
   constexpr double ria = 0.5, dlemin = 0.1, dtmin = 0.01;
   constexpr int itmax = 40, itmin = 2;
-  bool stop = false;
-  int itlef = 0, nmozsgn = 0;
-  double del = 0.0, efeb = 0.0, obuold = 0.0;
-  double qflx_tran_veg = C1(qflx_tran_veg), qflx_evap_veg = C1(qflx_evap_veg), eflx_sh_veg = C1(eflx_sh_veg);
-  double wtg = 0.0, wtl0 = 0.0, wta0 = 0.0, wtal = 0.0, wtgq = 0.0, wtalq = 0.0, wtlq0 = 0.0, wtaq0 = 0.0;
-  double tlbef = 0.0, dt_veg = 0.0;
-  MoProfiles p;
-  p.ustar = 0.0; p.temp1 = 0.0; p.temp2 = 0.0; p.temp12m = 0.0; p.temp22m = 0.0;
+  uint32_t err = (uint32_t)I.err;
+  const double elai = I.elai, esai = I.esai, forc_q = I.forc_q, pbot = I.pbot, thm = I.thm, tg = I.tg, qg = I.qg;
+  const double forc_rho = I.forc_rho, dtime = I.dtime, h2ocan0 = I.h2ocan0;
+  const int veg = I.veg;
 
-#pragma unroll 1
-  while (itlef <= itmax && !stop) {
-    p = mo_profiles(hgt_u, hgt_t, hgt_q, displa, um, obu, z0mv, z0hv, z0qv);
-    tlbef = t_veg;
-    const double del2 = del;
-    const double ram = 1.0 / (p.ustar * p.ustar / um);
-    const double rah0 = 1.0 / (p.temp1 * p.ustar);
-    const double raw0 = 1.0 / (p.temp2 * p.ustar);
-    const double uaf = um * sqrt(1.0 / (ram * um));
-    const double cf = 0.01 / (sqrt(uaf) * sqrt(P.dleaf));
-    const double rb = 1.0 / (cf * uaf);
-    const double w = exp(-(elai + esai));
-    const double csoilb = (VKC / (0.13 * pow((z0mg * uaf / 1.5e-5), 0.45)));
-    const double ri = (GRAV * htop * (taf - tg)) / (taf * sq(uaf));
-    double csoilcn;
-    if ((taf - tg) > 0.0) {
-      const double ricsoilc = CSOILC / (1.0 + ria * dmin(ri, 10.0));
-      csoilcn = csoilb * w + ricsoilc * (1.0 - w);
-    } else {
-      csoilcn = csoilb * w + CSOILC * (1.0 - w);
-    }
-    const double rah1 = 1.0 / (csoilcn * uaf);
-    const double raw1 = rah1;
-    const double svpts = el;
-    const double eah = pbot * qaf / 0.622;
+  const MoProfiles p = mo_profiles(I.hgt_u, I.hgt_t, I.hgt_q, I.displa, I.um, I.obu, I.z0mv, I.z0mv, I.z0mv);
+  I.p_ustar = p.ustar; I.p_temp1 = p.temp1; I.p_temp2 = p.temp2; I.p_temp12m = p.temp12m; I.p_temp22m = p.temp22m;
+  double t_veg = I.t_veg;
+  const double tlbef = t_veg;
+  I.tlbef = tlbef;
+  const double del2 = I.del;
+  const double ram = 1.0 / (p.ustar * p.ustar / I.um);
+  const double rah0 = 1.0 / (p.temp1 * p.ustar);
+  const double raw0 = 1.0 / (p.temp2 * p.ustar);
+  const double uaf = I.um * sqrt(1.0 / (ram * I.um));
+  const double cf = 0.01 / (sqrt(uaf) * sqrt(P.dleaf));
+  const double rb = 1.0 / (cf * uaf);
+  const double w = m_exp(-(elai + esai));
+  const double csoilb = (VKC / (0.13 * m_pow((I.z0mg * uaf / 1.5e-5), 0.45)));
+  const double ri = (GRAV * I.htop * (I.taf - tg)) / (I.taf * sq(uaf));
+  double csoilcn;
+  if ((I.taf - tg) > 0.0) {
+    const double ricsoilc = CSOILC / (1.0 + ria * dmin(ri, 10.0));
+    csoilcn = csoilb * w + ricsoilc * (1.0 - w);
+  } else {
+    csoilcn = csoilb * w + CSOILC * (1.0 - w);
+  }
+  const double rah1 = 1.0 / (csoilcn * uaf);
+  const double raw1 = rah1;
+  const double svpts = I.el;
+  const double eah = pbot * I.qaf / 0.622;
 
-    if (soybean) btran = dmin(1.0, btran * 1.25);
-    const double rssun = psn_stomatal_resistance(P, nrad, pbot, t_veg, t10, svpts, eah, forc_po2, forc_pco2, rb, btran,
-                                                 dayl_factor, thm, vcsun, parsun, laisun_z, err);
-    if (soybean) btran = dmin(1.0, btran * 1.25);
-    const double rssha = psn_stomatal_resistance(P, nrad, pbot, t_veg, t10, svpts, eah, forc_po2, forc_pco2, rb, btran,
-                                                 dayl_factor, thm, vcsha, parsha, laisha_z, err);
+  double btran = I.btran;
+  if (I.soybean) btran = dmin(1.0, btran * 1.25);
+  const double rssun = psn_stomatal_resistance(P, I.nrad, pbot, t_veg, I.t10, svpts, eah, I.forc_po2, I.forc_pco2, rb, btran,
+                                               I.dayl_factor, thm, I.vcsun, I.parsun, I.laisun_z, err);
+  if (I.soybean) btran = dmin(1.0, btran * 1.25);
+  const double rssha = psn_stomatal_resistance(P, I.nrad, pbot, t_veg, I.t10, svpts, eah, I.forc_po2, I.forc_pco2, rb, btran,
+                                               I.dayl_factor, thm, I.vcsha, I.parsha, I.laisha_z, err);
+  I.btran = btran;
 
-    // sensible-heat conductances: air, leaf, ground
-    const double wta = 1.0 / rah0;
-    const double wtl = (elai + esai) / rb;
-    wtg = 1.0 / rah1;
-    const double wtshi = 1.0 / (wta + wtl + wtg);
-    wtl0 = wtl * wtshi;
-    const double wtg0 = wtg * wtshi;
-    wta0 = wta * wtshi;
-    const double wtga = wta0 + wtg0;
-    wtal = wta0 + wtl0;
+  // sensible-heat conductances: air, leaf, ground
+  const double wta = 1.0 / rah0;
+  const double wtl = (elai + esai) / rb;
+  const double wtg = 1.0 / rah1;
+  const double wtshi = 1.0 / (wta + wtl + wtg);
+  const double wtl0 = wtl * wtshi;
+  const double wtg0 = wtg * wtshi;
+  const double wta0 = wta * wtshi;
+  const double wtga = wta0 + wtg0;
+  I.wtg = wtg; I.wtl0 = wtl0; I.wta0 = wta0;
+  I.wtal = wta0 + wtl0;
 
-    // fraction of potential evaporation from the leaf
-    double rppdry;
-    if (fdry > 0.0) {
-      rppdry = fdry * rb * (laisun / (rb + rssun) + laisha / (rb + rssha)) / elai;
-    } else {
-      rppdry = 0.0;
-    }
-    double efpot = forc_rho * wtl * (qsatl - qaf);
-    double rpp;
-    if (efpot > 0.0) {
-      if (btran > 0.0) {
-        qflx_tran_veg = efpot * rppdry;
-        rpp = rppdry + fwet;
-      } else {
-        rpp = fwet;
-        qflx_tran_veg = 0.0;
-      }
-      rpp = dmin(rpp, (qflx_tran_veg + h2ocan0 / dtime) / efpot);
-    } else {
-      rpp = 1.0;
-      qflx_tran_veg = 0.0;
-    }
-
-    // latent-heat conductances, with the dry-litter layer resistance
-    const double wtaq = veg / raw0;
-    const double wtlq = veg * (elai + esai) / rb * rpp;
-    const double fsno_dl = snow_depth / 0.05;
-    const double elai_dl = 0.5 * (1.0 - dmin(fsno_dl, 1.0));
-    const double rdl = (1.0 - exp(-elai_dl)) / (0.004 * uaf);
-    if (delq < 0.0) {
-      wtgq = veg / (raw1 + rdl);
-    } else {
-      wtgq = soilbeta * veg / (raw1 + rdl);
-    }
-    const double wtsqi = 1.0 / (wtaq + wtlq + wtgq);
-    const double wtgq0 = wtgq * wtsqi;
-    wtlq0 = wtlq * wtsqi;
-    wtaq0 = wtaq * wtsqi;
-    const double wtgaq = wtaq0 + wtgq0;
-    wtalq = wtaq0 + wtlq0;
-    const double dc1 = forc_rho * CPAIR * wtl;
-    const double dc2 = HVAP * forc_rho * wtlq;
-    const double efsh = dc1 * (wtga * t_veg - wtg0 * tg - wta0 * thm);
-    double efe = dc2 * (wtgaq * qsatl - wtgq0 * qg - wtaq0 * forc_q);
-    double erre = 0.0;
-    if ((efe * efeb) < 0.0) {
-      const double efeold = efe;
-      efe = 0.1 * efeold;
-      erre = efe - efeold;
-    }
-
-    // leaf energy balance: Newton step on t_veg, limited to 1 K per iteration
-    dt_veg = (sabv + air + bir * pow4(t_veg) + cir * lw_grnd - efsh - efe) /
-             (-4.0 * bir * cube(t_veg) + dc1 * wtga + dc2 * wtgaq * qsatldT);
-    t_veg = tlbef + dt_veg;
-    const double dels = dt_veg;
-    del = fabs(dels);
-    double errb = 0.0;
-    if (del > 1.0) {
-      dt_veg = dels / del;
-      t_veg = tlbef + dt_veg;
-      errb = sabv + air + bir * cube(tlbef) * (tlbef + 4.0 * dt_veg) + cir * lw_grnd - (efsh + dc1 * wtga * dt_veg) -
-             (efe + dc2 * wtgaq * qsatldT * dt_veg);
-    }
-
-    // fluxes from leaves to canopy air
-    efpot = forc_rho * wtl * (wtgaq * (qsatl + qsatldT * dt_veg) - wtgq0 * qg - wtaq0 * forc_q);
-    qflx_evap_veg = rpp * efpot;
-    if (efpot > 0.0 && btran > 0.0) {
+  // fraction of potential evaporation from the leaf
+  double rppdry;
+  if (I.fdry > 0.0) {
+    rppdry = I.fdry * rb * (I.laisun / (rb + rssun) + I.laisha / (rb + rssha)) / elai;
+  } else {
+    rppdry = 0.0;
+  }
+  double efpot = forc_rho * wtl * (I.qsatl - I.qaf);
+  double rpp;
+  double qflx_tran_veg;
+  if (efpot > 0.0) {
+    if (btran > 0.0) {
       qflx_tran_veg = efpot * rppdry;
+      rpp = rppdry + I.fwet;
     } else {
+      rpp = I.fwet;
       qflx_tran_veg = 0.0;
     }
-    const double ecidif = dmax(0.0, qflx_evap_veg - qflx_tran_veg - h2ocan0 / dtime);
-    qflx_evap_veg = dmin(qflx_evap_veg, qflx_tran_veg + h2ocan0 / dtime);
-    eflx_sh_veg = efsh + dc1 * wtga * dt_veg + errb + erre + HVAP * ecidif;
-    qsat(t_veg, pbot, el, deldT, qsatl, qsatldT);
-
-    // canopy air state and Monin-Obukhov length for the next pass
-    taf = wtg0 * tg + wta0 * thm + wtl0 * t_veg;
-    qaf = wtlq0 * qsatl + wtgq0 * qg + forc_q * wtaq0;
-    dth = thm - taf;
-    dqh = forc_q - qaf;
-    delq = wtalq * qg - wtlq0 * qsatl - wtaq0 * forc_q;
-    const double tstar = p.temp1 * dth;
-    const double qstar = p.temp2 * dqh;
-    const double thvstar = tstar * (1.0 + 0.61 * forc_q) + 0.61 * forc_th * qstar;
-    double zeta = zldis * VKC * GRAV * thvstar / (sq(p.ustar) * thv);
-    if (zeta >= 0.0) {
-      zeta = dmin(2.0, dmax(zeta, 0.01));
-      um = dmax(ur, 0.1);
-    } else {
-      zeta = dmax(-100.0, dmin(zeta, -0.01));
-      const double wc = 1.0 * pow((-GRAV * p.ustar * thvstar * 1000.0 / thv), 0.333);
-      um = sqrt(ur * ur + wc * wc);
-    }
-    obu = zldis / zeta;
-    if (obuold * obu < 0.0) nmozsgn += 1;
-    if (nmozsgn >= 4) obu = zldis / (-0.01);
-    obuold = obu;
-
-    // convergence: at least three passes, leaf temperature within 0.01 K twice in a row and the
-    // latent heat flux within 0.1 W/m2
-    itlef += 1;
-    if (itlef > itmin) {
-      const double dele = fabs(efe - efeb);
-      efeb = efe;
-      const double det = dmax(del, del2);
-      if ((det < dtmin) && (dele < dlemin)) stop = true;
-    }
+    rpp = dmin(rpp, (qflx_tran_veg + h2ocan0 / dtime) / efpot);
+  } else {
+    rpp = 1.0;
+    qflx_tran_veg = 0.0;
   }
 
-  C1(btran) = btran;
-  C1(t_veg) = t_veg;
-  C1(qflx_tran_veg) = qflx_tran_veg;
-  C1(qflx_evap_veg) = qflx_evap_veg;
-  C1(eflx_sh_veg) = eflx_sh_veg;
+  // latent-heat conductances, with the dry-litter layer resistance
+  const double wtaq = veg / raw0;
+  const double wtlq = veg * (elai + esai) / rb * rpp;
+  const double fsno_dl = I.snow_depth / 0.05;
+  const double elai_dl = 0.5 * (1.0 - dmin(fsno_dl, 1.0));
+  const double rdl = (1.0 - m_exp(-elai_dl)) / (0.004 * uaf);
+  double wtgq;
+  if (I.delq < 0.0) {
+    wtgq = veg / (raw1 + rdl);
+  } else {
+    wtgq = I.soilbeta * veg / (raw1 + rdl);
+  }
+  const double wtsqi = 1.0 / (wtaq + wtlq + wtgq);
+  const double wtgq0 = wtgq * wtsqi;
+  const double wtlq0 = wtlq * wtsqi;
+  const double wtaq0 = wtaq * wtsqi;
+  const double wtgaq = wtaq0 + wtgq0;
+  I.wtgq = wtgq; I.wtlq0 = wtlq0; I.wtaq0 = wtaq0;
+  I.wtalq = wtaq0 + wtlq0;
+  const double dc1 = forc_rho * CPAIR * wtl;
+  const double dc2 = HVAP * forc_rho * wtlq;
+  const double efsh = dc1 * (wtga * t_veg - wtg0 * tg - wta0 * thm);
+  double efe = dc2 * (wtgaq * I.qsatl - wtgq0 * qg - wtaq0 * forc_q);
+  double erre = 0.0;
+  if ((efe * I.efeb) < 0.0) {
+    const double efeold = efe;
+    efe = 0.1 * efeold;
+    erre = efe - efeold;
+  }
 
-  // ---- compute_flux (:482-539) ----
+  // leaf energy balance: Newton step on t_veg, limited to 1 K per iteration
+  double dt_veg = (I.sabv + I.air + I.bir * pow4(t_veg) + I.cir * I.lw_grnd - efsh - efe) /
+                  (-4.0 * I.bir * cube(t_veg) + dc1 * wtga + dc2 * wtgaq * I.qsatldT);
+  t_veg = tlbef + dt_veg;
+  const double dels = dt_veg;
+  const double del = fabs(dels);
+  I.del = del;
+  double errb = 0.0;
+  if (del > 1.0) {
+    dt_veg = dels / del;
+    t_veg = tlbef + dt_veg;
+    errb = I.sabv + I.air + I.bir * cube(tlbef) * (tlbef + 4.0 * dt_veg) + I.cir * I.lw_grnd - (efsh + dc1 * wtga * dt_veg) -
+           (efe + dc2 * wtgaq * I.qsatldT * dt_veg);
+  }
+  I.dt_veg = dt_veg;
+
+  // fluxes from leaves to canopy air
+  efpot = forc_rho * wtl * (wtgaq * (I.qsatl + I.qsatldT * dt_veg) - wtgq0 * qg - wtaq0 * forc_q);
+  double qflx_evap_veg = rpp * efpot;
+  if (efpot > 0.0 && btran > 0.0) {
+    qflx_tran_veg = efpot * rppdry;
+  } else {
+    qflx_tran_veg = 0.0;
+  }
+  const double ecidif = dmax(0.0, qflx_evap_veg - qflx_tran_veg - h2ocan0 / dtime);
+  qflx_evap_veg = dmin(qflx_evap_veg, qflx_tran_veg + h2ocan0 / dtime);
+  I.qflx_tran_veg = qflx_tran_veg;
+  I.qflx_evap_veg = qflx_evap_veg;
+  I.eflx_sh_veg = efsh + dc1 * wtga * dt_veg + errb + erre + HVAP * ecidif;
+  double deldT;
+  qsat(t_veg, pbot, I.el, deldT, I.qsatl, I.qsatldT);
+  I.t_veg = t_veg;
+
+  // canopy air state and Monin-Obukhov length for the next pass
+  I.taf = wtg0 * tg + wta0 * thm + wtl0 * t_veg;
+  I.qaf = wtlq0 * I.qsatl + wtgq0 * qg + forc_q * wtaq0;
+  I.dth = thm - I.taf;
+  I.dqh = forc_q - I.qaf;
+  I.delq = I.wtalq * qg - wtlq0 * I.qsatl - wtaq0 * forc_q;
+  const double tstar = p.temp1 * I.dth;
+  const double qstar = p.temp2 * I.dqh;
+  const double thvstar = tstar * (1.0 + 0.61 * forc_q) + 0.61 * I.forc_th * qstar;
+  double zeta = I.zldis * VKC * GRAV * thvstar / (sq(p.ustar) * I.thv);
+  if (zeta >= 0.0) {
+    zeta = dmin(2.0, dmax(zeta, 0.01));
+    I.um = dmax(I.ur, 0.1);
+  } else {
+    zeta = dmax(-100.0, dmin(zeta, -0.01));
+    const double wc = 1.0 * m_pow((-GRAV * p.ustar * thvstar * 1000.0 / I.thv), 0.333);
+    I.um = sqrt(I.ur * I.ur + wc * wc);
+  }
+  double obu = I.zldis / zeta;
+  if (I.obuold * obu < 0.0) I.nmozsgn += 1;
+  if (I.nmozsgn >= 4) obu = I.zldis / (-0.01);
+  I.obu = obu;
+  I.obuold = obu;
+  I.err = (int)err;
+
+  // convergence: at least three passes, leaf temperature within 0.01 K twice in a row and the
+  // latent heat flux within 0.1 W/m2
+  bool stop = false;
+  I.itlef += 1;
+  if (I.itlef > itmin) {
+    const double dele = fabs(efe - I.efeb);
+    I.efeb = efe;
+    const double det = dmax(del, del2);
+    if ((det < dtmin) && (dele < dlemin)) stop = true;
+  }
+  return stop || !(I.itlef <= itmax);
+}
+
+// compute_flux (:482-539) and the write-back of the iteration results
+ELMK_HD void canflux_end(const Cols& S, const int c, const CanopyIter& I)
+{
+  const double t_veg = I.t_veg, thm = I.thm, tg = I.tg, forc_q = I.forc_q, forc_rho = I.forc_rho;
+  const double wtg = I.wtg, wtl0 = I.wtl0, wta0 = I.wta0, wtal = I.wtal, wtgq = I.wtgq, wtalq = I.wtalq,
+               wtlq0 = I.wtlq0, wtaq0 = I.wtaq0, qsatl = I.qsatl;
+  const double emv = I.emv, emg = I.emg, forc_lwrad = I.forc_lwrad, tlbef = I.tlbef, dt_veg = I.dt_veg;
+#ifdef ELMK_DEBUG_ITER
+  C1(altmax_lastyear_indx) = I.itlef;   // development aid: outer iteration count into a field the chain never reads
+#endif
+  C1(btran) = I.btran;
+  C1(t_veg) = t_veg;
+  C1(qflx_tran_veg) = I.qflx_tran_veg;
+  C1(qflx_evap_veg) = I.qflx_evap_veg;
+  C1(eflx_sh_veg) = I.eflx_sh_veg;
+
   const double htvp = C1(htvp);
   const double delt = wtal * tg - wtl0 * t_veg - wta0 * thm;
   C1(eflx_sh_grnd) = CPAIR * forc_rho * wtg * delt;
-  const double delt_snow = wtal * t_snotop - wtl0 * t_veg - wta0 * thm;
+  const double delt_snow = wtal * I.t_snotop - wtl0 * t_veg - wta0 * thm;
   C1(eflx_sh_snow) = CPAIR * forc_rho * wtg * delt_snow;
-  const double delt_soil = wtal * t_soil1 - wtl0 * t_veg - wta0 * thm;
+  const double delt_soil = wtal * I.t_soil1 - wtl0 * t_veg - wta0 * thm;
   C1(eflx_sh_soil) = CPAIR * forc_rho * wtg * delt_soil;
-  const double delt_h2osfc = wtal * t_sfc - wtl0 * t_veg - wta0 * thm;
+  const double delt_h2osfc = wtal * I.t_sfc - wtl0 * t_veg - wta0 * thm;
   C1(eflx_sh_h2osfc) = CPAIR * forc_rho * wtg * delt_h2osfc;
-  C1(qflx_evap_soi) = forc_rho * wtgq * delq;
+  C1(qflx_evap_soi) = forc_rho * wtgq * I.delq;
   const double delq_snow = wtalq * C1(qg_snow) - wtlq0 * qsatl - wtaq0 * forc_q;
   C1(qflx_ev_snow) = forc_rho * wtgq * delq_snow;
   const double delq_soil = wtalq * C1(qg_soil) - wtlq0 * qsatl - wtaq0 * forc_q;
   C1(qflx_ev_soil) = forc_rho * wtgq * delq_soil;
   const double delq_h2osfc = wtalq * C1(qg_h2osfc) - wtlq0 * qsatl - wtaq0 * forc_q;
   C1(qflx_ev_h2osfc) = forc_rho * wtgq * delq_h2osfc;
-  const double t_ref2m = thm + p.temp1 * dth * (1.0 / p.temp12m - 1.0 / p.temp1);
-  const double q_ref2m = forc_q + p.temp2 * dqh * (1.0 / p.temp22m - 1.0 / p.temp2);
+  const double t_ref2m = thm + I.p_temp1 * I.dth * (1.0 / I.p_temp12m - 1.0 / I.p_temp1);
+  const double q_ref2m = forc_q + I.p_temp2 * I.dqh * (1.0 / I.p_temp22m - 1.0 / I.p_temp2);
   double e2m, de2m, qsat2m, dqsat2m;
-  qsat(t_ref2m, pbot, e2m, de2m, qsat2m, dqsat2m);
+  qsat(t_ref2m, I.pbot, e2m, de2m, qsat2m, dqsat2m);
   C1(t_ref2m) = t_ref2m;
   C1(q_ref2m) = q_ref2m;
   C1(rh_ref2m) = dmin(100.0, (q_ref2m / qsat2m) * 100.0);
@@ -641,15 +709,26 @@ ELMK_HD void column_canopy_fluxes(const Cols& S, const Tables& T, const StepArgs
   C1(dlrad) = (1.0 - emv) * emg * forc_lwrad + emv * emg * STEBOL * cube(tlbef) * (tlbef + 4.0 * dt_veg);
   C1(ulrad) = ((1.0 - emg) * (1.0 - emv) * (1.0 - emv) * forc_lwrad +
                emv * (1.0 + (1.0 - emg) * (1.0 - emv)) * STEBOL * cube(tlbef) * (tlbef + 4.0 * dt_veg) +
-               emg * (1.0 - emv) * STEBOL * lw_grnd);
+               emg * (1.0 - emv) * STEBOL * I.lw_grnd);
   double cgrnds = 0.0, cgrndl = 0.0;
   cgrnds += CPAIR * forc_rho * wtg * wtal;
   cgrndl += forc_rho * wtgq * wtalq * C1(dqgdT);
   C1(cgrnds) = cgrnds;
   C1(cgrndl) = cgrndl;
   C1(cgrnd) = cgrnds + cgrndl * htvp;
-  C1(h2ocan) = dmax(0.0, h2ocan0 + (qflx_tran_veg - qflx_evap_veg) * dtime);
-  if (err) C1(errmask) |= (int)err;
+  C1(h2ocan) = dmax(0.0, I.h2ocan0 + (I.qflx_tran_veg - I.qflx_evap_veg) * I.dtime);
+  if (I.err) C1(errmask) |= I.err;
+}
+
+ELMK_HD void column_canopy_fluxes(const Cols& S, const Tables& T, const StepArgs& A, const int c)
+{
+  const PsnPft P = load_psn_pft(S, c);
+  CanopyIter I;
+  if (!canflux_begin(S, T, A, P, c, I)) return;
+#pragma unroll 1
+  while (!canflux_iterate(P, I)) {
+  }
+  canflux_end(S, c, I);
 }
 
 } // namespace elmk

@@ -16,7 +16,7 @@ namespace elmk {
 
 // Saturation vapour pressure es [Pa], specific humidity qs [kg/kg] and their temperature
 // derivatives: 8th-order polynomials over water (0..100 C) and over ice (-75..0 C), Horner form.
-ELMK_HD void qsat(const double T, const double p, double& es, double& esdT, double& qs, double& qsdT)
+ELMK_HD_NOINLINE void qsat(const double T, const double p, double& es, double& esdT, double& qs, double& qsdT)
 {
   double td = T - TFRZ;
   if (td > 100.0) td = 100.0;
@@ -71,9 +71,9 @@ ELMK_HD void column_canopy_temperature(const Cols& S, const Tables& T, const int
   const double wx = (liq1 / DENH2O + ice1 / DENICE) / dz1;
   double fac = dmin(1.0, wx / watsat1);
   fac = dmax(fac, 0.01);
-  double psit = -C2(sucsat, 0) * pow(fac, (-C2(bsw, 0)));
+  double psit = -C2(sucsat, 0) * m_pow(fac, (-C2(bsw, 0)));
   psit = dmax(-1.e8, psit);
-  const double hr = exp(psit / ROVERG / t_soil1);
+  const double hr = m_exp(psit / ROVERG / t_soil1);
   // qred = (1 - fsno - fsfc) hr + fsno + fsfc is computed by the reference but only feeds soilalpha (unused)
 
   const double watfc1 = C2(watfc, 0);
@@ -81,7 +81,7 @@ ELMK_HD void column_canopy_temperature(const Cols& S, const Tables& T, const int
   if (wx < watfc1) {
     double fac_fc = dmin(1.0, wx / watfc1);
     fac_fc = dmax(fac_fc, 0.01);
-    soilbeta = (1.0 - fsno - fsfc) * 0.25 * sq(1.0 - cos(PI * fac_fc)) + fsno + fsfc;
+    soilbeta = (1.0 - fsno - fsfc) * 0.25 * sq(1.0 - m_cos(PI * fac_fc)) + fsno + fsfc;
   } else {
     soilbeta = 1.0;
   }
@@ -117,7 +117,7 @@ ELMK_HD void column_canopy_temperature(const Cols& S, const Tables& T, const int
   // -- ground_properties --
   const double lsai = C1(elai) + C1(esai);
   C1(emg) = (1.0 - fsno) * 0.96 + fsno * 0.97;
-  C1(emv) = 1.0 - exp(-lsai / 1.0);
+  C1(emv) = 1.0 - m_exp(-lsai / 1.0);
   double htvp = HVAP;
   if (C2(h2osoi_liq, top) <= 0 && C2(h2osoi_ice, top) > 0.0) htvp = HSUB;
   C1(htvp) = htvp;

@@ -15,13 +15,13 @@ ELMK_HD double mo_psi_m(const double zeta)   // wind-profile stability correctio
 {
   const double chik2 = sqrt(1.0 - 16.0 * zeta);
   const double chik = sqrt(chik2);
-  return 2.0 * log((1.0 + chik) * 0.5) + log((1.0 + chik2) * 0.5) - 2.0 * atan(chik) + PI * 0.5;
+  return 2.0 * m_log((1.0 + chik) * 0.5) + m_log((1.0 + chik2) * 0.5) - 2.0 * m_atan(chik) + PI * 0.5;
 }
 
 ELMK_HD double mo_psi_h(const double zeta)   // scalar-profile stability correction, unstable branch
 {
   const double chik2 = sqrt(1.0 - 16.0 * zeta);
-  return 2.0 * log((1.0 + chik2) * 0.5);
+  return 2.0 * m_log((1.0 + chik2) * 0.5);
 }
 
 // initial Monin-Obukhov length and wind speed from the bulk Richardson number
@@ -37,50 +37,50 @@ ELMK_HD void mo_initial_length(const double ur, const double thv, const double d
   const double rib = GRAV * zldis * dthv / (thv * um * um);
   double zeta;
   if (rib >= 0.0) {
-    zeta = rib * log(zldis / z0m) / (1.0 - 5.0 * dmin(rib, 0.19));
+    zeta = rib * m_log(zldis / z0m) / (1.0 - 5.0 * dmin(rib, 0.19));
     zeta = dmin(2.0, dmax(zeta, 0.01));
   } else {
-    zeta = rib * log(zldis / z0m);
+    zeta = rib * m_log(zldis / z0m);
     zeta = dmax(-100.0, dmin(zeta, -0.01));
   }
   obu = zldis / zeta;
 }
 
-ELMK_HD double mo_ustar(const double forc_hgt_u, const double displa, const double um, const double obu,
+ELMK_HD_NOINLINE double mo_ustar(const double forc_hgt_u, const double displa, const double um, const double obu,
                         const double z0m)
 {
   constexpr double zetam = 1.574;
   const double zldis = forc_hgt_u - displa;
   const double zeta = zldis / obu;
   if (zeta < (-zetam)) {
-    return VKC * um / (log(-zetam * obu / z0m) - mo_psi_m(-zetam) + mo_psi_m(z0m / obu) +
-                       1.14 * (pow((-zeta), 0.333) - pow(zetam, 0.333)));
+    return VKC * um / (m_log(-zetam * obu / z0m) - mo_psi_m(-zetam) + mo_psi_m(z0m / obu) +
+                       1.14 * (m_pow((-zeta), 0.333) - m_pow(zetam, 0.333)));
   } else if (zeta < 0.0) {
-    return VKC * um / (log(zldis / z0m) - mo_psi_m(zeta) + mo_psi_m(z0m / obu));
+    return VKC * um / (m_log(zldis / z0m) - mo_psi_m(zeta) + mo_psi_m(z0m / obu));
   } else if (zeta <= 1.0) {
-    return VKC * um / (log(zldis / z0m) + 5.0 * zeta - 5.0 * z0m / obu);
+    return VKC * um / (m_log(zldis / z0m) + 5.0 * zeta - 5.0 * z0m / obu);
   }
-  return VKC * um / (log(obu / z0m) + 5.0 - 5.0 * z0m / obu + (5.0 * log(zeta) + zeta - 1.0));
+  return VKC * um / (m_log(obu / z0m) + 5.0 - 5.0 * z0m / obu + (5.0 * m_log(zeta) + zeta - 1.0));
 }
 
 // scalar (temperature or humidity) profile relation for a reference height `zldis` above the
 // displacement height and roughness length z0
 // `grouped`: friction_velocity_temp2m writes the very-stable branch as 5 (z0/L) instead of (5 z0)/L
 // (:147), which can differ in the last bit; the other four callers use the ungrouped product.
-ELMK_HD double mo_scalar_profile(const double zldis, const double obu, const double z0, const bool grouped = false)
+ELMK_HD_NOINLINE double mo_scalar_profile(const double zldis, const double obu, const double z0, const bool grouped = false)
 {
   constexpr double zetat = 0.465;
   const double zeta = zldis / obu;
   if (zeta < (-zetat)) {
-    return VKC / (log(-zetat * obu / z0) - mo_psi_h(-zetat) + mo_psi_h(z0 / obu) +
-                  0.8 * (pow(zetat, -0.333) - pow((-zeta), -0.333)));
+    return VKC / (m_log(-zetat * obu / z0) - mo_psi_h(-zetat) + mo_psi_h(z0 / obu) +
+                  0.8 * (m_pow(zetat, -0.333) - m_pow((-zeta), -0.333)));
   } else if (zeta < 0.0) {
-    return VKC / (log(zldis / z0) - mo_psi_h(zeta) + mo_psi_h(z0 / obu));
+    return VKC / (m_log(zldis / z0) - mo_psi_h(zeta) + mo_psi_h(z0 / obu));
   } else if (zeta <= 1.0) {
-    return VKC / (log(zldis / z0) + 5.0 * zeta - 5.0 * z0 / obu);
+    return VKC / (m_log(zldis / z0) + 5.0 * zeta - 5.0 * z0 / obu);
   }
   const double stable = grouped ? 5.0 * (z0 / obu) : 5.0 * z0 / obu;
-  return VKC / (log(obu / z0) + 5.0 - stable + (5.0 * log(zeta) + zeta - 1.0));
+  return VKC / (m_log(obu / z0) + 5.0 - stable + (5.0 * m_log(zeta) + zeta - 1.0));
 }
 
 // the five profile quantities of one stability iteration

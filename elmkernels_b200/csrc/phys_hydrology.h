@@ -24,7 +24,7 @@ ELMK_HD void column_frac_wet(const Cols& S, const Tables& T, const int c)
       const double vegt = veg * (lai + sai);
       const double dewmxi = 1.0 / T.dewmx;
       // exponent literal as in the reference, not 2/3
-      wet = dmin(pow((dewmxi / vegt) * canwat, 0.666666666666), 1.0);
+      wet = dmin(m_pow((dewmxi / vegt) * canwat, 0.666666666666), 1.0);
     }
     dry = (1.0 - wet) * lai / (lai + sai);
   }
@@ -36,16 +36,16 @@ ELMK_HD void column_frac_wet(const Cols& S, const Tables& T, const int c)
 // density of newly fallen snow [kg/m3] as a function of air temperature (Alta relationship)
 ELMK_HD double fresh_snow_density(const double forc_t)
 {
-  if (forc_t > TFRZ + 2.0) return 50.0 + 1.7 * pow(17.0, 1.5);
-  if (forc_t > TFRZ - 15.0) return 50.0 + 1.7 * pow((forc_t - TFRZ + 15.0), 1.5);
+  if (forc_t > TFRZ + 2.0) return 50.0 + 1.7 * m_pow(17.0, 1.5);
+  if (forc_t > TFRZ - 15.0) return 50.0 + 1.7 * m_pow((forc_t - TFRZ + 15.0), 1.5);
   return 50.0;
 }
 
 // Niu & Yang (2007) snow-cover fraction used when oldfflag == 1
 ELMK_HD double fsca_niu_yang(const double snow_depth, const double swe)
 {
-  // pow(x, 1.0) == x exactly, kept out
-  return tanh(snow_depth / (2.5 * ZLND * dmin(800.0, (swe / snow_depth / 100.0))));
+  // m_pow(x, 1.0) == x exactly, kept out
+  return m_tanh(snow_depth / (2.5 * ZLND * dmin(800.0, (swe / snow_depth / 100.0))));
 }
 
 ELMK_HD void column_canopy_hydrology(const Cols& S, const Tables& T, const double dtime, const int c)
@@ -63,7 +63,7 @@ ELMK_HD void column_canopy_hydrology(const Cols& S, const Tables& T, const doubl
     fracsnow = snow / (snow + rain);
     fracrain = rain / (snow + rain);
     const double canmax = T.dewmx * lsai;
-    const double fpi = 0.25 * (1.0 - exp(-0.5 * lsai));
+    const double fpi = 0.25 * (1.0 - m_exp(-0.5 * lsai));
     thru_snow = snow * (1.0 - fpi);
     thru_rain = rain * (1.0 - fpi);
     const double intr = (snow + rain) * fpi;
@@ -124,11 +124,11 @@ ELMK_HD void column_canopy_hydrology(const Cols& S, const Tables& T, const doubl
     if (swe > 0.0) {
       if (snowmelt > 0.0) {
         const double smr = dmin(1.0, (swe / intsnow));
-        fsno = 1.0 - pow((acos(dmin(1.0, (2.0 * smr - 1.0))) / PI), nmelt);
+        fsno = 1.0 - m_pow((m_acos(dmin(1.0, (2.0 * smr - 1.0))) / PI), nmelt);
       }
       if (newsnow > 0.0) {
-        fsno = 1.0 - (1.0 - tanh(accum_factor * newsnow)) * (1.0 - fsno);
-        const double t = (swe + newsnow) / (0.5 * (cos(PI * pow((1.0 - dmax(fsno, 1.e-6)), (1.0 / nmelt))) + 1.0));
+        fsno = 1.0 - (1.0 - m_tanh(accum_factor * newsnow)) * (1.0 - fsno);
+        const double t = (swe + newsnow) / (0.5 * (m_cos(PI * m_pow((1.0 - dmax(fsno, 1.e-6)), (1.0 / nmelt))) + 1.0));
         intsnow = dmin(1.e8, t);
       }
       if (fsno > 0.0) {
@@ -143,8 +143,8 @@ ELMK_HD void column_canopy_hydrology(const Cols& S, const Tables& T, const doubl
     } else {
       if (newsnow > 0.0) {
         const double z_avg = newsnow / bifall;
-        fsno = tanh(accum_factor * newsnow);
-        const double t = (swe + newsnow) / (0.5 * (cos(PI * pow((1.0 - dmax(fsno, 1.e-6)), (1.0 / nmelt))) + 1.0));
+        fsno = m_tanh(accum_factor * newsnow);
+        const double t = (swe + newsnow) / (0.5 * (m_cos(PI * m_pow((1.0 - dmax(fsno, 1.e-6)), (1.0 / nmelt))) + 1.0));
         intsnow = dmin(1.e8, t);
         depth = z_avg / fsno;
         if (T.oldfflag == 1 && depth > 0.0) fsno = fsca_niu_yang(depth, swe + newsnow);
@@ -186,12 +186,12 @@ ELMK_HD void column_canopy_hydrology(const Cols& S, const Tables& T, const doubl
     double d = 0.0;
     const double sigma = 1.0e3 * C1(micro_sigma);
     for (int l = 0; l < 10; ++l) {
-      const double fd = 0.5 * d * (1.0 + erf(d / (sigma * sqrt(2.0)))) +
-                        sigma / sqrt(2.0 * PI) * exp(-sq(d) / (2.0 * sq(sigma))) - sfc;
-      const double dfdd = 0.5 * (1.0 + erf(d / (sigma * sqrt(2.0))));
+      const double fd = 0.5 * d * (1.0 + m_erf(d / (sigma * sqrt(2.0)))) +
+                        sigma / sqrt(2.0 * PI) * m_exp(-sq(d) / (2.0 * sq(sigma))) - sfc;
+      const double dfdd = 0.5 * (1.0 + m_erf(d / (sigma * sqrt(2.0))));
       d = d - fd / dfdd;
     }
-    fsfc = 0.5 * (1.0 + erf(d / (sigma * sqrt(2.0))));
+    fsfc = 0.5 * (1.0 + m_erf(d / (sigma * sqrt(2.0))));
   } else {
     fsfc = 0.0;
     C2(h2osoi_liq, NLEVSNO) = C2(h2osoi_liq, NLEVSNO) + sfc;

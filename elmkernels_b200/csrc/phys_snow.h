@@ -162,11 +162,11 @@ ELMK_HD void snow_compaction(snw::Pack& P, const double dtime, const double int_
     if (vd > 0.001 && P.ice[i] > 0.1) {
       const double bi = P.ice[i] / (frac_sno * P.dz[i]);
       const double td = TFRZ - P.t[i];
-      const double dexpf = exp(-c4 * td);
+      const double dexpf = m_exp(-c4 * td);
       double ddz1 = -c3 * dexpf;
-      if (bi > dm) ddz1 *= exp(-46.0e-3 * (bi - dm));
+      if (bi > dm) ddz1 *= m_exp(-46.0e-3 * (bi - dm));
       if (P.liq[i] > 0.01 * P.dz[i] * frac_sno) ddz1 *= c5;
-      const double ddz2 = -(burden + wx / 2.0) * exp(-0.08 * td - c2 * bi) / eta0;
+      const double ddz2 = -(burden + wx / 2.0) * m_exp(-0.08 * td - c2 * bi) / eta0;
       double ddz3;
       if (imelt[i] == 1) {
         ddz3 = dmax(0.0, dmin(1.0, (swe_old[i] - wx) / wx));
@@ -175,7 +175,7 @@ ELMK_HD void snow_compaction(snw::Pack& P, const double dtime, const double int_
           if (i == top) {
             for (int j = top; j < NS; ++j) wsum += P.liq[j] + P.ice[j];
           }
-          const double fsno_melt = 1.0 - pow(acos(2.0 * dmin(1.0, wsum / int_snow) - 1.0) / PI, n_melt);
+          const double fsno_melt = 1.0 - m_pow(m_acos(2.0 * dmin(1.0, wsum / int_snow) - 1.0) / PI, n_melt);
           ddz3 -= dmax(0.0, (fsno_melt - frac_sno) / frac_sno);
         }
         ddz3 = -1.0 / dtime * ddz3;
@@ -517,7 +517,7 @@ ELMK_HD void snow_aging(snw::Pack& P, const Tables& T, const int capsnow, const 
         err |= ERR_SNOWAGE_DR;   // the reference throws: the remaining layers of the column are left as they are
         return;
       }
-      double dr = (bst_drdt0 * pow(bst_tau / (dr_fresh + bst_tau), 1.0 / bst_kappa)) * (dtime / 3600.0);
+      double dr = (bst_drdt0 * m_pow(bst_tau / (dr_fresh + bst_tau), 1.0 / bst_kappa)) * (dtime / 3600.0);
       const double frc_liq = dmin(0.1, (P.liq[i] / (P.liq[i] + P.ice[i])));
       const double dr_wet = 1.0e18 * (dtime * (C2_liq_Brun89 * cube(frc_liq)) / (4.0 * PI * sq(P.rds[i])));
       dr += dr_wet;

@@ -60,9 +60,9 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
     satw = dmin(1.0, satw);
     const double tkdry = C2(tkdry, k);
     if (satw > 1.0e-6) {
-      const double dke = (t[i] >= TFRZ) ? dmax(0.0, log10(satw) + 1.0) : satw;
+      const double dke = (t[i] >= TFRZ) ? dmax(0.0, m_log10(satw) + 1.0) : satw;
       const double fl = (liq[i] / (DENH2O * dz[i])) / (liq[i] / (DENH2O * dz[i]) + ice[i] / (DENICE * dz[i]));
-      const double dksat = C2(tkmg, k) * pow(TKWAT, fl * watsat[k]) * pow(TKICE, (1.0 - fl) * watsat[k]);
+      const double dksat = C2(tkmg, k) * m_pow(TKWAT, fl * watsat[k]) * m_pow(TKICE, (1.0 - fl) * watsat[k]);
       thk[i] = dke * dksat + (1.0 - dke) * tkdry;
     } else {
       thk[i] = tkdry;
@@ -344,7 +344,7 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
     supercool[k] = 0.0;
     if (t[i] < TFRZ) {
       const double smp = HFUS * (TFRZ - t[i]) / (GRAV * t[i]) * 1000.0;
-      supercool[k] = watsat[k] * pow(smp / C2(sucsat, k), -1.0 / C2(bsw, k));
+      supercool[k] = watsat[k] * m_pow(smp / C2(sucsat, k), -1.0 / C2(bsw, k));
       supercool[k] *= dz[i] * 1000.0;
     }
     if (liq[i] > supercool[k] && t[i] < TFRZ) { imelt[i] = 2; tinc[i] = TFRZ - t[i]; t[i] = TFRZ; }

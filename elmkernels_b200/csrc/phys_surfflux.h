@@ -62,7 +62,7 @@ ELMK_HD void column_surface_fluxes(const Cols& S, const Tables& T, const double 
   const double emg = C1(emg), lwrad = C1(forc_lwrad), dlrad = C1(dlrad);
   {
     // quirk 5: exponent 40 on the surface-water term and the cube taken of the whole product
-    const double lw_grnd = (fse * pow4(tss_snotop) + (1.0 - fse - fsfc) * pow4(tss_soitop) + fsfc * pow(t_sfc_bef, 40.0));
+    const double lw_grnd = (fse * pow4(tss_snotop) + (1.0 - fse - fsfc) * pow4(tss_soitop) + fsfc * m_pow(t_sfc_bef, 40.0));
     const double p3 = emg * STEBOL * t_grnd0;
     C1(eflx_soil_grnd) = ((1.0 - fse) * C1(sabg_soil) + fse * C1(sabg_snow)) + dlrad +
                          (1.0 - (double)veg) * emg * lwrad - emg * STEBOL * lw_grnd - cube(p3) * (4.0 * tinc) -
