@@ -238,10 +238,15 @@ int elmk_create(elmk_handle* out, int /*device*/, int64_t ncols) {
   c->ncols = ncols;
   const int n = static_cast<int>(ncols);
   // as ELMInterface::ELMInterface (elm_kokkos_interface.cc:49-55) but with an empty forcing file name:
-  // the ELMState constructor does no file IO (elm_state_impl.hh:369-403)
+  // the ELMState constructor does no file IO (elm_state_impl.hh:369-403).  The domain-decomposition helper
+  // prints to std::cout; silenced so that programs using this library keep a clean stdout.
+  std::streambuf* keep = std::cout.rdbuf();
+  std::ostringstream sink;
+  std::cout.rdbuf(sink.rdbuf());
   c->S = std::make_unique<ELMStateType>(
       n, ELM::Utils::create_domain_decomposition_2D(ELM::Utils::square_numprocs(1), {1, 1}, {0, 0}), std::string(),
       ELM::Utils::Date(1985, 1, 1), 1);
+  std::cout.rdbuf(keep);
   c->dtend_column_h2o = ViewD1("dtend_column_h2o", n);
   c->errh2o = ViewD1("errh2o", n);
   c->errh2osno = ViewD1("errh2osno", n);
