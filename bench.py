@@ -295,12 +295,10 @@ def main():
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # optional global balance diagnostic: sum/min/max of the eight a11 fields over all GPUs (NCCL)
-        d = torch.from_numpy(cols.diag_reduce()).to(f"cuda:{local}")
-        s, lo, hi = d[:8].clone(), d[8:16].clone(), d[16:].clone()
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        # optional global balance diagnostic: sum/min/max of the eight a11 fields over all GPUs (NCCL),
+        # outside the timed region - the step itself has no collective
+        from elmkernels_b200.sharding import reduce_diagnostics
+        global_diag = reduce_diagnostics(cols.diag_reduce(), device=f"cuda:{local}")
     ms, ms_e2e = float(t[0]), float(t[1])
 
     if rank == 0:
