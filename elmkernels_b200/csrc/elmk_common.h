@@ -97,6 +97,27 @@ constexpr uint32_t ERR_NEG_STOMATAL = 1u << 9;
 constexpr uint32_t ERR_SNOWAGE_DR = 1u << 10;
 constexpr uint32_t ERR_DIVIDE_RADIUS = 1u << 11;
 
+// base^y for a constant base whose natural logarithm is given as a double-double (hi + lo): exp of the
+// exactly split product.  Two roundings (exp <= 1 ulp, final multiply-add) instead of the ~350-instruction
+// general pow; the host checker build keeps the reference's pow call.
+ELMK_HD double pow_cbase(const double base, const double ln_hi, const double ln_lo, const double y)
+{
+#ifdef ELMK_EXACT_POW
+  (void)ln_hi; (void)ln_lo;
+  return m_pow(base, y);
+#else
+  (void)base;
+  const double hi = y * ln_hi;
+  const double lo = fma(y, ln_hi, -hi) + y * ln_lo;
+  const double e = m_exp(hi);
+  return fma(e, lo, e);
+#endif
+}
+// ln(0.57), ln(2.29), ln(2) of the double constants, to double-double precision
+#define ELMK_LN_TKWAT -0x1.1fce0d03dd5e6p-1, 0x1.a4ee550808e41p-57
+#define ELMK_LN_TKICE 0x1.a837f19ef9d69p-1, 0x1.2e2416a47afa1p-55
+#define ELMK_LN_2 0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56
+
 // ---- arithmetic helpers ----
 // The reference is written with std::min/std::max; their NaN and signed-zero behaviour
 // ((b < a) ? b : a and (a < b) ? b : a) differs from fmin/fmax, so it is spelled out.

@@ -60,11 +60,8 @@ constexpr size_t kStageBytes = 64u << 20; // device staging buffer for layout co
 // column kernels
 // ------------------------------------------------------------------------------------------------
 template <uint32_t MASK>
-__global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
+__device__ __forceinline__ void run_groups(const Cols& S, const Tables& T, const StepArgs& A, const int c)
 {
-  const int c = blockIdx.x * kBlock + threadIdx.x;
-  if (c >= S.ncols) return;
-  const Tables& T = *Tp;
   if (MASK & ELMK_G_FRAC_WET) column_frac_wet(S, T, c);
   if (MASK & ELMK_G_ALBEDO) column_albedo(S, T, c);
   if (MASK & ELMK_G_CANOPY_HYDROLOGY) column_canopy_hydrology(S, T, A.dtime, c);
@@ -76,6 +73,22 @@ __global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* _
   if (MASK & ELMK_G_SNOW_HYDROLOGY) column_snow_hydrology(S, T, A.dtime, c);
   if (MASK & ELMK_G_SURFACE_FLUXES) column_surface_fluxes(S, T, A.dtime, c);
   if (MASK & ELMK_G_CONSERVATION) column_conservation(S, T, A.dtime, c);
+}
+
+template <uint32_t MASK>
+__global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
+{
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  if (c >= S.ncols) return;
+  run_groups<MASK>(S, *Tp, A, c);
+}
+// same, with a floor on the resident blocks per SM (caps the registers per thread)
+template <uint32_t MASK, int MINBLOCKS>
+__global__ void __launch_bounds__(kBlock, MINBLOCKS) k_groups_occ(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
+{
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  if (c >= S.ncols) return;
+  run_groups<MASK>(S, *Tp, A, c);
 }
 
 // ---- work-class sorted variant ------------------------------------------------------------------
@@ -102,12 +115,16 @@ template <uint32_t MASK> __device__ __forceinline__ int work_class(const Cols& S
     const int snl = S.snl[c];
     return 1 + (snl > 0 ? snl : 1);                               // SNICAR over 1..5 layers
   }
-  if (MASK & ELMK_G_SOIL_TEMPERATURE) return S.snl[c];
+  if (MASK & ELMK_G_BAREGROUND_FLUXES) return S.frac_veg_nosno[c] == 0 ? 1 : 0;   // bare: three MO passes
+  if (MASK & (ELMK_G_SOIL_TEMPERATURE | ELMK_G_SNOW_HYDROLOGY)) return S.snl[c];   // work grows with snow layers
   return 0;
 }
 
-template <uint32_t MASK>
-__global__ void __launch_bounds__(kBlock) k_groups_sorted(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
+// BLOCK threads per block; LOCKSTEP: the warps of a block take their chunks round by round behind a block
+// barrier (instruction-cache locality for the kernels whose body exceeds the 32 KB L1.5 cache), otherwise
+// they pull chunks from a shared counter (load balance).
+template <uint32_t MASK, int BLOCK, bool LOCKSTEP>
+__global__ void __launch_bounds__(BLOCK) k_groups_sorted(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
 {
   __shared__ unsigned short order[kWindow];
   __shared__ int count[kClasses], start[kClasses], next_chunk;
@@ -116,10 +133,11 @@ __global__ void __launch_bounds__(kBlock) k_groups_sorted(const Cols S, const Ta
   if (threadIdx.x < kClasses) count[threadIdx.x] = 0;
   if (threadIdx.x == 0) next_chunk = 0;
   __syncthreads();
-  int key[kWindow / kBlock], rank[kWindow / kBlock];
+  constexpr int R = (kWindow + BLOCK - 1) / BLOCK;
+  int key[R], rank[R];
 #pragma unroll
-  for (int r = 0; r < kWindow / kBlock; ++r) {
-    const int i = r * kBlock + threadIdx.x;
+  for (int r = 0; r < R; ++r) {
+    const int i = r * BLOCK + threadIdx.x;
     key[r] = -1;
     if (i < nvalid) {
       key[r] = work_class<MASK>(S, base + i);
@@ -136,23 +154,27 @@ __global__ void __launch_bounds__(kBlock) k_groups_sorted(const Cols S, const Ta
   }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < kWindow / kBlock; ++r)
-    if (key[r] >= 0) order[start[key[r]] + rank[r]] = (unsigned short)(r * kBlock + threadIdx.x);
+  for (int r = 0; r < R; ++r)
+    if (key[r] >= 0) order[start[key[r]] + rank[r]] = (unsigned short)(r * BLOCK + threadIdx.x);
   __syncthreads();
   const Tables& T = *Tp;
   const int lane = threadIdx.x & 31;
-  while (true) {
-    int chunk = 0;
-    if (lane == 0) chunk = atomicAdd(&next_chunk, 1);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    const int i = chunk * 32 + lane;
-    if (chunk * 32 >= nvalid) break;
-    if (i < nvalid) {
-      const int c = base + order[i];
-      if (MASK & ELMK_G_FRAC_WET) column_frac_wet(S, T, c);
-      if (MASK & ELMK_G_ALBEDO) column_albedo(S, T, c);
-      if (MASK & ELMK_G_CANOPY_FLUXES) column_canopy_fluxes(S, T, A, c);
-      if (MASK & ELMK_G_SOIL_TEMPERATURE) column_soil_temperature(S, T, A.dtime, c);
+  if (LOCKSTEP) {
+    constexpr int WARPS = BLOCK / 32;
+    const int warp = threadIdx.x >> 5;
+    for (int round = 0; round * WARPS * 32 < nvalid; ++round) {
+      __syncthreads();
+      const int i = (round * WARPS + warp) * 32 + lane;
+      if (i < nvalid) run_groups<MASK>(S, T, A, base + order[i]);
+    }
+  } else {
+    while (true) {
+      int chunk = 0;
+      if (lane == 0) chunk = atomicAdd(&next_chunk, 1);
+      chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      const int i = chunk * 32 + lane;
+      if (chunk * 32 >= nvalid) break;
+      if (i < nvalid) run_groups<MASK>(S, T, A, base + order[i]);
     }
   }
 }
@@ -303,9 +325,10 @@ __global__ void __launch_bounds__(kBlock) k_init_timestep(const Cols S, const Ta
 }
 
 typedef void (*GroupKernel)(const Cols, const Tables*, const StepArgs);
-struct Launch { uint32_t mask; GroupKernel fn; const char* name; int cols_per_block; };
-#define ELMK_LAUNCH(M, NAME) {(M), k_groups<(M)>, NAME, kBlock}
-#define ELMK_LAUNCH_SORTED(M, NAME) {(M), k_groups_sorted<(M)>, NAME, kWindow}
+struct Launch { uint32_t mask; GroupKernel fn; const char* name; int cols_per_block; int block; };
+#define ELMK_LAUNCH(M, NAME) {(M), k_groups<(M)>, NAME, kBlock, kBlock}
+#define ELMK_LAUNCH_OCC(M, NAME, MINBLOCKS) {(M), k_groups_occ<(M), MINBLOCKS>, NAME, kBlock, kBlock}
+#define ELMK_LAUNCH_SORTED(M, NAME, BLOCK, LOCKSTEP) {(M), k_groups_sorted<(M), BLOCK, LOCKSTEP>, NAME, kWindow, BLOCK}
 
 // plan "split": one launch per kernel group (the reference's wrapper granularity)
 const Launch kSplit[] = {
@@ -329,11 +352,26 @@ constexpr uint32_t M_SFC = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | 
                            ELMK_G_BAREGROUND_FLUXES;
 constexpr uint32_t M_END = ELMK_G_SNOW_HYDROLOGY | ELMK_G_SURFACE_FLUXES | ELMK_G_CONSERVATION;
 const Launch kFused[] = {
-    ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo"),
+    ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo", 128, false),
     ELMK_LAUNCH(M_SFC, "hydrology+radiation+temperature+bareground"),
-    ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes"),
+    ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes", 128, false),
     ELMK_LAUNCH(ELMK_G_SOIL_TEMPERATURE, "soil_temperature"),
     ELMK_LAUNCH(M_END, "snow+surface_fluxes+conservation"),
+};
+// experimental plans for A/B measurements (ELMK_PLAN=x1..)
+const Launch kX1[] = {
+    ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo", 128, false),
+    ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 8),
+    ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes", 128, false),
+    ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 3),
+    ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 4),
+};
+const Launch kX2[] = {
+    ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo", 128, false),
+    ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 6),
+    ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes", 128, false),
+    ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 4),
+    ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 6),
 };
 // plan "unsorted": the fused cut without work-class ordering (for A/B measurements)
 const Launch kFusedUnsorted[] = {
@@ -745,6 +783,12 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
   } else if (plan && std::strcmp(plan, "unsorted") == 0) {
     c->plan = kFusedUnsorted;
     c->plan_len = sizeof(kFusedUnsorted) / sizeof(kFusedUnsorted[0]);
+  } else if (plan && std::strcmp(plan, "x1") == 0) {
+    c->plan = kX1;
+    c->plan_len = sizeof(kX1) / sizeof(kX1[0]);
+  } else if (plan && std::strcmp(plan, "x2") == 0) {
+    c->plan = kX2;
+    c->plan_len = sizeof(kX2) / sizeof(kX2[0]);
   }
   const char* rp = std::getenv("ELMK_CANFLUX_REPACK");
   if (rp && rp[0] == '0') c->repack = false;
@@ -904,18 +948,18 @@ int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_
     const Launch& L = c->plan[i];
     const uint32_t want = L.mask & mask;
     if (!want) continue;
-    if (want == L.mask && L.mask == ELMK_G_CANOPY_FLUXES && c->repack && c->plan == kFused) {
+    if (want == L.mask && L.mask == ELMK_G_CANOPY_FLUXES && c->repack && c->plan != kSplit && c->plan != kFusedUnsorted) {
       TimedScope ts(c, L.name, L.mask);
       if (int rc = launch_canflux_repacked(c, A)) return rc;
     } else if (want == L.mask) {
       TimedScope ts(c, L.name, L.mask);
-      L.fn<<<grid_for(L), kBlock, 0, c->stream>>>(c->cols, c->d_tables, A);
+      L.fn<<<grid_for(L), L.block, 0, c->stream>>>(c->cols, c->d_tables, A);
       c->launches += 1;
     } else {
       for (const Launch& G : kSplit) {
         if (G.mask & want) {
           TimedScope ts(c, G.name, G.mask);
-          G.fn<<<grid_for(G), kBlock, 0, c->stream>>>(c->cols, c->d_tables, A);
+          G.fn<<<grid_for(G), G.block, 0, c->stream>>>(c->cols, c->d_tables, A);
           c->launches += 1;
         }
       }

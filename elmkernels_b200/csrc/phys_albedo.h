@@ -179,7 +179,7 @@ ELMK_HD_NOINLINE void snicar_solve(const Cols& S, const Tables& T, const int c, 
           const double R1 = rdif_a[i];
           const double T1 = tdif_a[i];
           double swt = 0.0, smr = 0.0, smt = 0.0;
-#pragma unroll
+#pragma unroll 1
           for (int ng = 0; ng < 8; ++ng) {
             const double mu = gauspt[ng];
             const double gwt = gauswt[ng];

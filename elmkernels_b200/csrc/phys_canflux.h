@@ -258,7 +258,7 @@ ELMK_HD_NOINLINE double psn_stomatal_resistance(const PsnPft& P, const int nrad,
     const double lmrc = psn_fth25(P.lmrhd, P.lmrse);
     lmr_z = lmr25 * psn_ft(t_veg, P.lmrha) * psn_fth(t_veg, P.lmrhd, P.lmrse, lmrc);
   } else {
-    lmr_z = lmr25 * m_pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
+    lmr_z = lmr25 * pow_cbase(2.0, ELMK_LN_2, ((t_veg - (TFRZ + 25.0)) / 10.0));
     lmr_z /= (1.0 + m_exp(1.3 * (t_veg - (TFRZ + 55.0))));
   }
   double vcmax_z, jmax_z, tpu_z, kp_z;
@@ -279,11 +279,11 @@ ELMK_HD_NOINLINE double psn_stomatal_resistance(const PsnPft& P, const int nrad,
     jmax_z = jmax25 * psn_ft(t_veg, P.jmaxha) * psn_fth(t_veg, P.jmaxhd, jmaxse, jmaxc);
     tpu_z = tpu25 * psn_ft(t_veg, P.tpuha) * psn_fth(t_veg, P.tpuhd, tpuse, tpuc);
     if (!c3) {
-      vcmax_z = vcmax25 * m_pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
+      vcmax_z = vcmax25 * pow_cbase(2.0, ELMK_LN_2, ((t_veg - (TFRZ + 25.0)) / 10.0));
       vcmax_z /= (1.0 + m_exp(0.2 * ((TFRZ + 15.0) - t_veg)));
       vcmax_z /= (1.0 + m_exp(0.3 * (t_veg - (TFRZ + 40.0))));
     }
-    kp_z = kp25 * m_pow(2.0, ((t_veg - (TFRZ + 25.0)) / 10.0));
+    kp_z = kp25 * pow_cbase(2.0, ELMK_LN_2, ((t_veg - (TFRZ + 25.0)) / 10.0));
   }
   vcmax_z *= btran;
   lmr_z *= btran;

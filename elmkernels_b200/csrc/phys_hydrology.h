@@ -36,7 +36,7 @@ ELMK_HD void column_frac_wet(const Cols& S, const Tables& T, const int c)
 // density of newly fallen snow [kg/m3] as a function of air temperature (Alta relationship)
 ELMK_HD double fresh_snow_density(const double forc_t)
 {
-  if (forc_t > TFRZ + 2.0) return 50.0 + 1.7 * m_pow(17.0, 1.5);
+  if (forc_t > TFRZ + 2.0) return 50.0 + 1.7 * 0x1.185f05d1aebd7p+6;   // pow(17.0, 1.5) as glibc rounds it
   if (forc_t > TFRZ - 15.0) return 50.0 + 1.7 * m_pow((forc_t - TFRZ + 15.0), 1.5);
   return 50.0;
 }

@@ -62,7 +62,7 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
     if (satw > 1.0e-6) {
       const double dke = (t[i] >= TFRZ) ? dmax(0.0, m_log10(satw) + 1.0) : satw;
       const double fl = (liq[i] / (DENH2O * dz[i])) / (liq[i] / (DENH2O * dz[i]) + ice[i] / (DENICE * dz[i]));
-      const double dksat = C2(tkmg, k) * m_pow(TKWAT, fl * watsat[k]) * m_pow(TKICE, (1.0 - fl) * watsat[k]);
+      const double dksat = C2(tkmg, k) * pow_cbase(TKWAT, ELMK_LN_TKWAT, fl * watsat[k]) * pow_cbase(TKICE, ELMK_LN_TKICE, (1.0 - fl) * watsat[k]);
       thk[i] = dke * dksat + (1.0 - dke) * tkdry;
     } else {
       thk[i] = tkdry;

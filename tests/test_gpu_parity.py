@@ -185,3 +185,21 @@ def test_large_ensemble_properties(cuda_lib, params):
     assert snl.min() >= 0 and snl.max() <= 5
     t = big.download("t_soisno")
     assert np.isfinite(t).all() and t[:, 5:].min() > 150.0 and t.max() < 350.0
+
+
+def test_elm_fortran_dump_of_test_canhydro(cuda_lib, params):
+    """BASELINE.json config 1 on the GPU: the ELM Fortran golden vectors of test_CanHydro, 38 variables x 48
+    records, at the closed-form tolerance."""
+    import elm_fixture
+    worst = elm_fixture.replay(cuda_lib, params)
+    bad = {k: v for k, v in worst.items() if v > parity.RTOL_CLOSED}
+    assert not bad, bad
+
+
+def test_elm_fortran_dump_of_test_canflux_night_records(cuda_lib, params):
+    """ELM Fortran golden vectors of test_CanFlux (night records) on the GPU, iterative tolerance."""
+    import elm_fixture
+    n, worst = elm_fixture.replay_canopy_fluxes(cuda_lib, params)
+    assert n == 47
+    bad = {k: v for k, v in worst.items() if v > parity.RTOL_ITER}
+    assert not bad, bad
