@@ -351,26 +351,12 @@ constexpr uint32_t M_RAD = ELMK_G_FRAC_WET | ELMK_G_ALBEDO;
 constexpr uint32_t M_SFC = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | ELMK_G_CANOPY_TEMPERATURE |
                            ELMK_G_BAREGROUND_FLUXES;
 constexpr uint32_t M_END = ELMK_G_SNOW_HYDROLOGY | ELMK_G_SURFACE_FLUXES | ELMK_G_CONSERVATION;
+// (register caps: measured on B200, 512k columns - 0.74 -> 0.64 ms, 2.66 -> 2.58 ms, 1.30 -> 1.11 ms)
 const Launch kFused[] = {
-    ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo", 128, false),
-    ELMK_LAUNCH(M_SFC, "hydrology+radiation+temperature+bareground"),
-    ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes", 128, false),
-    ELMK_LAUNCH(ELMK_G_SOIL_TEMPERATURE, "soil_temperature"),
-    ELMK_LAUNCH(M_END, "snow+surface_fluxes+conservation"),
-};
-// experimental plans for A/B measurements (ELMK_PLAN=x1..)
-const Launch kX1[] = {
     ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo", 128, false),
     ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 8),
     ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes", 128, false),
     ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 3),
-    ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 4),
-};
-const Launch kX2[] = {
-    ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo", 128, false),
-    ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 6),
-    ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes", 128, false),
-    ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 4),
     ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 6),
 };
 // plan "unsorted": the fused cut without work-class ordering (for A/B measurements)
@@ -783,12 +769,6 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
   } else if (plan && std::strcmp(plan, "unsorted") == 0) {
     c->plan = kFusedUnsorted;
     c->plan_len = sizeof(kFusedUnsorted) / sizeof(kFusedUnsorted[0]);
-  } else if (plan && std::strcmp(plan, "x1") == 0) {
-    c->plan = kX1;
-    c->plan_len = sizeof(kX1) / sizeof(kX1[0]);
-  } else if (plan && std::strcmp(plan, "x2") == 0) {
-    c->plan = kX2;
-    c->plan_len = sizeof(kX2) / sizeof(kX2[0]);
   }
   const char* rp = std::getenv("ELMK_CANFLUX_REPACK");
   if (rp && rp[0] == '0') c->repack = false;

@@ -203,3 +203,48 @@ def test_elm_fortran_dump_of_test_canflux_night_records(cuda_lib, params):
     assert n == 47
     bad = {k: v for k, v in worst.items() if v > parity.RTOL_ITER}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("case", ["capped_snow", "all_bare", "hot_and_wet"])
+def test_edge_ensembles(case, cuda_lib, checker, params):
+    """Snow capping (do_capsnow), all-bare ensembles and ponded surface water (incl. the 1e97 ground heat flux of
+    reference quirk 5), free-running for six steps."""
+    import edge_cases
+    st = edge_cases.build(case, 2048, params, cuda_lib.fields)
+    pair = parity.Pair(checker, cuda_lib, params, ensemble.EnsembleConfig(ncols=2048, seed=99, soil_temp_spread=4.0))
+    for c in (pair.a, pair.b):
+        c.upload_state(st)
+    for step in range(6):
+        pair.begin_step()
+        pair.run()
+    if case == "capped_snow":
+        assert pair.b.download("do_capsnow").sum() > 200
+    parity.check_with_rare_flips(pair, parity.RTOL_ITER, max_outliers=4, what=case)
+    assert pair.a.errors() == pair.b.errors()
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 129])
+def test_tiny_column_counts(n, cuda_lib, checker, params):
+    pair = parity.Pair(checker, cuda_lib, params, ensemble.EnsembleConfig(ncols=n, seed=n))
+    for _ in range(3):
+        pair.begin_step()
+        pair.run()
+    assert not pair.compare(parity.RTOL_ITER)
+
+
+def test_reference_throw_becomes_error_bit(cuda_lib, checker, params):
+    n = 4096
+    st = ensemble.make_state(ensemble.EnsembleConfig(ncols=n, seed=4, snow_fraction=1.0), params, cuda_lib.fields)
+    bad_cols = np.array([3, 1000, 4095])
+    st["snw_rds"][bad_cols, 4] = 10.0
+    out = []
+    for lib in (checker, cuda_lib):
+        c = lib.columns(n)
+        c.set_tables(params)
+        c.upload_state(st)
+        c.upload_state(ensemble.Forcing(n, seed=3, night_fraction=0.0).at(0, st))
+        c.init_timestep(True)
+        c.step(groups=abi.G_FRAC_WET | abi.G_ALBEDO)
+        out.append((c.errors(), set(np.nonzero(c.download("errmask"))[0])))
+    assert out[0] == out[1] == ((1 << 1, 3), set(bad_cols))
+    assert cuda_lib.dll.elmk_error_text(1 << 1).decode().startswith("ELM ERROR: SNICAR")
