@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
   bool have = false;
   int c = 0;
   PsnPft P = {};
+  PsnColumn PC = {};
   CanopyIter I = {};
   while (true) {
     // ---- refill idle lanes from the queue ----
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
           c = (q < nday) ? Q.list[q] : Q.list[Q.np - 1 - (q - nday)];
           canflux_load(Q, c, I);
           P = load_psn_pft(S, c);
+          PC = psn_column(P, I.t10, I.pbot, I.thm, I.forc_po2, I.dayl_factor);
           have = true;
         }
       }
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
     }
     // ---- one pass for every lane that owns a column ----
     if (have) {
-      if (canflux_iterate(P, I)) {
+      if (canflux_iterate(P, PC, I)) {
         canflux_store(Q, c, I, false);
         have = false;
       }

@@ -227,78 +227,136 @@ ELMK_HD void psn_hybrid(double x0, LeafPsn& L, uint32_t& err)
   }
 }
 
-// stomatal resistance of the sunlit or the shaded canopy fraction (nlevcan == 1, nrad == 1)
-ELMK_HD_NOINLINE double psn_stomatal_resistance(const PsnPft& P, const int nrad, const double pbot, const double t_veg,
-                                       const double t10, const double esat_tv, const double eair, const double oair,
-                                       const double cair, const double rb, const double btran,
-                                       const double dayl_factor, const double thm, const double vcmaxcint,
-                                       const double par, const double lai, uint32_t& err)
-{
-  constexpr double fnps = 0.15;
-  constexpr double theta_psii = 0.7;
-  constexpr double sco = 0.5 * 0.209 / (42.75 / 1.e06);
-  const bool c3 = (round(P.c3psn) == 1);   // anything else is treated as C4, as in the reference (:22-27)
-  if (nrad < 1) return 0.0;
+// Loop-invariant part of the photosynthesis model for one column: everything in photosynthesis() (:9-283) that
+// depends only on the PFT constants, the 10-day temperature, pressure and day length.  The reference
+// recomputes it in both calls (sunlit, shaded) of every stability pass; the values are identical, so it is
+// computed once per column here.
+struct PsnColumn {
+  bool c3;
+  double vcmax25top, jmax25top, tpu25top, kp25top, lmr25top, vcmaxse, jmaxse, tpuse;
+  double lmrc, vcmaxc, jmaxc, tpuc;   // high-temperature inhibition scaled to 1 at 25 C (fth25)
+  double cf, kc25, ko25, cp25;
+};
 
+ELMK_HD PsnColumn psn_column(const PsnPft& P, const double t10, const double pbot, const double thm, const double oair,
+                             const double dayl_factor)
+{
+  constexpr double sco = 0.5 * 0.209 / (42.75 / 1.e06);
+  PsnColumn C;
+  C.c3 = (round(P.c3psn) == 1);   // anything else is treated as C4, as in the reference (:22-27)
   const double lnc = 1.0 / (P.slatop * P.leafcn);
   const double act25 = P.act25 * 1000.0 / 60.0;
   double vcmax25top = lnc * P.flnr * P.fnr * act25 * dayl_factor;
   vcmax25top *= P.fnitr;
   const double t10c = dmin(dmax((t10 - TFRZ), 11.0), 35.0);
-  const double jmax25top = (2.59 - 0.035 * t10c) * vcmax25top;
-  const double tpu25top = 0.167 * vcmax25top;
-  const double kp25top = 20000.0 * vcmax25top;
-  const double lmr25top = c3 ? vcmax25top * 0.015 : vcmax25top * 0.025;
+  C.vcmax25top = vcmax25top;
+  C.jmax25top = (2.59 - 0.035 * t10c) * vcmax25top;
+  C.tpu25top = 0.167 * vcmax25top;
+  C.kp25top = 20000.0 * vcmax25top;
+  C.lmr25top = C.c3 ? vcmax25top * 0.015 : vcmax25top * 0.025;
+  C.vcmaxse = 668.39 - 1.07 * t10c;
+  C.jmaxse = 659.70 - 0.75 * t10c;
+  C.tpuse = C.vcmaxse;
+  C.lmrc = psn_fth25(P.lmrhd, P.lmrse);
+  C.vcmaxc = psn_fth25(P.vcmaxhd, C.vcmaxse);
+  C.jmaxc = psn_fth25(P.jmaxhd, C.jmaxse);
+  C.tpuc = psn_fth25(P.tpuhd, C.tpuse);
+  C.cf = pbot / (RGAS * 1.0e-3 * thm) * 1.e06;
+  C.kc25 = (404.9 / 1.e06) * pbot;
+  C.ko25 = (278.4 / 1.e03) * pbot;
+  C.cp25 = 0.5 * oair / sco;
+  return C;
+}
+
+// Leaf-temperature response factors of one stability pass: the sunlit and the shaded call see the same leaf
+// temperature, so the (up to 11) exponentials are evaluated once per pass instead of twice.
+struct PsnPass {
+  double lmr_a, lmr_b;                       // C3: ft, fth;  C4: 2^((T-25)/10), 1 + exp(1.3 (T-55))
+  double vc_a, vc_b, jm_a, jm_b, tp_a, tp_b; // ft, fth of vcmax, jmax, tpu (daytime only)
+  double p2, c4d1, c4d2;                     // 2^((T-25)/10) and the two C4 vcmax inhibition denominators
+  double kc, ko, cp;                         // Michaelis-Menten constants and CO2 compensation point
+};
+
+ELMK_HD PsnPass psn_pass(const PsnPft& P, const PsnColumn& C, const double t_veg, const bool day)
+{
+  PsnPass T;
+  T.p2 = 0.0; T.c4d1 = 1.0; T.c4d2 = 1.0;
+  T.vc_a = 0.0; T.vc_b = 0.0; T.jm_a = 0.0; T.jm_b = 0.0; T.tp_a = 0.0; T.tp_b = 0.0;
+  if (!C.c3 || day) T.p2 = pow_cbase(2.0, ELMK_LN_2, ((t_veg - (TFRZ + 25.0)) / 10.0));
+  if (C.c3) {
+    T.lmr_a = psn_ft(t_veg, P.lmrha);
+    T.lmr_b = psn_fth(t_veg, P.lmrhd, P.lmrse, C.lmrc);
+  } else {
+    T.lmr_a = T.p2;
+    T.lmr_b = (1.0 + m_exp(1.3 * (t_veg - (TFRZ + 55.0))));
+  }
+  if (day) {
+    T.vc_a = psn_ft(t_veg, P.vcmaxha);
+    T.vc_b = psn_fth(t_veg, P.vcmaxhd, C.vcmaxse, C.vcmaxc);
+    T.jm_a = psn_ft(t_veg, P.jmaxha);
+    T.jm_b = psn_fth(t_veg, P.jmaxhd, C.jmaxse, C.jmaxc);
+    T.tp_a = psn_ft(t_veg, P.tpuha);
+    T.tp_b = psn_fth(t_veg, P.tpuhd, C.tpuse, C.tpuc);
+    if (!C.c3) {
+      T.c4d1 = (1.0 + m_exp(0.2 * ((TFRZ + 15.0) - t_veg)));
+      T.c4d2 = (1.0 + m_exp(0.3 * (t_veg - (TFRZ + 40.0))));
+    }
+  }
+  T.kc = C.kc25 * psn_ft(t_veg, P.kcha);
+  T.ko = C.ko25 * psn_ft(t_veg, P.koha);
+  T.cp = C.cp25 * psn_ft(t_veg, P.cpha);
+  return T;
+}
+
+// stomatal resistance of the sunlit or the shaded canopy fraction (nlevcan == 1, nrad == 1)
+ELMK_HD_NOINLINE double psn_stomatal_resistance(const PsnPft& P, const PsnColumn& C, const PsnPass& T, const int nrad,
+                                                const double pbot, const double esat_tv, const double eair,
+                                                const double oair, const double cair, const double rb,
+                                                const double btran, const double vcmaxcint, const double par,
+                                                const double lai, uint32_t& err)
+{
+  constexpr double fnps = 0.15;
+  constexpr double theta_psii = 0.7;
+  const bool c3 = C.c3;
+  if (nrad < 1) return 0.0;
   const double nscaler = vcmaxcint;
 
   // leaf maintenance respiration (always) and the carboxylation capacities (daytime only)
   double lmr_z;
-  const double lmr25 = lmr25top * nscaler;
+  const double lmr25 = C.lmr25top * nscaler;
   if (c3) {
-    const double lmrc = psn_fth25(P.lmrhd, P.lmrse);
-    lmr_z = lmr25 * psn_ft(t_veg, P.lmrha) * psn_fth(t_veg, P.lmrhd, P.lmrse, lmrc);
+    lmr_z = lmr25 * T.lmr_a * T.lmr_b;
   } else {
-    lmr_z = lmr25 * pow_cbase(2.0, ELMK_LN_2, ((t_veg - (TFRZ + 25.0)) / 10.0));
-    lmr_z /= (1.0 + m_exp(1.3 * (t_veg - (TFRZ + 55.0))));
+    lmr_z = lmr25 * T.lmr_a;
+    lmr_z /= T.lmr_b;
   }
   double vcmax_z, jmax_z, tpu_z, kp_z;
   if (par <= 0.0) {
     vcmax_z = 0.0; jmax_z = 0.0; tpu_z = 0.0; kp_z = 0.0;
   } else {
-    const double vcmax25 = vcmax25top * nscaler;
-    const double jmax25 = jmax25top * nscaler;
-    const double tpu25 = tpu25top * nscaler;
-    const double kp25 = kp25top * nscaler;
-    const double vcmaxse = 668.39 - 1.07 * t10c;
-    const double jmaxse = 659.70 - 0.75 * t10c;
-    const double tpuse = vcmaxse;
-    const double vcmaxc = psn_fth25(P.vcmaxhd, vcmaxse);
-    const double jmaxc = psn_fth25(P.jmaxhd, jmaxse);
-    const double tpuc = psn_fth25(P.tpuhd, tpuse);
-    vcmax_z = vcmax25 * psn_ft(t_veg, P.vcmaxha) * psn_fth(t_veg, P.vcmaxhd, vcmaxse, vcmaxc);
-    jmax_z = jmax25 * psn_ft(t_veg, P.jmaxha) * psn_fth(t_veg, P.jmaxhd, jmaxse, jmaxc);
-    tpu_z = tpu25 * psn_ft(t_veg, P.tpuha) * psn_fth(t_veg, P.tpuhd, tpuse, tpuc);
+    const double vcmax25 = C.vcmax25top * nscaler;
+    const double jmax25 = C.jmax25top * nscaler;
+    const double tpu25 = C.tpu25top * nscaler;
+    const double kp25 = C.kp25top * nscaler;
+    vcmax_z = vcmax25 * T.vc_a * T.vc_b;
+    jmax_z = jmax25 * T.jm_a * T.jm_b;
+    tpu_z = tpu25 * T.tp_a * T.tp_b;
     if (!c3) {
-      vcmax_z = vcmax25 * pow_cbase(2.0, ELMK_LN_2, ((t_veg - (TFRZ + 25.0)) / 10.0));
-      vcmax_z /= (1.0 + m_exp(0.2 * ((TFRZ + 15.0) - t_veg)));
-      vcmax_z /= (1.0 + m_exp(0.3 * (t_veg - (TFRZ + 40.0))));
+      vcmax_z = vcmax25 * T.p2;
+      vcmax_z /= T.c4d1;
+      vcmax_z /= T.c4d2;
     }
-    kp_z = kp25 * pow_cbase(2.0, ELMK_LN_2, ((t_veg - (TFRZ + 25.0)) / 10.0));
+    kp_z = kp25 * T.p2;
   }
   vcmax_z *= btran;
   lmr_z *= btran;
 
-  const double cf = pbot / (RGAS * 1.0e-3 * thm) * 1.e06;
+  const double cf = C.cf;
   const double gb = 1.0 / rb;
   const double gb_mol = gb * cf;
   const double bbb = dmax(P.bbbopt * btran, 1.0);
   constexpr double rsmax0 = 2.0e4;
-  const double kc25 = (404.9 / 1.e06) * pbot;
-  const double ko25 = (278.4 / 1.e03) * pbot;
-  const double cp25 = 0.5 * oair / sco;
-  const double kc = kc25 * psn_ft(t_veg, P.kcha);
-  const double ko = ko25 * psn_ft(t_veg, P.koha);
-  const double cp = cp25 * psn_ft(t_veg, P.cpha);
+  const double kc = T.kc, ko = T.ko, cp = T.cp;
 
   double rs_z;
   if (par <= 0.0) {
@@ -484,7 +542,7 @@ ELMK_HD bool canflux_begin(const Cols& S, const Tables& T, const StepArgs& A, co
 
 // One pass of the stability iteration.  Returns true when the loop of the reference would end
 // (converged, or 41 passes done).
-ELMK_HD bool canflux_iterate(const PsnPft& P, CanopyIter& I)
+ELMK_HD bool canflux_iterate(const PsnPft& P, const PsnColumn& PC, CanopyIter& I)
 {
   constexpr double ria = 0.5, dlemin = 0.1, dtmin = 0.01;
   constexpr int itmax = 40, itmin = 2;
@@ -521,12 +579,13 @@ ELMK_HD bool canflux_iterate(const PsnPft& P, CanopyIter& I)
   const double eah = pbot * I.qaf / 0.622;
 
   double btran = I.btran;
+  const PsnPass PT = psn_pass(P, PC, t_veg, (I.parsun > 0.0) || (I.parsha > 0.0));
   if (I.soybean) btran = dmin(1.0, btran * 1.25);
-  const double rssun = psn_stomatal_resistance(P, I.nrad, pbot, t_veg, I.t10, svpts, eah, I.forc_po2, I.forc_pco2, rb, btran,
-                                               I.dayl_factor, thm, I.vcsun, I.parsun, I.laisun_z, err);
+  const double rssun = psn_stomatal_resistance(P, PC, PT, I.nrad, pbot, svpts, eah, I.forc_po2, I.forc_pco2, rb, btran,
+                                               I.vcsun, I.parsun, I.laisun_z, err);
   if (I.soybean) btran = dmin(1.0, btran * 1.25);
-  const double rssha = psn_stomatal_resistance(P, I.nrad, pbot, t_veg, I.t10, svpts, eah, I.forc_po2, I.forc_pco2, rb, btran,
-                                               I.dayl_factor, thm, I.vcsha, I.parsha, I.laisha_z, err);
+  const double rssha = psn_stomatal_resistance(P, PC, PT, I.nrad, pbot, svpts, eah, I.forc_po2, I.forc_pco2, rb, btran,
+                                               I.vcsha, I.parsha, I.laisha_z, err);
   I.btran = btran;
 
   // sensible-heat conductances: air, leaf, ground
@@ -725,8 +784,9 @@ ELMK_HD void column_canopy_fluxes(const Cols& S, const Tables& T, const StepArgs
   const PsnPft P = load_psn_pft(S, c);
   CanopyIter I;
   if (!canflux_begin(S, T, A, P, c, I)) return;
+  const PsnColumn PC = psn_column(P, I.t10, I.pbot, I.thm, I.forc_po2, I.dayl_factor);
 #pragma unroll 1
-  while (!canflux_iterate(P, I)) {
+  while (!canflux_iterate(P, PC, I)) {
   }
   canflux_end(S, c, I);
 }

@@ -40,55 +40,68 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
   double h2osfc = C1(h2osfc), h2osno = C1(h2osno);
   double t_sfc = C1(t_h2osfc);
 
-  double t[NLEVTOT], liq[NLEVTOT], ice[NLEVTOT], dz[NLEVTOT], z[NLEVTOT], zi[NLEVTOT + 1];
+  // The function streams over the layers three times - properties, matrix rows + forward elimination,
+  // phase change - and re-reads the few per-layer inputs each pass needs instead of holding the ~340 doubles
+  // of the column (state, conductivities, five bands, right-hand side, solver work arrays) at once: the first
+  // version of this kernel ran at 255 registers with 2.9 KB of spills per thread.
+  double t[NLEVTOT], z[NLEVTOT];
 #pragma unroll
   for (int i = 0; i < NLEVTOT; ++i) {
-    t[i] = C2(t_soisno, i); liq[i] = C2(h2osoi_liq, i); ice[i] = C2(h2osoi_ice, i);
-    dz[i] = C2(dz, i); z[i] = C2(zsoi, i); zi[i] = C2(zisoi, i);
+    t[i] = C2(t_soisno, i);
+    z[i] = C2(zsoi, i);
   }
-  zi[NLEVTOT] = C2(zisoi, NLEVTOT);
-  double watsat[NLEVGRND];
-#pragma unroll
-  for (int i = 0; i < NLEVGRND; ++i) watsat[i] = C2(watsat, i);
 
-  // ---- thermal conductivity of the layers (Johansen) and at the interfaces, heat capacities ----
-  double thk[NLEVTOT], tk[NLEVTOT], cv[NLEVTOT];
+  // ---- pass 1: thermal conductivity (Johansen) and heat capacity of every layer -> fact ----
+  double thk[NLEVTOT], fact[NLEVTOT];
 #pragma unroll
-  for (int i = NLEVSNO; i < NLEVTOT; ++i) {
-    const int k = i - NLEVSNO;
-    double satw = (liq[i] / DENH2O + ice[i] / DENICE) / (dz[i] * watsat[k]);
-    satw = dmin(1.0, satw);
-    const double tkdry = C2(tkdry, k);
-    if (satw > 1.0e-6) {
-      const double dke = (t[i] >= TFRZ) ? dmax(0.0, m_log10(satw) + 1.0) : satw;
-      const double fl = (liq[i] / (DENH2O * dz[i])) / (liq[i] / (DENH2O * dz[i]) + ice[i] / (DENICE * dz[i]));
-      const double dksat = C2(tkmg, k) * pow_cbase(TKWAT, ELMK_LN_TKWAT, fl * watsat[k]) * pow_cbase(TKICE, ELMK_LN_TKICE, (1.0 - fl) * watsat[k]);
-      thk[i] = dke * dksat + (1.0 - dke) * tkdry;
-    } else {
-      thk[i] = tkdry;
-    }
-    // (no layer lies below nlevbed == nlevgrnd, so the bedrock override never applies)
-    cv[i] = C2(csol, i) * (1.0 - watsat[k]) * dz[i] + (ice[i] * CPICE + liq[i] * CPWAT);
-    if (i == NLEVSNO && snl == 0 && h2osno > 0.0) cv[i] += CPICE * h2osno;
-  }
-#pragma unroll
-  for (int i = 0; i < NLEVSNO; ++i) {
-    if (i < top) {
+  for (int i = 0; i < NLEVTOT; ++i) {
+    const double liq = C2(h2osoi_liq, i), ice = C2(h2osoi_ice, i), dz = C2(dz, i);
+    double cv;
+    if (i >= NLEVSNO) {
+      const int k = i - NLEVSNO;
+      const double watsat = C2(watsat, k);
+      double satw = (liq / DENH2O + ice / DENICE) / (dz * watsat);
+      satw = dmin(1.0, satw);
+      const double tkdry = C2(tkdry, k);
+      if (satw > 1.0e-6) {
+        const double dke = (t[i] >= TFRZ) ? dmax(0.0, m_log10(satw) + 1.0) : satw;
+        const double fl = (liq / (DENH2O * dz)) / (liq / (DENH2O * dz) + ice / (DENICE * dz));
+        const double dksat = C2(tkmg, k) * pow_cbase(TKWAT, ELMK_LN_TKWAT, fl * watsat) * pow_cbase(TKICE, ELMK_LN_TKICE, (1.0 - fl) * watsat);
+        thk[i] = dke * dksat + (1.0 - dke) * tkdry;
+      } else {
+        thk[i] = tkdry;
+      }
+      // (no layer lies below nlevbed == nlevgrnd, so the bedrock override never applies)
+      cv = C2(csol, i) * (1.0 - watsat) * dz + (ice * CPICE + liq * CPWAT);
+      if (i == NLEVSNO && snl == 0 && h2osno > 0.0) cv += CPICE * h2osno;
+    } else if (i < top) {
       thk[i] = 0.0;
-      cv[i] = 0.0;
+      cv = 0.0;
     } else {
-      const double bw = (ice[i] + liq[i]) / (fsno * dz[i]);
+      const double bw = (ice + liq) / (fsno * dz);
       thk[i] = TKAIR + (7.75e-5 * bw + 1.105e-6 * bw * bw) * (TKICE - TKAIR);
-      cv[i] = (fsno > 0.0) ? dmax(THIN_SFCLAYER, (CPWAT * liq[i] + CPICE * ice[i]) / fsno) : THIN_SFCLAYER;
+      cv = (fsno > 0.0) ? dmax(THIN_SFCLAYER, (CPWAT * liq + CPICE * ice) / fsno) : THIN_SFCLAYER;
     }
+    if (i < top) fact[i] = 0.0;
+    else if (i == top) fact[i] = dtime / cv * dz / (0.5 * (z[i] - C2(zisoi, i) + CAPR * (z[(i + 1 < NLEVTOT) ? i + 1 : i] - C2(zisoi, i))));
+    else fact[i] = dtime / cv;
+    C2(fact, i) = fact[i];
   }
+  // conductivity at the interfaces and the diffusive heat flux through them
+  double tk[NLEVTOT], fn[NLEVTOT];
 #pragma unroll
   for (int i = 0; i < NLEVTOT - 1; ++i) {
-    tk[i] = (i < top) ? 0.0
-                      : thk[i] * thk[i + 1] * (z[i + 1] - z[i]) /
-                            (thk[i] * (z[i + 1] - zi[i + 1]) + thk[i + 1] * (zi[i + 1] - z[i]));
+    if (i < top) {
+      tk[i] = 0.0;
+      fn[i] = 0.0;
+    } else {
+      const double zi1 = C2(zisoi, i + 1);
+      tk[i] = thk[i] * thk[i + 1] * (z[i + 1] - z[i]) / (thk[i] * (z[i + 1] - zi1) + thk[i + 1] * (zi1 - z[i]));
+      fn[i] = tk[i] * (t[i + 1] - t[i]) / (z[i + 1] - z[i]);
+    }
   }
   tk[NLEVTOT - 1] = 0.0;
+  fn[NLEVTOT - 1] = 0.0;
   const double zh2osfc = 1.0e-3 * (0.5 * h2osfc);
   const double tk_sfc = TKWAT * thk[NLEVSNO] * (z[NLEVSNO] + zh2osfc) / (TKWAT * z[NLEVSNO] + thk[NLEVSNO] * zh2osfc);
   const bool ponded = (h2osfc > THIN_SFCLAYER) && (fsfc > THIN_SFCLAYER);
@@ -116,156 +129,125 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
                              (C1(eflx_sh_snow) + C1(qflx_ev_snow) * htvp);
   const double dhsdT = -C1(cgrnd) - 4.0 * emg * STEBOL * cube(C1(t_grnd));
 
-  // ---- diffusive heat flux at the interfaces and the time-step factor of each layer ----
-  double fn[NLEVTOT], fact[NLEVTOT];
-#pragma unroll
-  for (int i = 0; i < NLEVTOT - 1; ++i) fn[i] = (i < top) ? 0.0 : tk[i] * (t[i + 1] - t[i]) / (z[i + 1] - z[i]);
-  fn[NLEVTOT - 1] = 0.0;
-#pragma unroll
-  for (int i = 0; i < NLEVTOT; ++i) {
-    if (i < top) fact[i] = 0.0;
-    else if (i == top) fact[i] = dtime / cv[i] * dz[i] / (0.5 * (z[i] - zi[i] + CAPR * (z[i + 1] - zi[i])));
-    else fact[i] = dtime / cv[i];
-    C2(fact, i) = fact[i];
-  }
-
-  // ---- right-hand side: rows 0-4 snow, row 5 surface water, rows 6-20 soil ----
-  double rhs[NROWS];
-#pragma unroll
-  for (int i = 0; i < NLEVSNO; ++i) {
-    if (i < top) rhs[i] = 0.0;
-    else if (i == top) rhs[i] = t[i] + fact[i] * (hs_top_snow - dhsdT * t[i] + CNFAC * fn[i]);
-    else rhs[i] = t[i] + CNFAC * fact[i] * (fn[i] - fn[i - 1]) + fact[i] * sabg_lyr[i];
-  }
-  const double fn_sfc = tk_sfc * (t[NLEVSNO] - t_sfc) / (0.5 * dz_sfc + z[NLEVSNO]);
-  rhs[NLEVSNO] = t_sfc + (dtime / c_sfc) * (hs_sfc - dhsdT * t_sfc + CNFAC * fn_sfc);
-  {
-    const int s = NLEVSNO;
-    if (snl == 0) {
-      rhs[s + 1] = t[s] + fact[s] * (hs_top_snow - dhsdT * t[s] + CNFAC * fn[s]);
-    } else {
-      double r = t[s] + fact[s] * ((1.0 - fse) * (hs_soil - dhsdT * t[s]) + CNFAC * (fn[s] - fse * fn[s - 1]));
-      r += fse * fact[s] * sabg_lyr[s];
-      rhs[s + 1] = r;
-    }
-  }
-#pragma unroll
-  for (int j = NLEVSNO + 1; j < NLEVTOT - 1; ++j) rhs[j + 1] = t[j] + CNFAC * fact[j] * (fn[j] - fn[j - 1]);
-  {
-    const int b = NLEVTOT - 1;
-    rhs[b + 1] = t[b] - CNFAC * fact[b] * fn[b - 1] + fact[b] * fn[b];
-  }
-
-  // ---- left-hand side: five bands per row ----
-  double b0[NROWS], b1[NROWS], b2[NROWS], b3[NROWS], b4[NROWS];
-#pragma unroll
-  for (int i = 0; i < NROWS; ++i) { b0[i] = 0.0; b1[i] = 0.0; b2[i] = 0.0; b3[i] = 0.0; b4[i] = 0.0; }
+  // ---- pass 2: one row of the band system at a time (rows 0-4 snow, row 5 surface water, rows 6-20 soil;
+  //      band k of row i multiplies unknown i + 2 - k), eliminated as soon as it is built (PDMA forward
+  //      sweep).  Rows above the first active one leave A = B = Z = 0; with those zeros the general
+  //      elimination step reproduces the reference's special first and second steps bit for bit. ----
   constexpr double OMC = 1.0 - CNFAC;
-  if (snl > 0) {
-    // snow rows
+  constexpr int N = NROWS;
+  double A[N], B[N], Z[N];
+  const double fn_sfc = tk_sfc * (t[NLEVSNO] - t_sfc) / (0.5 * dz_sfc + z[NLEVSNO]);
 #pragma unroll
-    for (int i = 0; i < NLEVSNO; ++i) {
+  for (int r = 0; r < N; ++r) {
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, b4 = 0.0, rhs = 0.0;
+    bool active = true;
+    if (r < NLEVSNO) {
+      const int i = r;
+      active = (i >= top);
       if (i == top) {
         const double dzp = z[i + 1] - z[i];
-        b2[i] = 1.0 + OMC * fact[i] * tk[i] / dzp - fact[i] * dhsdT;
-        if (snl > 1) b1[i] = -OMC * fact[i] * tk[i] / dzp;
+        b2 = 1.0 + OMC * fact[i] * tk[i] / dzp - fact[i] * dhsdT;
+        if (snl > 1) b1 = -OMC * fact[i] * tk[i] / dzp;
+        rhs = t[i] + fact[i] * (hs_top_snow - dhsdT * t[i] + CNFAC * fn[i]);
       } else if (i > top) {
-        const double dzm = z[i] - z[i - 1];
+        const int im = (i > 0) ? i - 1 : 0;
+        const double dzm = z[i] - z[im];
         const double dzp = z[i + 1] - z[i];
-        b3[i] = -OMC * fact[i] * tk[i - 1] / dzm;
-        b2[i] = 1.0 + OMC * fact[i] * (tk[i] / dzp + tk[i - 1] / dzm);
-        if (i != NLEVSNO - 1) b1[i] = -OMC * fact[i] * tk[i] / dzp;
+        b3 = -OMC * fact[i] * tk[im] / dzm;
+        b2 = 1.0 + OMC * fact[i] * (tk[i] / dzp + tk[im] / dzm);
+        if (i != NLEVSNO - 1) b1 = -OMC * fact[i] * tk[i] / dzp;
+        rhs = t[i] + CNFAC * fact[i] * (fn[i] - fn[im]) + fact[i] * sabg_lyr[i];
       }
-    }
-    // bottom snow layer -> top soil layer, across the surface-water row
-    b0[NLEVSNO - 1] = -OMC * fact[NLEVSNO - 1] * tk[NLEVSNO - 1] / (z[NLEVSNO] - z[NLEVSNO - 1]);
-  }
-  // surface-water row
-  b2[NLEVSNO] = 1.0 + OMC * (dtime / c_sfc) * tk_sfc / (0.5 * dz_sfc + z[NLEVSNO]) - (dtime / c_sfc) * dhsdT;
-  b1[NLEVSNO] = -OMC * (dtime / c_sfc) * tk_sfc / (0.5 * dz_sfc + z[NLEVSNO]);
-  // top soil row
-  {
-    const int s = NLEVSNO, r = NLEVSNO + 1;
-    const double dzp = z[s + 1] - z[s];
-    if (snl == 0) {
-      b2[r] = 1.0 + OMC * fact[s] * tk[s] / dzp - fact[s] * dhsdT;
-      b1[r] = -OMC * fact[s] * tk[s] / dzp;
+      // bottom snow layer -> top soil layer, across the surface-water row
+      if (i == NLEVSNO - 1 && snl > 0) b0 = -OMC * fact[i] * tk[i] / (z[NLEVSNO] - z[i]);
+    } else if (r == NLEVSNO) {
+      b2 = 1.0 + OMC * (dtime / c_sfc) * tk_sfc / (0.5 * dz_sfc + z[NLEVSNO]) - (dtime / c_sfc) * dhsdT;
+      b1 = -OMC * (dtime / c_sfc) * tk_sfc / (0.5 * dz_sfc + z[NLEVSNO]);
+      rhs = t_sfc + (dtime / c_sfc) * (hs_sfc - dhsdT * t_sfc + CNFAC * fn_sfc);
+    } else if (r == NLEVSNO + 1) {
+      const int s = NLEVSNO;
+      const double dzp = z[s + 1] - z[s];
+      if (snl == 0) {
+        b2 = 1.0 + OMC * fact[s] * tk[s] / dzp - fact[s] * dhsdT;
+        b1 = -OMC * fact[s] * tk[s] / dzp;
+        rhs = t[s] + fact[s] * (hs_top_snow - dhsdT * t[s] + CNFAC * fn[s]);
+      } else {
+        const double dzm = z[s] - z[s - 1];
+        b2 = 1.0 + OMC * fact[s] * (tk[s] / dzp + fse * tk[s - 1] / dzm) - (1.0 - fse) * fact[s] * dhsdT;
+        b1 = -OMC * fact[s] * tk[s] / dzp;
+        b4 = -fse * OMC * fact[s] * tk[s - 1] / dzm;
+        double rr = t[s] + fact[s] * ((1.0 - fse) * (hs_soil - dhsdT * t[s]) + CNFAC * (fn[s] - fse * fn[s - 1]));
+        rr += fse * fact[s] * sabg_lyr[s];
+        rhs = rr;
+      }
+      if (fsfc != 0.0) {
+        const double dzm = 0.5 * dz_sfc + z[s];
+        b2 += fsfc * (OMC * fact[s] * tk_sfc / dzm + fact[s] * dhsdT);
+        b3 = -fsfc * OMC * fact[s] * tk_sfc / (0.5 * dz_sfc + z[s]);
+      }
+    } else if (r < N - 1) {
+      const int j = r - 1;
+      const double dzm = z[j] - z[j - 1];
+      const double dzp = z[j + 1] - z[j];
+      b3 = -OMC * fact[j] * tk[j - 1] / dzm;
+      b2 = 1.0 + OMC * fact[j] * (tk[j] / dzp + tk[j - 1] / dzm);
+      b1 = -OMC * fact[j] * tk[j] / dzp;
+      rhs = t[j] + CNFAC * fact[j] * (fn[j] - fn[j - 1]);
     } else {
-      const double dzm = z[s] - z[s - 1];
-      b2[r] = 1.0 + OMC * fact[s] * (tk[s] / dzp + fse * tk[s - 1] / dzm) - (1.0 - fse) * fact[s] * dhsdT;
-      b1[r] = -OMC * fact[s] * tk[s] / dzp;
-      b4[r] = -fse * OMC * fact[s] * tk[s - 1] / dzm;
+      const int b = NLEVTOT - 1;
+      const double dzm = z[b] - z[b - 1];
+      b3 = -OMC * fact[b] * tk[b - 1] / dzm;
+      b2 = 1.0 + OMC * fact[b] * tk[b - 1] / dzm;
+      rhs = t[b] - CNFAC * fact[b] * fn[b - 1] + fact[b] * fn[b];
     }
-    if (fsfc != 0.0) {
-      const double dzm = 0.5 * dz_sfc + z[s];
-      b2[r] += fsfc * (OMC * fact[s] * tk_sfc / dzm + fact[s] * dhsdT);
-      b3[r] = -fsfc * OMC * fact[s] * tk_sfc / (0.5 * dz_sfc + z[s]);
+
+    // forward elimination of row r
+    const double Am2 = (r >= 2) ? A[(r >= 2) ? r - 2 : 0] : 0.0, Bm2 = (r >= 2) ? B[(r >= 2) ? r - 2 : 0] : 0.0,
+                 Zm2 = (r >= 2) ? Z[(r >= 2) ? r - 2 : 0] : 0.0;
+    const double Am1 = (r >= 1) ? A[(r >= 1) ? r - 1 : 0] : 0.0, Bm1 = (r >= 1) ? B[(r >= 1) ? r - 1 : 0] : 0.0,
+                 Zm1 = (r >= 1) ? Z[(r >= 1) ? r - 1 : 0] : 0.0;
+    if (!active) {
+      A[r] = 0.0; B[r] = 0.0; Z[r] = 0.0;
+    } else if (r < N - 2) {
+      const double Y1 = b3 - Am2 * b4;
+      const double U1 = 1.0 / (b2 - Bm2 * b4 - Am1 * Y1);
+      A[r] = (b1 - Bm1 * Y1) * U1;
+      B[r] = b0 * U1;
+      Z[r] = (rhs - Zm2 * b4 - Zm1 * Y1) * U1;
+    } else if (r == N - 2) {
+      const double Y1 = b3 - Am2 * b4;
+      const double U1 = 1.0 / (b2 - Bm2 * b4 - Am1 * Y1);
+      A[r] = (b1 - Bm1 * Y1) * U1;
+      B[r] = 0.0;
+      // the reference uses Z(N-3) twice here where Z(N-4), Z(N-3) are meant; band 4 is zero in this row
+      Z[r] = (rhs - Zm1 * b4 - Zm1 * Y1) * U1;
+    } else {
+      // last row: Y2 / U2 of the reference, again with its doubled Z(N-2)
+      const double Y2 = b3 - Am2 * b4;
+      const double U2 = 1.0 / (b2 - Bm2 * b4 - Am1 * Y2);
+      A[r] = 0.0;
+      B[r] = 0.0;
+      Z[r] = (rhs - Zm1 * b4 - Zm1 * Y2) * U2;
     }
   }
-  // interior soil rows and the bottom row
+  // back substitution; the solution overwrites Z
+  double sol[N];
+  sol[N - 1] = Z[N - 1];
+  sol[N - 2] = Z[N - 2] - A[N - 2] * sol[N - 1];
 #pragma unroll
-  for (int j = NLEVSNO + 1; j < NLEVTOT - 1; ++j) {
-    const double dzm = z[j] - z[j - 1];
-    const double dzp = z[j + 1] - z[j];
-    b3[j + 1] = -OMC * fact[j] * tk[j - 1] / dzm;
-    b2[j + 1] = 1.0 + OMC * fact[j] * (tk[j] / dzp + tk[j - 1] / dzm);
-    b1[j + 1] = -OMC * fact[j] * tk[j] / dzp;
-  }
-  {
-    const int b = NLEVTOT - 1;
-    const double dzm = z[b] - z[b - 1];
-    b3[b + 1] = -OMC * fact[b] * tk[b - 1] / dzm;
-    b2[b + 1] = 1.0 + OMC * fact[b] * tk[b - 1] / dzm;
-  }
+  for (int i = N - 3; i >= 0; --i) sol[i] = Z[i] - A[i] * sol[i + 1] - B[i] * sol[i + 2];
 
-  // ---- pentadiagonal solve (PDMA); A, B, Z are zero above the first active row ----
-  {
-    constexpr int N = NROWS;
-    double A[N], B[N], Z[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) { A[i] = 0.0; B[i] = 0.0; Z[i] = 0.0; }
-    double U1 = 1.0 / b2[top];
-    A[top] = b1[top] * U1;
-    B[top] = b0[top] * U1;
-    Z[top] = rhs[top] * U1;
-    double Y1 = b3[top + 1];
-    U1 = 1.0 / (b2[top + 1] - A[top] * Y1);
-    A[top + 1] = (b1[top + 1] - B[top] * Y1) * U1;
-    B[top + 1] = b0[top + 1] * U1;
-    Z[top + 1] = (rhs[top + 1] - Z[top] * Y1) * U1;
-    for (int i = top + 2; i < N - 2; ++i) {
-      Y1 = b3[i] - A[i - 2] * b4[i];
-      U1 = 1.0 / (b2[i] - B[i - 2] * b4[i] - A[i - 1] * Y1);
-      A[i] = (b1[i] - B[i - 1] * Y1) * U1;
-      B[i] = b0[i] * U1;
-      Z[i] = (rhs[i] - Z[i - 2] * b4[i] - Z[i - 1] * Y1) * U1;
-    }
-    Y1 = b3[N - 2] - A[N - 4] * b4[N - 2];
-    U1 = 1.0 / (b2[N - 2] - B[N - 4] * b4[N - 2] - A[N - 3] * Y1);
-    A[N - 2] = (b1[N - 2] - B[N - 3] * Y1) * U1;
-    const double Y2 = b3[N - 1] - A[N - 3] * b4[N - 1];
-    const double U2 = 1.0 / (b2[N - 1] - B[N - 3] * b4[N - 1] - A[N - 2] * Y2);
-    // the reference uses Z(N-3) and Z(N-2) twice here; band 4 is zero in these rows
-    Z[N - 2] = (rhs[N - 2] - Z[N - 3] * b4[N - 2] - Z[N - 3] * Y1) * U1;
-    Z[N - 1] = (rhs[N - 1] - Z[N - 2] * b4[N - 1] - Z[N - 2] * Y2) * U2;
-    rhs[N - 1] = Z[N - 1];
-    rhs[N - 2] = Z[N - 2] - A[N - 2] * rhs[N - 1];
-    for (int i = N - 3; i >= 0; --i) rhs[i] = Z[i] - A[i] * rhs[i + 1] - B[i] * rhs[i + 2];
-  }
+  // surface-water temperature: the solution of its row when there is surface water, else the top soil value
+  t_sfc = (fsfc != 0.0) ? sol[NLEVSNO] : sol[NLEVSNO + 1];
 
-  // ---- new temperatures ----
-#pragma unroll
-  for (int i = 0; i < NLEVSNO; ++i)
-    if (i >= top) t[i] = rhs[i];
-#pragma unroll
-  for (int i = NLEVSNO; i < NLEVTOT; ++i) t[i] = rhs[i + 1];
-  t_sfc = (fsfc != 0.0) ? rhs[NLEVSNO] : t[NLEVSNO];
-
-  // ---- phase change of standing surface water ----
+  // ---- phase change of standing surface water (touches the bottom snow slot only) ----
+  constexpr int SB = NLEVSNO - 1;   // bottom snow slot
+  const double fact_sb = fact[SB];
+  double t_sb = (SB >= top) ? sol[SB] : C2(t_soisno, SB);
+  double ice_sb = C2(h2osoi_ice, SB);
   double int_snow = C1(int_snow), snow_depth = C1(snow_depth);
   double xmf_sfc = 0.0, q_sfc_ice = 0.0, e_sfc_snow = 0.0;
   {
-    const int b = NLEVSNO - 1;   // bottom snow slot
     if (fsfc > 0.0 && t_sfc <= TFRZ) {
       const double tinc = TFRZ - t_sfc;
       t_sfc = TFRZ;
@@ -278,19 +260,19 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
         // part of the pond freezes onto the snow pack
         h2osno -= xm;
         int_snow -= xm;
-        if (snl > 0) ice[b] -= xm;
+        if (snl > 0) ice_sb -= xm;
         h2osfc += xm;
         xmf_sfc = hm;
         q_sfc_ice = -xm / dtime;
         snow_depth = (fsno > 0 && snl > 0) ? h2osno / (rho_avg * fsno) : h2osno / DENICE;
         if (snl == 0) {
-          t[b] = t_sfc;
+          t_sb = t_sfc;
           e_sfc_snow = 0.0;
         } else {
-          const double c1 = (snl == 1) ? fsno * (dtime / fact[b] - dhsdT * dtime) : fsno / fact[b] * dtime;
+          const double c1 = (snl == 1) ? fsno * (dtime / fact_sb - dhsdT * dtime) : fsno / fact_sb * dtime;
           const double c2 = (fsfc != 0.0) ? (-CPWAT * xm - fsfc * dhsdT * dtime) : 0.0;
-          t[b] = (c1 * t[b] + c2 * t_sfc) / (c1 + c2);
-          e_sfc_snow = (t_sfc - t[b]) * c2 / dtime;
+          t_sb = (c1 * t_sb + c2 * t_sfc) / (c1 + c2);
+          e_sfc_snow = (t_sfc - t_sb) * c2 / dtime;
         }
       } else {
         // the whole pond freezes
@@ -298,16 +280,16 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
         h2osno += h2osfc;
         int_snow += h2osfc;
         q_sfc_ice = h2osfc / dtime;
-        if (snl > 0) ice[b] = ice[b] + h2osfc;
+        if (snl > 0) ice_sb = ice_sb + h2osfc;
         t_sfc = t_sfc - temp1 * HFUS / (dtime * dhsdT - c_sfc);
         xmf_sfc = hm - fsfc * temp1 * HFUS / dtime;
         if (snl == 0) {
-          t[b] = t_sfc;
+          t_sb = t_sfc;
         } else {
-          const double c1 = (snl == 1) ? fsno * (dtime / fact[b] - dhsdT * dtime) : fsno / fact[b] * dtime;
+          const double c1 = (snl == 1) ? fsno * (dtime / fact_sb - dhsdT * dtime) : fsno / fact_sb * dtime;
           const double c2 = (fsfc != 0.0) ? fsfc * (c_sfc - dtime * dhsdT) : 0.0;
-          t[b] = (c1 * t[b] + c2 * t_sfc) / (c1 + c2);
-          t_sfc = t[b];
+          t_sb = (c1 * t_sb + c2 * t_sfc) / (c1 + c2);
+          t_sfc = t_sb;
         }
         h2osfc = 0.0;
         snow_depth = (fsno > 0.0 && snl > 0) ? h2osno / (rho_avg * fsno) : h2osno / DENICE;
@@ -318,61 +300,63 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
   C1(qflx_h2osfc_ice) = q_sfc_ice;
   C1(eflx_h2osfc_snow) = e_sfc_snow;
 
-  // ---- phase change in snow and soil layers ----
-  double xmf = 0.0, q_snomelt = 0.0, q_snow_melt = 0.0;
-  double snofrz_lyr[NLEVSNO];
-  int imelt[NLEVTOT];
-  double tinc[NLEVTOT], supercool[NLEVGRND];
-#pragma unroll
-  for (int i = 0; i < NLEVSNO; ++i) snofrz_lyr[i] = 0.0;
+  // ---- pass 3: phase change in snow and soil layers, one layer at a time; the water state of a layer is
+  //      read only now (the solve does not need it) and written back at once ----
+  double xmf = 0.0, q_snomelt = 0.0, q_snow_melt = 0.0, q_snofrz = 0.0;
+  double t_new_top = 0.0, t_new_soil1 = 0.0;
 #pragma unroll
   for (int i = 0; i < NLEVTOT; ++i) {
-    imelt[i] = (i >= top) ? 0 : C2(imelt, i);   // rows above the snow pack keep their stale flags (quirk 13)
-    tinc[i] = 0.0;
-  }
-#pragma unroll
-  for (int i = 0; i < NLEVSNO; ++i) {
-    if (i >= top) {
-      if (ice[i] > 0.0 && t[i] > TFRZ) { imelt[i] = 1; tinc[i] = TFRZ - t[i]; t[i] = TFRZ; }
-      if (liq[i] > 0.0 && t[i] < TFRZ) { imelt[i] = 2; tinc[i] = TFRZ - t[i]; t[i] = TFRZ; }
+    if (i < top) {
+      // rows above the snow pack are untouched (their melt flags stay stale, quirk 13), except the bottom
+      // snow slot, which the surface-water phase change may have initialised (phase_change_impl.hh:79-83,123-125)
+      if (i < NLEVSNO) C2(qflx_snofrz_lyr, i) = 0.0;
+      if (i == SB) {
+        C2(t_soisno, i) = t_sb;
+        C2(h2osoi_ice, i) = ice_sb;
+      }
+      continue;
     }
-  }
-#pragma unroll
-  for (int i = NLEVSNO; i < NLEVTOT; ++i) {
-    const int k = i - NLEVSNO;
-    if (ice[i] > 0.0 && t[i] > TFRZ) { imelt[i] = 1; tinc[i] = TFRZ - t[i]; t[i] = TFRZ; }
-    supercool[k] = 0.0;
-    if (t[i] < TFRZ) {
-      const double smp = HFUS * (TFRZ - t[i]) / (GRAV * t[i]) * 1000.0;
-      supercool[k] = watsat[k] * m_pow(smp / C2(sucsat, k), -1.0 / C2(bsw, k));
-      supercool[k] *= dz[i] * 1000.0;
-    }
-    if (liq[i] > supercool[k] && t[i] < TFRZ) { imelt[i] = 2; tinc[i] = TFRZ - t[i]; t[i] = TFRZ; }
-    if (snl == 0 && h2osno > 0.0 && i == NLEVSNO) {
-      if (t[i] > TFRZ) { imelt[i] = 1; tinc[i] = TFRZ - t[i]; t[i] = TFRZ; }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NLEVTOT; ++i) {
-    if (i < top) continue;
-    double hm = 0.0;
-    if (imelt[i] > 0) {
-      if (i == top) {
-        if (i < NLEVSNO) {
-          hm = fse * (dhsdT * tinc[i] - tinc[i] / fact[i]);
-        } else {
-          const double temp_hm = dhsdT * tinc[i] - tinc[i] / fact[i];
-          hm = (fsfc != 0.0) ? temp_hm - fsfc * (dhsdT * tinc[i]) : temp_hm;
-        }
-      } else if (i == NLEVSNO) {
-        hm = (1.0 - fse - fsfc) * dhsdT * tinc[i] - tinc[i] / fact[i];
-      } else {
-        hm = (i < NLEVSNO) ? -fse * (tinc[i] / fact[i]) : -tinc[i] / fact[i];
+    double ti = (i == SB) ? t_sb : ((i < NLEVSNO) ? sol[i] : sol[(i + 1 < N) ? i + 1 : i]);
+    double liq = C2(h2osoi_liq, i);
+    double ice = (i == SB) ? ice_sb : C2(h2osoi_ice, i);
+    const double fi = fact[i];
+    int imelt = 0;
+    double tinc = 0.0, supercool = 0.0;
+    if (i < NLEVSNO) {
+      if (ice > 0.0 && ti > TFRZ) { imelt = 1; tinc = TFRZ - ti; ti = TFRZ; }
+      if (liq > 0.0 && ti < TFRZ) { imelt = 2; tinc = TFRZ - ti; ti = TFRZ; }
+    } else {
+      const int k = i - NLEVSNO;
+      if (ice > 0.0 && ti > TFRZ) { imelt = 1; tinc = TFRZ - ti; ti = TFRZ; }
+      if (ti < TFRZ) {
+        const double smp = HFUS * (TFRZ - ti) / (GRAV * ti) * 1000.0;
+        supercool = C2(watsat, k) * m_pow(smp / C2(sucsat, k), -1.0 / C2(bsw, k));
+        supercool *= C2(dz, i) * 1000.0;
+      }
+      if (liq > supercool && ti < TFRZ) { imelt = 2; tinc = TFRZ - ti; ti = TFRZ; }
+      if (snl == 0 && h2osno > 0.0 && i == NLEVSNO) {
+        if (ti > TFRZ) { imelt = 1; tinc = TFRZ - ti; ti = TFRZ; }
       }
     }
-    if (imelt[i] == 1 && hm < 0.0) { hm = 0.0; imelt[i] = 0; }
-    if (imelt[i] == 2 && hm > 0.0) { hm = 0.0; imelt[i] = 0; }
-    if (imelt[i] > 0 && fabs(hm) > 0.0) {
+    double hm = 0.0;
+    if (imelt > 0) {
+      if (i == top) {
+        if (i < NLEVSNO) {
+          hm = fse * (dhsdT * tinc - tinc / fi);
+        } else {
+          const double temp_hm = dhsdT * tinc - tinc / fi;
+          hm = (fsfc != 0.0) ? temp_hm - fsfc * (dhsdT * tinc) : temp_hm;
+        }
+      } else if (i == NLEVSNO) {
+        hm = (1.0 - fse - fsfc) * dhsdT * tinc - tinc / fi;
+      } else {
+        hm = (i < NLEVSNO) ? -fse * (tinc / fi) : -tinc / fi;
+      }
+    }
+    if (imelt == 1 && hm < 0.0) { hm = 0.0; imelt = 0; }
+    if (imelt == 2 && hm > 0.0) { hm = 0.0; imelt = 0; }
+    double snofrz = 0.0;
+    if (imelt > 0 && fabs(hm) > 0.0) {
       double xm = hm * dtime / HFUS;
       if (i == NLEVSNO) {
         if (snl == 0 && h2osno > 0.0 && xm > 0.0) {
@@ -395,45 +379,48 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
         }
       }
       double heatr = 0.0;
-      const double wmass0 = ice[i] + liq[i];
-      const double wice0 = ice[i];
+      const double wmass0 = ice + liq;
+      const double wice0 = ice;
       if (xm > 0.0) {
-        ice[i] = dmax(0.0, wice0 - xm);
-        heatr = hm - HFUS * (wice0 - ice[i]) / dtime;
+        ice = dmax(0.0, wice0 - xm);
+        heatr = hm - HFUS * (wice0 - ice) / dtime;
       } else if (xm < 0.0) {
         if (i < NLEVSNO) {
-          ice[i] = dmin(wmass0, wice0 - xm);
+          ice = dmin(wmass0, wice0 - xm);
         } else {
-          const double sc = supercool[(i >= NLEVSNO) ? i - NLEVSNO : 0];
-          ice[i] = (wmass0 < sc) ? 0.0 : dmin(wmass0 - sc, wice0 - xm);
+          ice = (wmass0 < supercool) ? 0.0 : dmin(wmass0 - supercool, wice0 - xm);
         }
-        heatr = hm - HFUS * (wice0 - ice[i]) / dtime;
+        heatr = hm - HFUS * (wice0 - ice) / dtime;
       }
-      liq[i] = dmax(0.0, wmass0 - ice[i]);
+      liq = dmax(0.0, wmass0 - ice);
       if (fabs(heatr) > 0.0) {
         if (i == top) {
-          if (snl == 0) t[i] += fact[i] * heatr / (1.0 - (1.0 - fsfc) * fact[i] * dhsdT);
-          else t[i] += (fact[i] / fse) * heatr / (1.0 - fact[i] * dhsdT);
+          if (snl == 0) ti += fi * heatr / (1.0 - (1.0 - fsfc) * fi * dhsdT);
+          else ti += (fi / fse) * heatr / (1.0 - fi * dhsdT);
         } else if (i == NLEVSNO) {
-          t[i] += fact[i] * heatr / (1.0 - (1.0 - fse - fsfc) * fact[i] * dhsdT);
+          ti += fi * heatr / (1.0 - (1.0 - fse - fsfc) * fi * dhsdT);
         } else {
-          if (i >= NLEVSNO) t[i] += fact[i] * heatr;
-          else if (fse > 0.0) t[i] += (fact[i] / fse) * heatr;
+          if (i >= NLEVSNO) ti += fi * heatr;
+          else if (fse > 0.0) ti += (fi / fse) * heatr;
         }
         if (i < NLEVSNO) {
-          if (liq[i] * ice[i] > 0.0) t[i] = TFRZ;
+          if (liq * ice > 0.0) ti = TFRZ;
         }
       }
-      xmf += HFUS * (wice0 - ice[i]) / dtime;
-      if (imelt[i] == 1 && i < NLEVSNO) q_snomelt += dmax(0.0, (wice0 - ice[i])) / dtime;
-      if (imelt[i] == 2 && i < NLEVSNO) snofrz_lyr[i] = dmax(0.0, (ice[i] - wice0)) / dtime;
+      xmf += HFUS * (wice0 - ice) / dtime;
+      if (imelt == 1 && i < NLEVSNO) q_snomelt += dmax(0.0, (wice0 - ice)) / dtime;
+      if (imelt == 2 && i < NLEVSNO) snofrz = dmax(0.0, (ice - wice0)) / dtime;
     }
-  }
-  double q_snofrz = 0.0;
-#pragma unroll
-  for (int i = 0; i < NLEVSNO; ++i) {
-    if (imelt[i] == 2) q_snofrz += snofrz_lyr[i];
-    C2(qflx_snofrz_lyr, i) = snofrz_lyr[i];
+    if (i < NLEVSNO) {
+      if (imelt == 2) q_snofrz += snofrz;
+      C2(qflx_snofrz_lyr, i) = snofrz;
+    }
+    if (i == top) t_new_top = ti;
+    if (i == NLEVSNO) t_new_soil1 = ti;
+    C2(t_soisno, i) = ti;
+    C2(h2osoi_ice, i) = ice;
+    C2(h2osoi_liq, i) = liq;
+    C2(imelt, i) = imelt;
   }
   C1(xmf) = xmf;
   C1(qflx_snofrz) = q_snofrz;
@@ -443,32 +430,14 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
 
   // ---- new ground temperature ----
   double tg;
-  t_top = t[NLEVSNO];
-#pragma unroll
-  for (int i = 0; i < NLEVSNO; ++i)
-    if (i == top) t_top = t[i];
   if (snl > 0) {
-    tg = (fsfc != 0.0) ? fse * t_top + (1.0 - fse - fsfc) * t[NLEVSNO] + fsfc * t_sfc
-                       : fse * t_top + (1.0 - fse) * t[NLEVSNO];
+    tg = (fsfc != 0.0) ? fse * t_new_top + (1.0 - fse - fsfc) * t_new_soil1 + fsfc * t_sfc
+                       : fse * t_new_top + (1.0 - fse) * t_new_soil1;
   } else {
-    tg = (fsfc != 0.0) ? (1.0 - fsfc) * t[NLEVSNO] + fsfc * t_sfc : t[NLEVSNO];
+    tg = (fsfc != 0.0) ? (1.0 - fsfc) * t_new_soil1 + fsfc * t_sfc : t_new_soil1;
   }
   C1(t_grnd) = tg;
 
-  // ---- write back the prognostic column ----
-  // Rows above the snow pack are untouched by the reference, except slot 4 which the surface-water
-  // phase change may initialise when there is no snow layer (phase_change_impl.hh:79-83,123-125).
-#pragma unroll
-  for (int i = 0; i < NLEVTOT; ++i) {
-    if (i >= top || i == NLEVSNO - 1) {
-      C2(t_soisno, i) = t[i];
-      C2(h2osoi_ice, i) = ice[i];
-    }
-    if (i >= top) {
-      C2(h2osoi_liq, i) = liq[i];
-      C2(imelt, i) = imelt[i];
-    }
-  }
   C1(t_h2osfc) = t_sfc;
   C1(h2osfc) = h2osfc;
   C1(h2osno) = h2osno;

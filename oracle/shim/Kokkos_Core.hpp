@@ -12,6 +12,13 @@
 //   * every allocation is padded: the reference writes rt_snow(c, 5) one past a 5-wide
 //     row (soil_temp_rhs_impl.hh:93,101 - SURVEY.md quirk 12); the pad absorbs the write for
 //     the last column;
+//   * optional stack scrubbing (environment ELMREF_SCRUB_STACK=1, set by the test suite, not by the
+//     timing runs): the reference reads two elements past a stack array in snow_water
+//     (snow_hydrology_impl.hh:388), so its result depends on what the calling thread
+//     left on its stack - the previous column, another library's kernel, the Python interpreter.  With
+//     scrubbing, parallel_for zero-fills the stack region the functor's frame will occupy before every
+//     column, which turns that read into a well-defined 0 (or the column's own value when all five snow
+//     layers are active) and makes the oracle deterministic.  The reference code itself is untouched;
 //   * parallel_for runs the functor under "#pragma omp parallel for"; a C++ exception
 //     thrown by one column (the reference throws inside kernels) is caught per column and
 //     recorded in kokkos_shim::errors() instead of terminating the process.
@@ -35,6 +42,16 @@ namespace kokkos_shim {
 struct ColumnError { long col; std::string what; };
 inline std::mutex& error_mutex() { static std::mutex m; return m; }
 inline std::vector<ColumnError>& errors() { static std::vector<ColumnError> e; return e; }
+inline bool scrub_enabled() {
+  static const bool on = [] { const char* e = std::getenv("ELMREF_SCRUB_STACK"); return e && e[0] == '1'; }();
+  return on;
+}
+// zero-fill the next 16 KB of the calling thread's stack (the frames of the functor and its callees)
+__attribute__((noinline)) inline void scrub_stack() {
+  volatile unsigned char buf[16384];
+  std::memset(const_cast<unsigned char*>(buf), 0, sizeof(buf));
+  __asm__ __volatile__("" ::: "memory");
+}
 inline void record(long col, const char* what) {
   std::lock_guard<std::mutex> g(error_mutex());
   if (errors().size() < 4096) errors().push_back({col, what});
@@ -128,10 +145,12 @@ template <class DT, class... Extents> void resize(View<DT>& v, Extents... e) { v
 
 template <class Functor> void parallel_for(const std::string&, size_t n, const Functor& f) {
   const long count = static_cast<long>(n);
+  const bool scrub = kokkos_shim::scrub_enabled();
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)
 #endif
   for (long i = 0; i < count; ++i) {
+    if (scrub) kokkos_shim::scrub_stack();
     try {
       f(static_cast<int>(i));
     } catch (const std::exception& e) {

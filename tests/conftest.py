@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# make the oracle deterministic where the reference reads uninitialised stack (oracle/shim/Kokkos_Core.hpp)
+os.environ.setdefault("ELMREF_SCRUB_STACK", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

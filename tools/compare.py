@@ -5,6 +5,7 @@ report, per kernel group and per field, the largest relative difference.  With -
 library's state is overwritten by the first one's after every group, so each group is checked in
 isolation on identical inputs."""
 import argparse, os, sys
+os.environ.setdefault("ELMREF_SCRUB_STACK", "1")
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
