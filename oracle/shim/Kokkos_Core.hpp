@@ -18,7 +18,9 @@
 //     left on its stack - the previous column, another library's kernel, the Python interpreter.  With
 //     scrubbing, parallel_for zero-fills the stack region the functor's frame will occupy before every
 //     column, which turns that read into a well-defined 0 (or the column's own value when all five snow
-//     layers are active) and makes the oracle deterministic.  The reference code itself is untouched;
+//     layers are active) and makes the oracle deterministic.  The same switch makes parallel_for run the
+//     columns in an order that hides the cross-column write of quirk 12 from its neighbour (see
+//     parallel_for below).  The reference code itself is untouched;
 //   * parallel_for runs the functor under "#pragma omp parallel for"; a C++ exception
 //     thrown by one column (the reference throws inside kernels) is caught per column and
 //     recorded in kokkos_shim::errors() instead of terminating the process.
@@ -145,18 +147,49 @@ template <class DT, class... Extents> void resize(View<DT>& v, Extents... e) { v
 
 template <class Functor> void parallel_for(const std::string&, size_t n, const Functor& f) {
   const long count = static_cast<long>(n);
-  const bool scrub = kokkos_shim::scrub_enabled();
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static)
-#endif
-  for (long i = 0; i < count; ++i) {
+  auto one = [&](long i, bool scrub) {
     if (scrub) kokkos_shim::scrub_stack();
     try {
       f(static_cast<int>(i));
     } catch (const std::exception& e) {
       kokkos_shim::record(i, e.what());
     }
+  };
+  if (kokkos_shim::scrub_enabled()) {
+    // deterministic mode: blocks of 64 consecutive columns; the last column of every block runs in a
+    // second phase, after all other columns are done.  Column c of the reference writes one element
+    // into column c+1's row of a scratch View (quirk 12); in serial order that element is overwritten by
+    // column c+1 before it is read, but when c and c+1 belong to different threads the write can land
+    // between c+1's own write and read (observed: 33 columns on 16 threads).  With two phases the stray
+    // write of a block's last column always lands after its neighbour has finished, which gives the
+    // serial-order result whatever the thread count.
+    constexpr long BLK = 64;
+    const long nb = (count + BLK - 1) / BLK;
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+      for (long b = 0; b < nb; ++b) {
+        const long end = (b + 1) * BLK < count ? (b + 1) * BLK : count;
+        for (long i = b * BLK; i < end - 1; ++i) one(i, true);
+      }
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+      for (long b = 0; b < nb; ++b) {
+        const long end = (b + 1) * BLK < count ? (b + 1) * BLK : count;
+        one(end - 1, true);
+      }
+    }
+    return;
   }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (long i = 0; i < count; ++i) one(i, false);
 }
 template <class Functor> void parallel_for(size_t n, const Functor& f) { parallel_for(std::string(), n, f); }
 
