@@ -10,7 +10,8 @@ from .abi import Columns, ElmkError, Library  # noqa: F401
 from . import abi  # noqa: F401
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libelmk_b200.so")
+# ELMK_LIB: development override used for A/B measurements of differently built copies of the same CUDA library
+LIB_PATH = os.environ.get("ELMK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libelmk_b200.so")
 
 
 def load() -> Library:

@@ -11,9 +11,12 @@ from __future__ import annotations
 
 import os
 import pathlib
+import re
+import shlex
 import shutil
 import subprocess
 import sys
+import tempfile
 
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
@@ -23,8 +26,13 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "--expt-relaxed-constexpr", "-diag-suppress", "550", "-Xcompiler", "-fPIC", "-shared"]
 
 
+# kernels / device functions (regex on the mangled name) that keep their divisions in line behind a zero test
+# instead of calling m_div (see ptx_rewrite.py)
+INLINE_DIV = os.environ.get("ELMK_INLINE_DIV", "")
+
+
 def sources():
-    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.h")) + [HERE.parent / "include/elmk_b200.h",
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.h")) + [HERE / "ptx_rewrite.py", HERE / "build.py",HERE.parent / "include/elmk_b200.h",
                                                                      HERE.parent / "include/elmk_fields.def"]
 
 
@@ -35,17 +43,53 @@ def up_to_date() -> bool:
     return all(s.stat().st_mtime <= t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
-    if not force and up_to_date():
+def pipeline(cmd, keep: pathlib.Path):
+    """The compilation steps nvcc would run for `cmd` (its --dryrun listing), as a bash script with one extra
+    step between cicc and ptxas: ptx_rewrite.py on the generated PTX (see that file for what and why)."""
+    r = subprocess.run(cmd + ["--dryrun", "--keep", "--keep-dir", str(keep)], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc --dryrun failed")
+    script, ptx = ["set -e"], None
+    for line in (r.stdout + r.stderr).splitlines():
+        if not line.startswith("#$ "):
+            continue
+        line = line[3:]
+        m = re.match(r"^([A-Za-z_][A-Za-z0-9_]*)=(.*)$", line)
+        if m:
+            if m.group(1) in ("PATH", "LD_LIBRARY_PATH", "CICC_PATH", "NVVMIR_LIBRARY_DIR", "TOP"):
+                script.append(f"export {m.group(1)}={shlex.quote(m.group(2).strip())}")
+            continue
+        if line.startswith("rm "):
+            line = "rm -f " + line[3:]
+        if re.match(r"^ptxas\b", line):
+            m = re.search(r'"([^"]+\.ptx)"', line)
+            if not m:
+                raise RuntimeError("could not find the PTX file in nvcc's ptxas step")
+            ptx = m.group(1)
+            script.append(f"{shlex.quote(sys.executable)} {shlex.quote(str(HERE / 'ptx_rewrite.py'))} {shlex.quote(ptx)} "
+                          f"{shlex.quote(INLINE_DIV)}")
+        script.append(line)
+    if ptx is None:
+        raise RuntimeError("nvcc --dryrun listed no ptxas step")
+    return "\n".join(script) + "\n"
+
+
+def build(force: bool = False, verbose: bool = False, out: pathlib.Path | None = None) -> pathlib.Path:
+    if out is None and not force and up_to_date():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB), str(CSRC / "elmk_lib.cu")]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    out = out or LIB
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(out), str(CSRC / "elmk_lib.cu")]
+    with tempfile.TemporaryDirectory(prefix="elmk_build_") as keep:
+        script = pipeline(cmd, pathlib.Path(keep))
+        r = subprocess.run(["bash", "-c", script], capture_output=True, text=True, cwd=str(HERE.parent))
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libelmk_b200.so")
-    return LIB
+        raise RuntimeError("nvcc pipeline failed building libelmk_b200.so")
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _out = [a[6:] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=pathlib.Path(_out[0]) if _out else None))

@@ -31,6 +31,23 @@ ELMK_HD_NOINLINE double m_acos(double x) { return acos(x); }
 ELMK_HD_NOINLINE double m_tanh(double x) { return tanh(x); }
 ELMK_HD_NOINLINE double m_erf(double x) { return erf(x); }
 ELMK_HD_NOINLINE double m_cos(double x) { return cos(x); }
+
+// IEEE double division with a short cut for a zero numerator.  ptxas expands every `a / b` inline into a
+// Newton sequence whose fast path excludes zero and subnormal numerators; those go through a ~70-instruction
+// slow path, and column state is full of exact zeros (no snow, dry canopy, frozen soil, night).  For a == 0 and
+// a finite non-zero b the quotient is the zero with the sign of the product, i.e. exactly a * b.  The build
+// (elmkernels_b200/ptx_rewrite.py) routes every `/` of the device code through this one function, so the
+// sources keep the plain operator; the host checker build never sees the short cut.
+ELMK_HD_NOINLINE double m_div(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+  if (__builtin_expect(a == 0.0, 0)) {
+    const double m = fabs(b);
+    if (m > 0.0 && m <= 1.7976931348623157e308) return a * b;
+  }
+#endif
+  return a / b;
+}
 } // namespace elmk
 
 namespace elmk {

@@ -60,7 +60,7 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
     if (i >= NLEVSNO) {
       const int k = i - NLEVSNO;
       const double watsat = C2(watsat, k);
-      double satw = (liq / DENH2O + ice / DENICE) / (dz * watsat);
+      double satw = m_div(liq / DENH2O + ice / DENICE, dz * watsat);   // (explicit use keeps m_div in the module)
       satw = dmin(1.0, satw);
       const double tkdry = C2(tkdry, k);
       if (satw > 1.0e-6) {

@@ -1,0 +1,7 @@
+#!/bin/bash
+# A/B of differently built copies of the CUDA library (development): tools/ab.sh [ncols] lib1.so lib2.so ...
+N=${1:-2097152}; shift
+for so in "$@"; do
+  echo "== $so"
+  ELMK_LIB=$PWD/$so python bench.py --ncols $N --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python tools/show_bench.py
+done
