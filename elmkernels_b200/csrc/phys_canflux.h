@@ -80,6 +80,9 @@ struct LeafPsn {
   // inputs
   double gb_mol, je, cair, oair, lmr, par, rh_can, vcmax, pbot, cp, kc, ko, qe, tpu, kp, theta_cj, bbb, mbb;
   bool c3;
+  // sub-expressions of ci_func that do not depend on ci (same operations, same order - evaluated once per root
+  // find instead of once per function evaluation; two of them are divisions)
+  double kco, cp8, r14gb, gb16, gbmb;   // kc (1 + oair/ko), 8 cp, 1.4 / gb, 1.6 gb, gb - bbb
   // outputs of the last evaluation
   double gs_mol, ac, aj, ap, ag, an;
 };
@@ -89,8 +92,8 @@ ELMK_HD_NOINLINE double psn_ci_func(const double ci, LeafPsn& L, uint32_t& err)
 {
   constexpr double theta_ip = 0.95;
   if (L.c3) {
-    L.ac = L.vcmax * dmax(ci - L.cp, 0.0) / (ci + L.kc * (1.0 + L.oair / L.ko));
-    L.aj = L.je * dmax(ci - L.cp, 0.0) / (4.0 * ci + 8.0 * L.cp);
+    L.ac = L.vcmax * dmax(ci - L.cp, 0.0) / (ci + L.kco);
+    L.aj = L.je * dmax(ci - L.cp, 0.0) / (4.0 * ci + L.cp8);
     L.ap = 3.0 * L.tpu;
   } else {
     L.ac = L.vcmax;
@@ -104,14 +107,14 @@ ELMK_HD_NOINLINE double psn_ci_func(const double ci, LeafPsn& L, uint32_t& err)
   L.ag = dmin(r1, r2);
   L.an = L.ag - L.lmr;
   if (L.an < 0.0) return 0.0;
-  double cs = L.cair - 1.4 / L.gb_mol * L.an * L.pbot;
+  double cs = L.cair - L.r14gb * L.an * L.pbot;
   cs = dmax(cs, 1.e-6);
   const double aquad = cs;
-  const double bquad = cs * (L.gb_mol - L.bbb) - L.mbb * L.an * L.pbot;
+  const double bquad = cs * L.gbmb - L.mbb * L.an * L.pbot;
   const double cquad = -L.gb_mol * (cs * L.bbb + L.mbb * L.an * L.pbot * L.rh_can);
   psn_quadratic(aquad, bquad, cquad, r1, r2, err);
   L.gs_mol = dmax(r1, r2);
-  return ci - L.cair + L.an * L.pbot * (1.4 * L.gs_mol + 1.6 * L.gb_mol) / (L.gb_mol * L.gs_mol);
+  return ci - L.cair + L.an * L.pbot * (1.4 * L.gs_mol + L.gb16) / (L.gb_mol * L.gs_mol);
 }
 
 // Brent's method on [x1, x2] (Numerical Recipes form used by the reference)
@@ -371,6 +374,7 @@ ELMK_HD_NOINLINE double psn_stomatal_resistance(const PsnPft& P, const PsnColumn
     L.gb_mol = gb_mol; L.je = dmin(r1, r2); L.cair = cair; L.oair = oair; L.lmr = lmr_z; L.par = par;
     L.rh_can = rh_can; L.vcmax = vcmax_z; L.pbot = pbot; L.cp = cp; L.kc = kc; L.ko = ko; L.qe = P.qe;
     L.tpu = tpu_z; L.kp = kp_z; L.theta_cj = P.theta_cj; L.bbb = bbb; L.mbb = P.mbbopt; L.c3 = c3;
+    L.kco = kc * (1.0 + oair / ko); L.cp8 = 8.0 * cp; L.r14gb = 1.4 / gb_mol; L.gb16 = 1.6 * gb_mol; L.gbmb = gb_mol - bbb;
     L.gs_mol = 0.0; L.ac = 0.0; L.aj = 0.0; L.ap = 0.0; L.ag = 0.0; L.an = 0.0;
     // every call restarts from the atmospheric CO2 guess: iterations do not inherit the previous root
     psn_hybrid(c3 ? 0.7 * cair : 0.4 * cair, L, err);
@@ -405,7 +409,7 @@ ELMK_HD_NOINLINE double psn_stomatal_resistance(const PsnPft& P, const PsnColumn
 #define ELMK_CANFLUX_CARRIED(X)                                                                                   \
   X(btran) X(t_veg) X(el) X(qsatl) X(qsatldT) X(taf) X(qaf) X(dth) X(dqh) X(delq) X(um) X(obu) X(obuold) X(del)  \
   X(efeb) X(qflx_tran_veg) X(qflx_evap_veg) X(eflx_sh_veg) X(wtg) X(wtl0) X(wta0) X(wtal) X(wtgq) X(wtalq)       \
-  X(wtlq0) X(wtaq0) X(tlbef) X(dt_veg) X(p_ustar) X(p_temp1) X(p_temp2) X(p_temp12m) X(p_temp22m)
+  X(wtlq0) X(wtaq0) X(tlbef) X(dt_veg) X(p_ustar) X(p_temp1) X(p_temp2) X(p_obu)
 #define ELMK_CANFLUX_INT(X) X(nrad) X(veg) X(soybean) X(itlef) X(nmozsgn) X(err)
 
 struct CanopyIter {
@@ -536,7 +540,7 @@ ELMK_HD bool canflux_begin(const Cols& S, const Tables& T, const StepArgs& A, co
   I.qflx_tran_veg = C1(qflx_tran_veg); I.qflx_evap_veg = C1(qflx_evap_veg); I.eflx_sh_veg = C1(eflx_sh_veg);
   I.wtg = 0.0; I.wtl0 = 0.0; I.wta0 = 0.0; I.wtal = 0.0; I.wtgq = 0.0; I.wtalq = 0.0; I.wtlq0 = 0.0; I.wtaq0 = 0.0;
   I.tlbef = 0.0; I.dt_veg = 0.0;
-  I.p_ustar = 0.0; I.p_temp1 = 0.0; I.p_temp2 = 0.0; I.p_temp12m = 0.0; I.p_temp22m = 0.0;
+  I.p_ustar = 0.0; I.p_temp1 = 0.0; I.p_temp2 = 0.0; I.p_obu = 0.0;
   return true;
 }
 
@@ -551,8 +555,14 @@ ELMK_HD bool canflux_iterate(const PsnPft& P, const PsnColumn& PC, CanopyIter& I
   const double forc_rho = I.forc_rho, dtime = I.dtime, h2ocan0 = I.h2ocan0;
   const int veg = I.veg;
 
-  const MoProfiles p = mo_profiles(I.hgt_u, I.hgt_t, I.hgt_q, I.displa, I.um, I.obu, I.z0mv, I.z0mv, I.z0mv);
-  I.p_ustar = p.ustar; I.p_temp1 = p.temp1; I.p_temp2 = p.temp2; I.p_temp12m = p.temp12m; I.p_temp22m = p.temp22m;
+  // friction velocity and the profile relations at the forcing heights (z0h = z0q = z0m for vegetation).  The
+  // reference also evaluates the 2 m relations in every pass (canopy_fluxes_impl.hh:232-240) but only reads those of the last one
+  // (t_ref2m, q_ref2m): they are evaluated once, in canflux_end, from the Obukhov length this pass started with.
+  MoProfiles p;
+  p.ustar = mo_ustar(I.hgt_u, I.displa, I.um, I.obu, I.z0mv);
+  p.temp1 = mo_scalar_profile(I.hgt_t - I.displa, I.obu, I.z0mv);
+  p.temp2 = (I.hgt_q == I.hgt_t) ? p.temp1 : mo_scalar_profile(I.hgt_q - I.displa, I.obu, I.z0mv);
+  I.p_ustar = p.ustar; I.p_temp1 = p.temp1; I.p_temp2 = p.temp2; I.p_obu = I.obu;
   double t_veg = I.t_veg;
   const double tlbef = t_veg;
   I.tlbef = tlbef;
@@ -757,8 +767,10 @@ ELMK_HD void canflux_end(const Cols& S, const int c, const CanopyIter& I)
   C1(qflx_ev_soil) = forc_rho * wtgq * delq_soil;
   const double delq_h2osfc = wtalq * C1(qg_h2osfc) - wtlq0 * qsatl - wtaq0 * forc_q;
   C1(qflx_ev_h2osfc) = forc_rho * wtgq * delq_h2osfc;
-  const double t_ref2m = thm + I.p_temp1 * I.dth * (1.0 / I.p_temp12m - 1.0 / I.p_temp1);
-  const double q_ref2m = forc_q + I.p_temp2 * I.dqh * (1.0 / I.p_temp22m - 1.0 / I.p_temp2);
+  const double p_temp12m = mo_scalar_profile(2.0 + I.z0mv, I.p_obu, I.z0mv, true);
+  const double p_temp22m = p_temp12m;   // same roughness length for heat and moisture
+  const double t_ref2m = thm + I.p_temp1 * I.dth * (1.0 / p_temp12m - 1.0 / I.p_temp1);
+  const double q_ref2m = forc_q + I.p_temp2 * I.dqh * (1.0 / p_temp22m - 1.0 / I.p_temp2);
   double e2m, de2m, qsat2m, dqsat2m;
   qsat(t_ref2m, I.pbot, e2m, de2m, qsat2m, dqsat2m);
   C1(t_ref2m) = t_ref2m;

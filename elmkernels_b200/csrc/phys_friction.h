@@ -46,21 +46,48 @@ ELMK_HD void mo_initial_length(const double ur, const double thv, const double d
   obu = zldis / zeta;
 }
 
+// The four stability regimes of the two profile functions below share their leading logarithm, and the two
+// unstable (resp. stable) regimes share everything but one term.  A warp holds columns of every regime, so the
+// functions are written regime-convergent: pick the regime's operands first, then evaluate each transcendental
+// once for all lanes that need it, instead of once per regime branch (ncu, round 1: 10 active lanes per
+// instruction in this file with the reference's if / else-if ladder).  Every lane still performs exactly the
+// reference's operations in the reference's order.
+//
+// psi(-zetam), psi(-zetat) and the two constant powers are values of the reference's expressions at constant
+// arguments (evaluated with the same libm, tools/mo_constants.py); the host checker build keeps the calls.
+#ifdef ELMK_EXACT_POW
+#define ELMK_MO_PSI_M_ZETAM mo_psi_m(-1.574)
+#define ELMK_MO_PSI_H_ZETAT mo_psi_h(-0.465)
+#define ELMK_MO_POW_ZETAM m_pow(1.574, 0.333)
+#define ELMK_MO_POW_ZETAT m_pow(0.465, -0.333)
+#else
+#define ELMK_MO_PSI_M_ZETAM 0x1.5ba94811aa58ep+0
+#define ELMK_MO_PSI_H_ZETAT 0x1.569b4c1ef37bbp+0
+#define ELMK_MO_POW_ZETAM 0x1.29be614584642p+0
+#define ELMK_MO_POW_ZETAT 0x1.4a5a581293329p+0
+#endif
+
 ELMK_HD_NOINLINE double mo_ustar(const double forc_hgt_u, const double displa, const double um, const double obu,
                         const double z0m)
 {
   constexpr double zetam = 1.574;
   const double zldis = forc_hgt_u - displa;
   const double zeta = zldis / obu;
-  if (zeta < (-zetam)) {
-    return VKC * um / (m_log(-zetam * obu / z0m) - mo_psi_m(-zetam) + mo_psi_m(z0m / obu) +
-                       1.14 * (m_pow((-zeta), 0.333) - m_pow(zetam, 0.333)));
-  } else if (zeta < 0.0) {
-    return VKC * um / (m_log(zldis / z0m) - mo_psi_m(zeta) + mo_psi_m(z0m / obu));
-  } else if (zeta <= 1.0) {
-    return VKC * um / (m_log(zldis / z0m) + 5.0 * zeta - 5.0 * z0m / obu);
+  const bool unstable = (zeta < 0.0);
+  const bool far = unstable ? (zeta < (-zetam)) : !(zeta <= 1.0);   // very unstable / very stable
+  const double num = far ? (unstable ? -zetam * obu : obu) : zldis;
+  const double lead = m_log(num / z0m);
+  double den;
+  if (unstable) {
+    const double p1 = far ? ELMK_MO_PSI_M_ZETAM : mo_psi_m(zeta);
+    den = lead - p1 + mo_psi_m(z0m / obu);
+    if (far) den = den + 1.14 * (m_pow((-zeta), 0.333) - ELMK_MO_POW_ZETAM);
+  } else {
+    const double t = 5.0 * z0m / obu;
+    if (far) den = lead + 5.0 - t + (5.0 * m_log(zeta) + zeta - 1.0);
+    else den = lead + 5.0 * zeta - t;
   }
-  return VKC * um / (m_log(obu / z0m) + 5.0 - 5.0 * z0m / obu + (5.0 * m_log(zeta) + zeta - 1.0));
+  return VKC * um / den;
 }
 
 // scalar (temperature or humidity) profile relation for a reference height `zldis` above the
@@ -71,16 +98,22 @@ ELMK_HD_NOINLINE double mo_scalar_profile(const double zldis, const double obu, 
 {
   constexpr double zetat = 0.465;
   const double zeta = zldis / obu;
-  if (zeta < (-zetat)) {
-    return VKC / (m_log(-zetat * obu / z0) - mo_psi_h(-zetat) + mo_psi_h(z0 / obu) +
-                  0.8 * (m_pow(zetat, -0.333) - m_pow((-zeta), -0.333)));
-  } else if (zeta < 0.0) {
-    return VKC / (m_log(zldis / z0) - mo_psi_h(zeta) + mo_psi_h(z0 / obu));
-  } else if (zeta <= 1.0) {
-    return VKC / (m_log(zldis / z0) + 5.0 * zeta - 5.0 * z0 / obu);
+  const bool unstable = (zeta < 0.0);
+  const bool far = unstable ? (zeta < (-zetat)) : !(zeta <= 1.0);
+  const double num = far ? (unstable ? -zetat * obu : obu) : zldis;
+  const double lead = m_log(num / z0);
+  double den;
+  if (unstable) {
+    const double p1 = far ? ELMK_MO_PSI_H_ZETAT : mo_psi_h(zeta);
+    den = lead - p1 + mo_psi_h(z0 / obu);
+    if (far) den = den + 0.8 * (ELMK_MO_POW_ZETAT - m_pow((-zeta), -0.333));
+  } else if (far) {
+    const double stable = grouped ? 5.0 * (z0 / obu) : 5.0 * z0 / obu;
+    den = lead + 5.0 - stable + (5.0 * m_log(zeta) + zeta - 1.0);
+  } else {
+    den = lead + 5.0 * zeta - 5.0 * z0 / obu;
   }
-  const double stable = grouped ? 5.0 * (z0 / obu) : 5.0 * z0 / obu;
-  return VKC / (m_log(obu / z0) + 5.0 - stable + (5.0 * m_log(zeta) + zeta - 1.0));
+  return VKC / den;
 }
 
 // the five profile quantities of one stability iteration
