@@ -102,6 +102,12 @@ class Library:
             "elmk_diag_reduce": (C.c_int, [H, _PD]),
             "elmk_device_ptr": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
             "elmk_stream": (C.c_int, [H, C.POINTER(C.c_void_p)]),
+            "elmk_exchange_create": (C.c_int, [H, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(H)]),
+            "elmk_exchange_destroy": (C.c_int, [H]),
+            "elmk_exchange_post": (C.c_int, [H, C.POINTER(C.c_void_p)]),
+            "elmk_exchange_commit": (C.c_int, [H]),
+            "elmk_exchange_fetch": (C.c_int, [H, C.POINTER(C.c_void_p)]),
+            "elmk_exchange_wait": (C.c_int, [H]),
             "elmk_timing_enable": (C.c_int, [H, C.c_int]),
             "elmk_timing_read": (C.c_int, [H, C.c_int, C.POINTER(C.c_char_p), _PD, C.POINTER(C.c_int64),
                                            C.POINTER(C.c_uint32)]),
@@ -123,6 +129,52 @@ class Library:
         return Columns(self, ncols, device)
 
 
+class Exchange:
+    """Double-buffered host<->device exchange that overlaps with the step (include/elmk_b200.h, elmk_exchange_*).
+    Host arrays are in the reference layout (ncols[, nlev]); pass pinned memory for real overlap."""
+
+    def __init__(self, cols: "Columns", in_names: Sequence[str], out_names: Sequence[str]):
+        self.cols, self.in_names, self.out_names = cols, list(in_names), list(out_names)
+        ids_in = (C.c_int * len(self.in_names))(*[cols._spec(n)[0] for n in self.in_names])
+        ids_out = (C.c_int * len(self.out_names))(*[cols._spec(n)[0] for n in self.out_names])
+        self._x = C.c_void_p()
+        cols._check(cols.lib.dll.elmk_exchange_create(cols._h, len(self.in_names), ids_in, len(self.out_names), ids_out,
+                                                     C.byref(self._x)), "elmk_exchange_create")
+        self._keep = []
+
+    def _ptrs(self, names, arrays):
+        assert len(arrays) == len(names)
+        for n, a in zip(names, arrays):
+            _, dt, nl = self.cols._spec(n)
+            assert a.flags["C_CONTIGUOUS"] and a.shape[0] == self.cols.ncols and a.dtype == _NP[dt], n
+        return (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+
+    def post(self, arrays: Sequence[np.ndarray]):
+        self._keep = (self._keep + [list(arrays)])[-4:]   # the copies are asynchronous: keep the buffers alive
+        self.cols._check(self.cols.lib.dll.elmk_exchange_post(self._x, self._ptrs(self.in_names, arrays)), "elmk_exchange_post")
+
+    def commit(self):
+        self.cols._check(self.cols.lib.dll.elmk_exchange_commit(self._x), "elmk_exchange_commit")
+
+    def fetch(self, arrays: Sequence[np.ndarray]):
+        self._keep = (self._keep + [list(arrays)])[-4:]
+        self.cols._check(self.cols.lib.dll.elmk_exchange_fetch(self._x, self._ptrs(self.out_names, arrays)), "elmk_exchange_fetch")
+
+    def wait(self):
+        self.cols._check(self.cols.lib.dll.elmk_exchange_wait(self._x), "elmk_exchange_wait")
+
+    def close(self):
+        if self._x:
+            self.cols.lib.dll.elmk_exchange_destroy(self._x)
+            self._x = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Columns:
     """One handle: `ncols` land columns resident on one device."""
 
@@ -130,6 +182,7 @@ class Columns:
         self.lib, self.ncols = lib, int(ncols)
         self._h = C.c_void_p()
         self._keep = None
+        self._exchanges = []
         rc = lib.dll.elmk_create(C.byref(self._h), int(device), self.ncols)
         if rc != 0:
             raise ElmkError(f"elmk_create({ncols}) failed with {rc} on {lib.backend}")
@@ -141,6 +194,9 @@ class Columns:
             raise ElmkError(f"{what} failed with {rc}: {msg.decode() if msg else ''}")
 
     def close(self):
+        for x in getattr(self, "_exchanges", []):
+            x.close()
+        self._exchanges = []
         if self._h:
             self.lib.dll.elmk_destroy(self._h)
             self._h = C.c_void_p()
@@ -237,6 +293,12 @@ class Columns:
         ids, ptrs, k, _ = plan
         self._check(self.lib.dll.elmk_download_many(self._h, k, ids, ptrs, col0, self.ncols if n is None else n,
                                                     COL_OUTER), "elmk_download_many")
+
+    def exchange(self, in_names: Sequence[str], out_names: Sequence[str]) -> "Exchange":
+        """Overlapped per-step exchange of a fixed set of input and output fields (elmk_exchange_*)."""
+        x = Exchange(self, in_names, out_names)
+        self._exchanges.append(x)
+        return x
 
     # -- stepping --
     def init_timestep(self, reset_forc_hgt: bool = True):

@@ -689,6 +689,42 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
   return ELMK_OK;
 }
 
+// ---- overlapped per-step exchange (see include/elmk_b200.h) ----
+struct Exchange {
+  Ctx* c = nullptr;
+  std::vector<int> in_fields, out_fields;
+  std::vector<size_t> in_off, out_off;   // byte offsets of the fields inside one staging slot
+  size_t in_bytes = 0, out_bytes = 0;
+  char* in_stage[2] = {nullptr, nullptr};
+  char* out_stage[2] = {nullptr, nullptr};
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t in_ready[2] = {nullptr, nullptr};     // H2D of the slot finished            (recorded on s_in)
+  cudaEvent_t in_consumed[2] = {nullptr, nullptr};  // commit has read the slot            (recorded on the step stream)
+  cudaEvent_t out_ready[2] = {nullptr, nullptr};    // snapshot written into the slot      (recorded on the step stream)
+  cudaEvent_t out_done[2] = {nullptr, nullptr};     // D2H of the slot finished            (recorded on s_out)
+  int64_t posts = 0, commits = 0, fetches = 0, waits = 0;
+};
+Exchange* xch(elmk_exchange x) { return reinterpret_cast<Exchange*>(x); }
+
+size_t field_bytes(const Ctx* c, int field) { return (size_t)c->ncols * kSpecs[field].nlev * esize(kSpecs[field].dtype); }
+
+// staging (reference layout rows) <-> field (column-innermost), on the step stream
+int exchange_convert(Ctx* c, int field, char* staged, bool up) {
+  const int nlev = kSpecs[field].nlev, dt = kSpecs[field].dtype;
+  char* dev = static_cast<char*>(c->base[field]);
+  if (nlev == 1) {
+    if (up) CU(cudaMemcpyAsync(dev, staged, field_bytes(c, field), cudaMemcpyDeviceToDevice, c->stream));
+    else CU(cudaMemcpyAsync(staged, dev, field_bytes(c, field), cudaMemcpyDeviceToDevice, c->stream));
+    return ELMK_OK;
+  }
+  if (dt == ELMK_F64) return up ? convert<double>(c, true, (const double*)staged, (double*)dev, c->ncols, nlev, 0)
+                                : convert<double>(c, false, (const double*)dev, (double*)staged, c->ncols, nlev, 0);
+  if (dt == ELMK_I32) return up ? convert<int>(c, true, (const int*)staged, (int*)dev, c->ncols, nlev, 0)
+                                : convert<int>(c, false, (const int*)dev, (int*)staged, c->ncols, nlev, 0);
+  return up ? convert<unsigned char>(c, true, (const unsigned char*)staged, (unsigned char*)dev, c->ncols, nlev, 0)
+            : convert<unsigned char>(c, false, (const unsigned char*)dev, (unsigned char*)staged, c->ncols, nlev, 0);
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -881,6 +917,141 @@ int elmk_download_many(elmk_handle h, int nf, const int* fields, void* const* ho
   for (int i = 0; i < nf; ++i)
     if (int rc = move_field(c, fields[i], hosts[i], col0, n, layout, false)) return rc;
   CU(cudaStreamSynchronize(c->stream));
+  return ELMK_OK;
+}
+
+int elmk_exchange_create(elmk_handle h, int n_in, const int* in_fields, int n_out, const int* out_fields,
+                         elmk_exchange* out) {
+  Ctx* c = ctx(h);
+  if (!c || !out || n_in < 0 || n_out < 0 || (n_in && !in_fields) || (n_out && !out_fields)) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  auto* x = new Exchange();
+  x->c = c;
+  auto layout = [&](int n, const int* f, std::vector<int>& ids, std::vector<size_t>& off, size_t& total) {
+    for (int i = 0; i < n; ++i) {
+      if (f[i] < 0 || f[i] >= kNumFields) return false;
+      ids.push_back(f[i]);
+      off.push_back(total);
+      total += (field_bytes(c, f[i]) + 255) / 256 * 256;
+    }
+    return true;
+  };
+  if (!layout(n_in, in_fields, x->in_fields, x->in_off, x->in_bytes) ||
+      !layout(n_out, out_fields, x->out_fields, x->out_off, x->out_bytes)) {
+    delete x;
+    c->last_error = "elmk_exchange_create: bad field id";
+    return ELMK_EINVAL;
+  }
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  ok(cudaStreamCreateWithFlags(&x->s_in, cudaStreamNonBlocking));
+  ok(cudaStreamCreateWithFlags(&x->s_out, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; ++s) {
+    if (x->in_bytes) ok(cudaMalloc(&x->in_stage[s], x->in_bytes));
+    if (x->out_bytes) ok(cudaMalloc(&x->out_stage[s], x->out_bytes));
+    ok(cudaEventCreateWithFlags(&x->in_ready[s], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&x->in_consumed[s], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&x->out_ready[s], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&x->out_done[s], cudaEventDisableTiming));
+  }
+  if (e != cudaSuccess) {
+    elmk_exchange_destroy(reinterpret_cast<elmk_exchange>(x));
+    return fail(c, e, "elmk_exchange_create");
+  }
+  *out = reinterpret_cast<elmk_exchange>(x);
+  return ELMK_OK;
+}
+
+int elmk_exchange_destroy(elmk_exchange xh) {
+  Exchange* x = xch(xh);
+  if (!x) return ELMK_EINVAL;
+  cudaSetDevice(x->c->device);
+  if (x->s_in) cudaStreamSynchronize(x->s_in);
+  if (x->s_out) cudaStreamSynchronize(x->s_out);
+  cudaStreamSynchronize(x->c->stream);
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(x->in_stage[s]);
+    cudaFree(x->out_stage[s]);
+    if (x->in_ready[s]) cudaEventDestroy(x->in_ready[s]);
+    if (x->in_consumed[s]) cudaEventDestroy(x->in_consumed[s]);
+    if (x->out_ready[s]) cudaEventDestroy(x->out_ready[s]);
+    if (x->out_done[s]) cudaEventDestroy(x->out_done[s]);
+  }
+  if (x->s_in) cudaStreamDestroy(x->s_in);
+  if (x->s_out) cudaStreamDestroy(x->s_out);
+  delete x;
+  return ELMK_OK;
+}
+
+int elmk_exchange_post(elmk_exchange xh, const void* const* in_hosts) {
+  Exchange* x = xch(xh);
+  if (!x || (!in_hosts && !x->in_fields.empty())) return ELMK_EINVAL;
+  Ctx* c = x->c;
+  if (int rc = bind(c)) return rc;
+  if (x->posts - x->commits >= 2) {
+    c->last_error = "elmk_exchange_post: two posts already await elmk_exchange_commit";
+    return ELMK_EINVAL;
+  }
+  const int slot = (int)(x->posts & 1);
+  if (x->posts >= 2) CU(cudaStreamWaitEvent(x->s_in, x->in_consumed[slot], 0));   // the slot's previous contents were committed
+  for (size_t i = 0; i < x->in_fields.size(); ++i)
+    CU(cudaMemcpyAsync(x->in_stage[slot] + x->in_off[i], in_hosts[i], field_bytes(c, x->in_fields[i]),
+                       cudaMemcpyHostToDevice, x->s_in));
+  CU(cudaEventRecord(x->in_ready[slot], x->s_in));
+  x->posts += 1;
+  return ELMK_OK;
+}
+
+int elmk_exchange_commit(elmk_exchange xh) {
+  Exchange* x = xch(xh);
+  if (!x) return ELMK_EINVAL;
+  Ctx* c = x->c;
+  if (int rc = bind(c)) return rc;
+  if (x->commits >= x->posts) {
+    c->last_error = "elmk_exchange_commit without a matching elmk_exchange_post";
+    return ELMK_EINVAL;
+  }
+  const int slot = (int)(x->commits & 1);
+  CU(cudaStreamWaitEvent(c->stream, x->in_ready[slot], 0));
+  for (size_t i = 0; i < x->in_fields.size(); ++i)
+    if (int rc = exchange_convert(c, x->in_fields[i], x->in_stage[slot] + x->in_off[i], true)) return rc;
+  CU(cudaEventRecord(x->in_consumed[slot], c->stream));
+  x->commits += 1;
+  return ELMK_OK;
+}
+
+int elmk_exchange_fetch(elmk_exchange xh, void* const* out_hosts) {
+  Exchange* x = xch(xh);
+  if (!x || (!out_hosts && !x->out_fields.empty())) return ELMK_EINVAL;
+  Ctx* c = x->c;
+  if (int rc = bind(c)) return rc;
+  if (x->fetches - x->waits >= 2) {
+    c->last_error = "elmk_exchange_fetch: two fetches already await elmk_exchange_wait";
+    return ELMK_EINVAL;
+  }
+  const int slot = (int)(x->fetches & 1);
+  if (x->fetches >= 2) CU(cudaStreamWaitEvent(c->stream, x->out_done[slot], 0));   // the slot's previous snapshot left the device
+  for (size_t i = 0; i < x->out_fields.size(); ++i)
+    if (int rc = exchange_convert(c, x->out_fields[i], x->out_stage[slot] + x->out_off[i], false)) return rc;
+  CU(cudaEventRecord(x->out_ready[slot], c->stream));
+  CU(cudaStreamWaitEvent(x->s_out, x->out_ready[slot], 0));
+  for (size_t i = 0; i < x->out_fields.size(); ++i)
+    CU(cudaMemcpyAsync(out_hosts[i], x->out_stage[slot] + x->out_off[i], field_bytes(c, x->out_fields[i]),
+                       cudaMemcpyDeviceToHost, x->s_out));
+  CU(cudaEventRecord(x->out_done[slot], x->s_out));
+  x->fetches += 1;
+  return ELMK_OK;
+}
+
+int elmk_exchange_wait(elmk_exchange xh) {
+  Exchange* x = xch(xh);
+  if (!x) return ELMK_EINVAL;
+  Ctx* c = x->c;
+  if (int rc = bind(c)) return rc;
+  if (x->waits >= x->fetches) return ELMK_OK;   // nothing outstanding
+  const int slot = (int)(x->waits & 1);
+  CU(cudaEventSynchronize(x->out_done[slot]));
+  x->waits += 1;
   return ELMK_OK;
 }
 

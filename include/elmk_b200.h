@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ELMK_ABI_VERSION 1
+#define ELMK_ABI_VERSION 2
 
 /* ---- dimensions (reference src/data/elm_constants.h:84-98) ---- */
 #define ELMK_NLEVSNO 5
@@ -154,6 +154,30 @@ int elmk_upload_many(elmk_handle h, int nfields, const int* fields, const void* 
                      int64_t col0, int64_t n, int layout);
 int elmk_download_many(elmk_handle h, int nfields, const int* fields, void* const* hosts,
                        int64_t col0, int64_t n, int layout);
+
+/* ---- overlapped per-step exchange.  The reference's driver refreshes the forcing of ELMState and copies the
+ *      primary variables out once per step from the single host thread that also runs the kernels
+ *      (elm_kokkos_interface.cc:269-288 and copyPrimaryVars :324-347): movement and compute are serial.  An
+ *      exchange owns two copy streams and double-buffered device staging for a fixed set of input fields and a
+ *      fixed set of output fields (reference host layout, ELMK_COL_OUTER, all columns of the handle), so that the
+ *      host->device copy of step k+1's inputs and the device->host copy of step k's outputs run while step k+1
+ *      computes:
+ *        elmk_exchange_post(x, in_hosts)    start the asynchronous copy of the next inputs into staging;
+ *        elmk_exchange_commit(x)            the inputs posted last become the fields' contents, ordered after
+ *                                           everything issued on the handle's stream so far;
+ *        elmk_exchange_fetch(x, out_hosts)  snapshot the output fields (ordered after everything issued so far)
+ *                                           and start their asynchronous copy to out_hosts;
+ *        elmk_exchange_wait(x)              block until the oldest unfinished fetch has arrived on the host.
+ *      At most two posts and two fetches can be in flight.  Host buffers should be pinned
+ *      (cudaHostAlloc / cudaHostRegister); pageable memory works but does not overlap. ---- */
+typedef struct elmk_exchange_s* elmk_exchange;
+int elmk_exchange_create(elmk_handle h, int n_in, const int* in_fields, int n_out, const int* out_fields,
+                         elmk_exchange* out);
+int elmk_exchange_destroy(elmk_exchange x);
+int elmk_exchange_post(elmk_exchange x, const void* const* in_hosts);
+int elmk_exchange_commit(elmk_exchange x);
+int elmk_exchange_fetch(elmk_exchange x, void* const* out_hosts);
+int elmk_exchange_wait(elmk_exchange x);
 
 /* ---- the per-column part of kokkos_init_timestep (init_timestep_kokkos.cc:53-72):
  *      h2osno_old, dtbegin_column_h2o, ELM::init_timestep; resets forc_hgt_*_patch to

@@ -257,4 +257,6 @@ int elmk_stream(elmk_handle, void** stream) { if (stream) *stream = nullptr; ret
 int elmk_timing_enable(elmk_handle, int) { return ELMK_OK; }
 int elmk_timing_read(elmk_handle, int, const char**, double*, int64_t*, uint32_t*) { return 0; }
 
+#include "../exchange_host.h"
+
 } // extern "C"

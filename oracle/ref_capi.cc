@@ -501,4 +501,6 @@ int elmref_init_columns(elmk_handle h, const double* pct_sand, const double* pct
   return ELMK_OK;
 }
 
+#include "exchange_host.h"
+
 } // extern "C"
