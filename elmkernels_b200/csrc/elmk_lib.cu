@@ -123,8 +123,8 @@ template <uint32_t MASK> __device__ __forceinline__ int work_class(const Cols& S
 // BLOCK threads per block; LOCKSTEP: the warps of a block take their chunks round by round behind a block
 // barrier (instruction-cache locality for the kernels whose body exceeds the 32 KB L1.5 cache), otherwise
 // they pull chunks from a shared counter (load balance).
-template <uint32_t MASK, int BLOCK, bool LOCKSTEP>
-__global__ void __launch_bounds__(BLOCK) k_groups_sorted(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
+template <uint32_t MASK, int BLOCK, bool LOCKSTEP, int MINBLOCKS = 1>
+__global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_groups_sorted(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
 {
   __shared__ unsigned short order[kWindow];
   __shared__ int count[kClasses], start[kClasses], next_chunk;
@@ -361,6 +361,16 @@ const Launch kFused[] = {
     ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 3),
     ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 6),
 };
+// development: alternative launch configurations of the radiative-transfer launch (ELMK_RAD_VARIANT=1..)
+#define ELMK_LAUNCH_SORTED_OCC(M, NAME, BLOCK, LOCKSTEP, MINB) {(M), k_groups_sorted<(M), BLOCK, LOCKSTEP, MINB>, NAME, kWindow, BLOCK}
+const Launch kRadVariants[] = {
+    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 128, false, 3),
+    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 128, false, 4),
+    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 256, false, 1),
+    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 256, false, 2),
+    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 256, true, 1),
+    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 512, true, 1),
+};
 // plan "unsorted": the fused cut without work-class ordering (for A/B measurements)
 const Launch kFusedUnsorted[] = {
     ELMK_LAUNCH(M_RAD, "fracwet+albedo"),
@@ -524,6 +534,7 @@ struct Ctx {
   std::vector<Acc> acc;
   const Launch* plan = kFused;
   int plan_len = sizeof(kFused) / sizeof(kFused[0]);
+  std::vector<Launch> plan_own;   // a modified copy of a built-in plan (development variants)
   std::string last_error;
 };
 Ctx* ctx(elmk_handle h) { return reinterpret_cast<Ctx*>(h); }
@@ -665,6 +676,8 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
       case 4: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<384, true>, 384, 0)); break;
       case 5: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<512, true>, 512, 0)); break;
       case 6: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<768, true>, 768, 0)); break;
+      case 7: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<640, true>, 640, 0)); break;
+      case 8: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<448, true>, 448, 0)); break;
       default: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<128, false>, 128, 0)); break;
     }
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
@@ -681,6 +694,8 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
     case 4: k_canflux_iterate<384, true><<<persistent, 384, 0, c->stream>>>(c->cols, c->cq); break;
     case 5: k_canflux_iterate<512, true><<<persistent, 512, 0, c->stream>>>(c->cols, c->cq); break;
     case 6: k_canflux_iterate<768, true><<<persistent, 768, 0, c->stream>>>(c->cols, c->cq); break;
+    case 7: k_canflux_iterate<640, true><<<persistent, 640, 0, c->stream>>>(c->cols, c->cq); break;
+    case 8: k_canflux_iterate<448, true><<<persistent, 448, 0, c->stream>>>(c->cols, c->cq); break;
     default: k_canflux_iterate<128, false><<<persistent, 128, 0, c->stream>>>(c->cols, c->cq); break;
   }
   k_canflux_end<<<grid, kBlock, 0, c->stream>>>(c->cols, c->cq);
@@ -810,6 +825,14 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
   }
   const char* rp = std::getenv("ELMK_CANFLUX_REPACK");
   if (rp && rp[0] == '0') c->repack = false;
+  const char* rv = std::getenv("ELMK_RAD_VARIANT");
+  if (rv && c->plan == kFused) {
+    const int v = std::atoi(rv);
+    if (v >= 1 && v <= (int)(sizeof(kRadVariants) / sizeof(kRadVariants[0]))) {
+      c->plan_own.assign(kFused, kFused + c->plan_len);
+      c->plan_own[0] = kRadVariants[v - 1];
+    }
+  }
   *out = reinterpret_cast<elmk_handle>(c);
   return ELMK_OK;
 }
@@ -1098,7 +1121,7 @@ int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_
   // cover the requested groups, in chain order, with the launches of the plan; a launch whose group
   // set is only partly requested falls back to one launch per requested group
   for (int i = 0; i < c->plan_len; ++i) {
-    const Launch& L = c->plan[i];
+    const Launch& L = c->plan_own.empty() ? c->plan[i] : c->plan_own[i];
     const uint32_t want = L.mask & mask;
     if (!want) continue;
     if (want == L.mask && L.mask == ELMK_G_CANOPY_FLUXES && c->repack && c->plan != kSplit && c->plan != kFusedUnsorted) {

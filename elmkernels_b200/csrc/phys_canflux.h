@@ -87,8 +87,8 @@ struct LeafPsn {
   double gs_mol, ac, aj, ap, ag, an;
 };
 
-// f(ci) = ci - (ca - (1.4/gb + 1.6/gs) p an)
-ELMK_HD_NOINLINE double psn_ci_func(const double ci, LeafPsn& L, uint32_t& err)
+// f(ci) = ci - (ca - (1.4/gb + 1.6/gs) p an).  Inlined at its single call site (psn_hybrid below).
+ELMK_HD double psn_ci_func(const double ci, LeafPsn& L, uint32_t& err)
 {
   constexpr double theta_ip = 0.95;
   if (L.c3) {
@@ -117,19 +117,99 @@ ELMK_HD_NOINLINE double psn_ci_func(const double ci, LeafPsn& L, uint32_t& err)
   return ci - L.cair + L.an * L.pbot * (1.4 * L.gs_mol + L.gb16) / (L.gb_mol * L.gs_mol);
 }
 
-// Brent's method on [x1, x2] (Numerical Recipes form used by the reference)
-ELMK_HD double psn_brent(const double x1, const double x2, const double f1, const double f2, const double tol,
-                         LeafPsn& L, uint32_t& err)
+// Root of ci_func: secant search for a sign change, Brent's method (Numerical Recipes form) once a root is
+// bracketed; leaves the side outputs of the last ci_func evaluation in L.  Reference: hybrid
+// (photosynthesis_impl.hh:517-600) calling brent (:396-515), both calling ci_func at several places.
+//
+// Written here as ONE loop around ONE ci_func evaluation, with the position inside the reference's control flow
+// kept in `state`: the sequence of evaluation points and every arithmetic operation are the reference's, but
+//   * the lanes of a warp meet at the same ci_func code whatever phase (first two points, secant, Brent, fall-back)
+//     each of them is in, instead of executing the phases one after the other;
+//   * with a single call site ci_func is inlined and LeafPsn lives in registers - as a called function with the
+//     state behind a reference it cost ~40 local-memory accesses per evaluation (round-1 ncu: 18 M local loads
+//     and 18 M local stores per 512k columns in the iteration kernel).
+ELMK_HD void psn_hybrid(double x0, LeafPsn& L, uint32_t& err)
 {
-  constexpr int ITMAX = 20;
-  constexpr double EPS = 1.0e-2;
-  double a = x1, b = x2, fa = f1, fb = f2;
-  if ((fa > 0.0 && fb > 0.0) || (fa < 0.0 && fb < 0.0)) err |= ERR_BRENT_BRACKET;
-  double cc = b, fc = fb;
-  double d = 0.0, e = 0.0;
+  constexpr double eps = 1.0e-2;
+  constexpr double eps1 = 1.0e-4;
+  constexpr int itmax = 40;
+  constexpr int BRENT_ITMAX = 20;
+  constexpr double BRENT_EPS = 1.0e-2;
+  enum { AT_X0, AT_X1, IN_SECANT, IN_BRENT, AT_MINX };
+  int state = AT_X0;
+  double x = x0;                            // where ci_func is evaluated next
+  double f0 = 0.0, x1 = 0.0, f1 = 0.0, minx = x0, minf = 0.0, tol = 0.0;
   int iter = 0;
-  while (iter != ITMAX) {
-    iter += 1;
+  double a = 0.0, b = 0.0, cc = 0.0, fa = 0.0, fb = 0.0, fc = 0.0, d = 0.0, e = 0.0;   // Brent
+  int biter = 0;
+#pragma unroll 1
+  while (true) {
+    const double f = psn_ci_func(x, L, err);
+    bool brent_step = false;
+    if (state == AT_X0) {
+      f0 = f;
+      if (f0 == 0.0) break;
+      minx = x0;
+      minf = f0;
+      x1 = x0 * 0.99;
+      x = x1;
+      state = AT_X1;
+      continue;
+    } else if (state == AT_X1) {
+      f1 = f;
+      if (f1 == 0.0) break;
+      if (f1 < minf) {
+        minx = x1;
+        minf = f1;
+      }
+      iter = 0;
+    } else if (state == IN_SECANT) {
+      f1 = f;
+      if (f1 < minf) {
+        minx = x1;
+        minf = f1;
+      }
+      if (fabs(f1) <= eps1) break;
+      if (f1 * f0 < 0.0) {
+        // bracketed: Brent on [x0, x1] with the tolerance of the last secant step
+        a = x0; b = x1; fa = f0; fb = f1;
+        if ((fa > 0.0 && fb > 0.0) || (fa < 0.0 && fb < 0.0)) err |= ERR_BRENT_BRACKET;
+        cc = b; fc = fb;
+        d = 0.0; e = 0.0;
+        biter = 0;
+        brent_step = true;
+      } else if (iter > itmax) {
+        // not converged: fall back to the evaluation with the smallest residual
+        x = minx;
+        state = AT_MINX;
+        continue;
+      }
+    } else if (state == IN_BRENT) {
+      fb = f;
+      if (fb == 0.0) break;
+      brent_step = true;
+    } else {
+      break;   // AT_MINX: that evaluation was the last one
+    }
+
+    if (!brent_step) {
+      // one secant step
+      iter += 1;
+      const double dx = -f1 * (x1 - x0) / (f1 - f0);
+      const double xn = x1 + dx;
+      tol = fabs(xn) * eps;
+      if (fabs(dx) < tol) break;
+      x0 = x1;
+      f0 = f1;
+      x1 = xn;
+      x = x1;
+      state = IN_SECANT;
+      continue;
+    }
+
+    // one Brent step: the body of the reference's loop up to its ci_func call
+    if (biter == BRENT_ITMAX) break;
+    biter += 1;
     if ((fb > 0.0 && fc > 0.0) || (fb < 0.0 && fc < 0.0)) {
       cc = a;
       fc = fa;
@@ -144,9 +224,9 @@ ELMK_HD double psn_brent(const double x1, const double x2, const double f1, cons
       fb = fc;
       fc = fa;
     }
-    const double tol1 = 2.0 * EPS * fabs(b) + 0.5 * tol;
+    const double tol1 = 2.0 * BRENT_EPS * fabs(b) + 0.5 * tol;
     const double xm = 0.5 * (cc - b);
-    if (fabs(xm) <= tol1 || fb == 0.0) return b;
+    if (fabs(xm) <= tol1 || fb == 0.0) break;
     if (fabs(e) >= tol1 && fabs(fa) > fabs(fb)) {
       const double s = fb / fa;
       double p, q;
@@ -179,54 +259,8 @@ ELMK_HD double psn_brent(const double x1, const double x2, const double f1, cons
     } else {
       b = b + copysign(tol1, xm);
     }
-    fb = psn_ci_func(b, L, err);
-    if (fb == 0.0) break;
-  }
-  return b;
-}
-
-// secant search for a sign change, Brent once bracketed; leaves the side outputs of the last
-// ci_func evaluation in L
-ELMK_HD void psn_hybrid(double x0, LeafPsn& L, uint32_t& err)
-{
-  constexpr double eps = 1.0e-2;
-  constexpr double eps1 = 1.0e-4;
-  constexpr int itmax = 40;
-  double f0 = psn_ci_func(x0, L, err);
-  if (f0 == 0.0) return;
-  double minx = x0, minf = f0;
-  double x1 = x0 * 0.99;
-  double f1 = psn_ci_func(x1, L, err);
-  if (f1 == 0.0) return;
-  if (f1 < minf) {
-    minx = x1;
-    minf = f1;
-  }
-  int iter = 0;
-  while (true) {
-    iter += 1;
-    const double dx = -f1 * (x1 - x0) / (f1 - f0);
-    const double x = x1 + dx;
-    const double tol = fabs(x) * eps;
-    if (fabs(dx) < tol) break;
-    x0 = x1;
-    f0 = f1;
-    x1 = x;
-    f1 = psn_ci_func(x1, L, err);
-    if (f1 < minf) {
-      minx = x1;
-      minf = f1;
-    }
-    if (fabs(f1) <= eps1) break;
-    if (f1 * f0 < 0.0) {
-      psn_brent(x0, x1, f0, f1, tol, L, err);
-      break;
-    }
-    if (iter > itmax) {
-      // not converged: fall back to the evaluation with the smallest residual
-      f1 = psn_ci_func(minx, L, err);
-      break;
-    }
+    x = b;
+    state = IN_BRENT;
   }
 }
 
@@ -312,7 +346,7 @@ ELMK_HD PsnPass psn_pass(const PsnPft& P, const PsnColumn& C, const double t_veg
 }
 
 // stomatal resistance of the sunlit or the shaded canopy fraction (nlevcan == 1, nrad == 1)
-ELMK_HD_NOINLINE double psn_stomatal_resistance(const PsnPft& P, const PsnColumn& C, const PsnPass& T, const int nrad,
+ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const PsnColumn& C, const PsnPass& T, const int nrad,
                                                 const double pbot, const double esat_tv, const double eair,
                                                 const double oair, const double cair, const double rb,
                                                 const double btran, const double vcmaxcint, const double par,
@@ -590,12 +624,16 @@ ELMK_HD bool canflux_iterate(const PsnPft& P, const PsnColumn& PC, CanopyIter& I
 
   double btran = I.btran;
   const PsnPass PT = psn_pass(P, PC, t_veg, (I.parsun > 0.0) || (I.parsha > 0.0));
-  if (I.soybean) btran = dmin(1.0, btran * 1.25);
-  const double rssun = psn_stomatal_resistance(P, PC, PT, I.nrad, pbot, svpts, eah, I.forc_po2, I.forc_pco2, rb, btran,
-                                               I.vcsun, I.parsun, I.laisun_z, err);
-  if (I.soybean) btran = dmin(1.0, btran * 1.25);
-  const double rssha = psn_stomatal_resistance(P, PC, PT, I.nrad, pbot, svpts, eah, I.forc_po2, I.forc_pco2, rb, btran,
-                                               I.vcsha, I.parsha, I.laisha_z, err);
+  // sunlit, then shaded leaves: one copy of the (inlined) photosynthesis code, run twice
+  double rssun = 0.0, rssha = 0.0;
+#pragma unroll 1
+  for (int leaf = 0; leaf < 2; ++leaf) {
+    if (I.soybean) btran = dmin(1.0, btran * 1.25);
+    const double rs = psn_stomatal_resistance(P, PC, PT, I.nrad, pbot, svpts, eah, I.forc_po2, I.forc_pco2, rb, btran,
+                                              leaf ? I.vcsha : I.vcsun, leaf ? I.parsha : I.parsun,
+                                              leaf ? I.laisha_z : I.laisun_z, err);
+    if (leaf) rssha = rs; else rssun = rs;
+  }
   I.btran = btran;
 
   // sensible-heat conductances: air, leaf, ground

@@ -16,8 +16,12 @@ namespace elmk {
 
 // Saturation vapour pressure es [Pa], specific humidity qs [kg/kg] and their temperature
 // derivatives: 8th-order polynomials over water (0..100 C) and over ice (-75..0 C), Horner form.
-ELMK_HD_NOINLINE void qsat(const double T, const double p, double& es, double& esdT, double& qs, double& qsdT)
+// The called copy returns its four results by value: reference parameters of a non-inlined function would force
+// the caller's variables - in CanopyFluxes, members of the iteration state - into local memory.
+struct QSat { double es, esdT, qs, qsdT; };
+ELMK_HD_NOINLINE QSat qsat_values(const double T, const double p)
 {
+  double es, esdT, qs, qsdT;
   double td = T - TFRZ;
   if (td > 100.0) td = 100.0;
   if (td < -75.0) td = -75.0;
@@ -39,6 +43,12 @@ ELMK_HD_NOINLINE void qsat(const double T, const double p, double& es, double& e
   const double vp2 = vp1 * vp;
   qs = es * vp1;
   qsdT = esdT * vp2 * p;
+  return {es, esdT, qs, qsdT};
+}
+ELMK_HD void qsat(const double T, const double p, double& es, double& esdT, double& qs, double& qsdT)
+{
+  const QSat q = qsat_values(T, p);
+  es = q.es; esdT = q.esdT; qs = q.qs; qsdT = q.qsdT;
 }
 
 ELMK_HD void column_canopy_temperature(const Cols& S, const Tables& T, const int c)
