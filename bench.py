@@ -90,10 +90,23 @@ def make_chunk(params, fields, ncols, seed):
     return st, forcing
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms are meant to use every host core."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (oracle/_ref), all host threads."""
     if rank != 0:
         return
+    use_all_host_threads()
     from elmkernels_b200 import abi, params as prm
     path = os.path.join(ROOT, "oracle", "_ref", "libelmref.so")
     kind = "reference"
@@ -139,6 +152,7 @@ def cpu_baseline(P, ncols, steps=3, warmup=1):
         path, kind = os.path.join(ROOT, "oracle", "port", "_build", "libelmport.so"), "port"
     if not os.path.exists(path):
         return None
+    use_all_host_threads()
     lib = abi.Library(path)
     st, forcing = make_chunk(P, lib.fields, ncols, 20240000 + 5)
     cols = lib.columns(ncols)
