@@ -43,6 +43,24 @@ FORCING_FIELDS = ("coszen forc_tbot forc_thbot forc_pbot forc_qbot forc_lwrad fo
 RESULT_FIELDS = "dtend_column_h2o errh2o errh2osno dwb errsol errlon errseb netrad errmask".split()
 
 
+def kernel_counters():
+    """ncu counters of one step of this workload (profiles/r1_kernel_counters.json, written by tools/ncu_counters.py
+    from a capture of `bench.py --ncols 524288 --steps 1`): DRAM bytes and FP64 instructions per column and launch
+    group.  Static evidence committed with the repo - nothing is profiled while the benchmark runs."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_counters.json")))
+    except Exception:
+        return None
+
+
+def fp64_peak():
+    """Measured FP64 pipe peak of this pool's B200 (tools/fp64_peak.cu -> profiles/r1_fp64_peak.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_peak.json")))
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -349,6 +367,21 @@ def main():
         achieved = bytes_per_col * n / (per_launch_ms * 1e-3) / 1e9
         value = n * world * args.steps / (ms * 1e-3)
         e2e = n * world * args.steps / (ms_e2e * 1e-3)
+        counters, fpk = kernel_counters(), fp64_peak()
+        cg = (counters or {}).get("groups", {})
+        traffic = cg[top[0]]["dram_bytes_per_column"] * n if top[0] in cg else None
+        fp64 = None
+        if top[0] in cg and fpk:
+            # FP64 pipe: thread-level DADD+DMUL+DFMA instructions per launch / live duration, against the measured
+            # instruction rate of the pipe (a DFMA counts as one instruction; the physics is built without FMA
+            # contraction, so its flop rate is bounded by the DMUL/DADD figure)
+            inst = cg[top[0]]["fp64_inst_per_column"] * n
+            peak_inst = fpk["dfma_tflops"] / 2.0
+            fp64 = {"achieved": inst / (per_launch_ms * 1e-3) / 1e12, "peak": peak_inst, "unit": "T FP64 inst/s",
+                    "frac": inst / (per_launch_ms * 1e-3) / 1e12 / peak_inst,
+                    "flop_per_column": cg[top[0]]["flop_per_column"], "inst_per_column": cg[top[0]]["fp64_inst_per_column"],
+                    "peak_source": "measured DFMA microbenchmark (profiles/r1_fp64_peak.json)",
+                    "counts_source": "ncu, profiles/r1_kernel_counters.json (%d columns)" % counters["ncols"]}
         line = {
             "metric": METRIC, "value": value, "unit": "column-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -359,7 +392,8 @@ def main():
                        "parallelism": f"columns sharded over {world} GPU(s), no collective on the step",
                        "l2": "inputs larger than L2: %.1f GB of column state per GPU vs 126 MB" % (n * 5765 / 1e9)},
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "fp64": fp64,
+                         "note": "the dominant launch is bounded by FP64 latency / issue, not by HBM: see fp64 and DESIGN.md section 4",
                          "bytes_per_column": bytes_per_col, "ms_per_launch": per_launch_ms,
                          "share_of_step": top[2] / total_kernel_ms,
                          "step": {"bytes_per_column": ALGORITHMIC_BYTES_PER_COLUMN_STEP,
@@ -367,7 +401,9 @@ def main():
                                   "frac": ALGORITHMIC_BYTES_PER_COLUMN_STEP * n * args.steps / (ms * 1e-3) / 1e9 / peak},
                          "kernels": {k[0]: {"ms_per_launch": k[2] / k[3], "share": k[2] / total_kernel_ms,
                                             "bytes_per_column": launch_bytes(gb, k[1]),
-                                            "GBps": launch_bytes(gb, k[1]) * n / (k[2] / k[3] * 1e-3) / 1e9}
+                                            "GBps": launch_bytes(gb, k[1]) * n / (k[2] / k[3] * 1e-3) / 1e9,
+                                            "traffic_bytes_per_column": cg.get(k[0], {}).get("dram_bytes_per_column"),
+                                            "fp64_inst_per_column": cg.get(k[0], {}).get("fp64_inst_per_column")}
                                      for k in kern}},
             "e2e": {"value": e2e, "unit": "column-steps/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps},

@@ -26,11 +26,6 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "--expt-relaxed-constexpr", "-diag-suppress", "550", "-Xcompiler", "-fPIC", "-shared"]
 
 
-# kernels / device functions (regex on the mangled name) that keep their divisions in line behind a zero test
-# instead of calling m_div (see ptx_rewrite.py)
-INLINE_DIV = os.environ.get("ELMK_INLINE_DIV", "")
-
-
 def sources():
     return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.h")) + [HERE / "ptx_rewrite.py", HERE / "build.py",HERE.parent / "include/elmk_b200.h",
                                                                      HERE.parent / "include/elmk_fields.def"]
@@ -67,8 +62,7 @@ def pipeline(cmd, keep: pathlib.Path):
             if not m:
                 raise RuntimeError("could not find the PTX file in nvcc's ptxas step")
             ptx = m.group(1)
-            script.append(f"{shlex.quote(sys.executable)} {shlex.quote(str(HERE / 'ptx_rewrite.py'))} {shlex.quote(ptx)} "
-                          f"{shlex.quote(INLINE_DIV)}")
+            script.append(f"{shlex.quote(sys.executable)} {shlex.quote(str(HERE / 'ptx_rewrite.py'))} {shlex.quote(ptx)}")
         script.append(line)
     if ptx is None:
         raise RuntimeError("nvcc --dryrun listed no ptxas step")

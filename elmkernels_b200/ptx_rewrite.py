@@ -17,6 +17,7 @@ bit-identical to IEEE division in every case - this is a code-generation change,
 from __future__ import annotations
 
 import re
+import struct
 import sys
 
 DIV = re.compile(r"^(\s*)div\.rn\.f64\s+(%fd\d+),\s*([^,]+),\s*([^;]+);\s*$")
@@ -40,54 +41,136 @@ def _call(ind: str, d: str, a: str, b: str) -> str:
             f"{ind}ld.param.f64 \t{d}, [retval0];\n{ind}}}")
 
 
-def rewrite(text: str, inline_pattern: str | None = None) -> tuple[str, int, int]:
-    """Returns (new text, divisions turned into calls, divisions guarded in line).
+def _f64_imm(x: float) -> str:
+    return "0d%016X" % struct.unpack("<Q", struct.pack("<d", x))[0]
 
-    Default: `div.rn.f64 d, a, b` becomes a call of m_div.  In functions / kernels whose (mangled) name matches
-    `inline_pattern` the division stays in line behind a zero test of the numerator and only a zero numerator
-    takes the call - for kernels where the call overhead (~14 instructions per division) costs more than the
-    instruction-cache footprint of the in-line expansion."""
+
+def _recip_div(ind: str, d: str, a: str, rc: str, nc: str, k: int, b_for_call: str, ok_pred: str | None) -> str:
+    """d = a / c through the correctly rounded reciprocal rc = RN(1/c) (nc = -c):
+         q = a * rc;  r = fma(q, -c, a);  d = fma(r, rc, q)
+    which is the correctly rounded quotient when rc is correctly rounded and nothing under- or overflows
+    (Markstein's theorem; the same three operations end the Newton sequence ptxas emits for div.rn.f64).  The
+    numerator's exponent is checked to lie in [-500, 500] (the divisor's in [-100, 100]: at build time for a
+    literal, by `ok_pred` for a kernel parameter); zero, subnormal, huge, infinite and NaN numerators take the
+    general m_div call."""
+    guard = f"{ind}and.pred \t%pg, %pg, {ok_pred};\n" if ok_pred else ""
+    return (f"{ind}{{ // elmk division by a constant / kernel parameter\n"
+            f"{ind}.reg .b32 %lo, %hi, %ex;\n{ind}.reg .pred %pg;\n{ind}.reg .f64 %q, %r;\n"
+            f"{ind}mov.b64 \t{{%lo, %hi}}, {a};\n"
+            f"{ind}bfe.u32 \t%ex, %hi, 20, 11;\n"
+            f"{ind}sub.u32 \t%ex, %ex, 523;\n"
+            f"{ind}setp.lt.u32 \t%pg, %ex, 1001;\n" + guard +
+            f"{ind}@!%pg bra \t$L__elmk_s{k};\n"
+            f"{ind}mul.rn.f64 \t%q, {a}, {rc};\n"
+            f"{ind}fma.rn.f64 \t%r, %q, {nc}, {a};\n"
+            f"{ind}fma.rn.f64 \t{d}, %r, {rc}, %q;\n"
+            f"{ind}bra \t$L__elmk_e{k};\n"
+            f"$L__elmk_s{k}:\n" + _call(ind, d, a, b_for_call) + f"\n$L__elmk_e{k}:\n{ind}}}")
+
+
+LDPARAM = re.compile(r"^\s*ld\.param\.f64\s+(%fd\d+),\s*\[([\w$]+)_param_\d+(?:\+\d+)?\];")
+DEST = re.compile(r"^\s*(?:@!?%p\d+\s+)?[a-z][\w.]*\s+(%fd\d+)\s*[,;]")
+
+
+def _rewrite_function(name: str, body: list[str], counter: list[int], stats: dict) -> list[str]:
+    """body: the lines of one .func / .entry, from its header to its closing brace."""
+    if name == M_DIV or name.startswith("__internal") or name.startswith("__nv_"):
+        return body
+    is_entry = any(l.startswith(".entry") or l.startswith(".visible .entry") for l in body[:1])
+    # f64 registers loaded straight from kernel parameters and never written again: uniform divisors
+    params = {}
+    if is_entry:
+        writes = {}
+        for l in body:
+            m = DEST.match(l)
+            if m:
+                writes[m.group(1)] = writes.get(m.group(1), 0) + 1
+        for l in body:
+            m = LDPARAM.match(l)
+            if m and m.group(2) == name and writes.get(m.group(1), 0) == 1:
+                params[m.group(1)] = len(params)
+    used = set()
+    out = []
+    for l in body:
+        m = DIV.match(l)
+        if not m:
+            out.append(l)
+            continue
+        ind, d, a, b = (x.strip() if i else x for i, x in enumerate(m.groups()))
+        if b.startswith("0d") and not a.startswith("0d"):
+            c = struct.unpack("<d", struct.pack("<Q", int(b[2:], 16)))[0]
+            if c == c and 2.0 ** -100 < abs(c) < 2.0 ** 100:
+                out.append(_recip_div(ind, d, a, _f64_imm(1.0 / c), _f64_imm(-c), counter[0], b, None))
+                counter[0] += 1
+                stats["const"] += 1
+                continue
+        if b in params and not a.startswith("0d"):
+            i = params[b]
+            used.add(b)
+            out.append(_recip_div(ind, d, a, f"%elmk_rc{i}", f"%elmk_nc{i}", counter[0], b, f"%elmk_pc{i}"))
+            counter[0] += 1
+            stats["param"] += 1
+            continue
+        out.append(_call(ind, d, a, b))
+        stats["call"] += 1
+    if used:
+        # declare and fill the reciprocals right after the parameter loads
+        res = []
+        for l in out:
+            res.append(l)
+            if l.strip() == "{" and not any(x.startswith("\t.reg .f64 %elmk_rc") for x in res):
+                n = len(params)
+                res.append(f"\t.reg .f64 \t%elmk_rc<{n}>;\n\t.reg .f64 \t%elmk_nc<{n}>;\n\t.reg .pred \t%elmk_pc<{n}>;\n"
+                           f"\t.reg .b32 \t%elmk_t<3>;")
+            m = LDPARAM.match(l)
+            if m and m.group(1) in used:
+                r, i = m.group(1), params[m.group(1)]
+                res.append(f"\trcp.rn.f64 \t%elmk_rc{i}, {r};\n\tneg.f64 \t%elmk_nc{i}, {r};\n"
+                           f"\tmov.b64 \t{{%elmk_t0, %elmk_t1}}, {r};\n\tbfe.u32 \t%elmk_t2, %elmk_t1, 20, 11;\n"
+                           f"\tsub.u32 \t%elmk_t2, %elmk_t2, 923;\n\tsetp.lt.u32 \t%elmk_pc{i}, %elmk_t2, 201;")
+        out = res
+    return out
+
+
+def rewrite(text: str) -> tuple[str, dict]:
+    """Returns (new text, counts of divisions by kind)."""
     if f"{M_DIV}(" not in text:
         raise RuntimeError(f"ptx_rewrite: {M_DIV} is not defined in the PTX (elmk::m_div must be used at least once)")
-    inl = re.compile(inline_pattern) if inline_pattern else None
-    out, n_call, n_inl, cur = [], 0, 0, None
     lines = text.split("\n")
     have_proto = any(l.startswith(".func") and l.rstrip().endswith(M_DIV) for l in lines[:400])
-    for line in lines:
-        if line.startswith("."):
-            m = FUNC.match(line)
-            if m:
-                cur = m.group(1)
-        m = DIV.match(line)
-        if m and cur is not None and cur != M_DIV and not cur.startswith("__internal") and not cur.startswith("__nv_"):
-            ind, d, a, b = (x.strip() if i else x for i, x in enumerate(m.groups()))
-            if inl is not None and inl.search(cur) and not a.startswith("0d"):
-                k = n_inl
-                out.append(f"{ind}{{ // elmk guarded div\n{ind}.reg .pred %pz;\n"
-                           f"{ind}setp.eq.f64 \t%pz, {a}, 0d0000000000000000;\n"
-                           f"{ind}@%pz bra \t$L__elmk_z{k};\n"
-                           f"{ind}div.rn.f64 \t{d}, {a}, {b};\n"
-                           f"{ind}bra \t$L__elmk_e{k};\n"
-                           f"$L__elmk_z{k}:\n" + _call(ind, d, a, b) + f"\n$L__elmk_e{k}:\n{ind}}}")
-                n_inl += 1
-            else:
-                out.append(_call(ind, d, a, b))
-                n_call += 1
-            continue
+    out, stats, counter = [], {"call": 0, "const": 0, "param": 0}, [0]
+    i = 0
+    while i < len(lines):
+        line = lines[i]
+        m = FUNC.match(line) if line.startswith(".") else None
+        if m:
+            # a prototype ends with ';' before any '{'; a definition runs to the closing brace in column 0
+            j = i
+            while j < len(lines) and not lines[j].startswith("{") and not lines[j].rstrip().endswith(";"):
+                j += 1
+            if j < len(lines) and lines[j].startswith("{"):
+                k = j
+                while not lines[k].startswith("}"):
+                    k += 1
+                out.extend(_rewrite_function(m.group(1), lines[i:k + 1], counter, stats))
+                i = k + 1
+                continue
         out.append(line)
         if not have_proto and line.startswith(".address_size"):
             out.append("")
             out.append(PROTO)
             have_proto = True
-    return "\n".join(out), n_call, n_inl
+        i += 1
+    return "\n".join(out), stats
 
 
-def main(path: str, inline_pattern: str | None = None) -> None:
+def main(path: str) -> None:
     text = open(path).read()
-    new, n_call, n_inl = rewrite(text, inline_pattern)
+    new, st = rewrite(text)
     open(path, "w").write(new)
-    print(f"ptx_rewrite: {n_call} double divisions routed through elmk::m_div, {n_inl} guarded in line, in {path}")
+    print(f"ptx_rewrite: {st['call']} double divisions routed through elmk::m_div, {st['const']} by literals and "
+          f"{st['param']} by kernel parameters through exact reciprocal sequences, in {path}")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] else None)
+    main(sys.argv[1])
