@@ -108,6 +108,10 @@ class Library:
             "elmk_exchange_commit": (C.c_int, [H]),
             "elmk_exchange_fetch": (C.c_int, [H, C.POINTER(C.c_void_p)]),
             "elmk_exchange_wait": (C.c_int, [H]),
+            "elmk_atm_series": (C.c_int, [H, C.c_int, _PD, C.c_int]),
+            "elmk_atm_forcing": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_int]),
+            "elmk_phen_series": (C.c_int, [H, C.c_int, _PD, C.c_int]),
+            "elmk_phenology": (C.c_int, [H, C.c_int, C.c_double, C.c_double]),
             "elmk_timing_enable": (C.c_int, [H, C.c_int]),
             "elmk_timing_read": (C.c_int, [H, C.c_int, C.POINTER(C.c_char_p), _PD, C.POINTER(C.c_int64),
                                            C.POINTER(C.c_uint32)]),
@@ -299,6 +303,30 @@ class Columns:
         x = Exchange(self, in_names, out_names)
         self._exchanges.append(x)
         return x
+
+    # -- per-step input producers on the device (forcing functors, phenology) --
+    ATM_VARS = ("TBOT", "PBOT", "QBOT", "FLDS", "FSDS", "PREC", "WIND")
+    PHEN_VARS = ("MLAI", "MSAI", "MHTOP", "MHBOT")
+
+    def _series(self, fn, what, var_index: int, arr: np.ndarray):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        if a.ndim != 2 or a.shape[1] != self.ncols:
+            raise ElmkError(f"{what}: expected shape (ntimes, {self.ncols}), got {a.shape}")
+        self._check(fn(self._h, var_index, a.ctypes.data_as(_PD), a.shape[0]), what)
+
+    def atm_series(self, var: str, arr: np.ndarray):
+        """Raw forcing series of one variable, shape (ntimes, ncols) as AtmDataManager::data."""
+        self._series(self.lib.dll.elmk_atm_series, f"elmk_atm_series({var})", self.ATM_VARS.index(var), arr)
+
+    def atm_forcing(self, t_idx: int, wt1: float, wt2: float, qbot_is_rh: bool = True):
+        self._check(self.lib.dll.elmk_atm_forcing(self._h, int(t_idx), float(wt1), float(wt2), int(qbot_is_rh)),
+                    "elmk_atm_forcing")
+
+    def phen_series(self, var: str, arr: np.ndarray):
+        self._series(self.lib.dll.elmk_phen_series, f"elmk_phen_series({var})", self.PHEN_VARS.index(var), arr)
+
+    def phenology(self, start_idx: int, wt1: float, wt2: float):
+        self._check(self.lib.dll.elmk_phenology(self._h, int(start_idx), float(wt1), float(wt2)), "elmk_phenology")
 
     # -- stepping --
     def init_timestep(self, reset_forc_hgt: bool = True):

@@ -25,6 +25,7 @@
 #include "phys_bareground.h"
 #include "phys_canflux.h"
 #include "phys_cantemp.h"
+#include "phys_forcing.h"
 #include "phys_hydrology.h"
 #include "phys_radiation.h"
 #include "phys_snow.h"
@@ -326,6 +327,21 @@ __global__ void __launch_bounds__(kBlock) k_init_timestep(const Cols S, const Ta
   column_init_timestep(S, *Tp, reset, c);
 }
 
+__global__ void __launch_bounds__(kBlock) k_atm_forcing(const Cols S, const AtmSeries A, const int t, const double wt1,
+                                                        const double wt2, const int qbot_is_rh)
+{
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  if (c >= S.ncols) return;
+  column_atm_forcing(S, A, t, wt1, wt2, qbot_is_rh != 0, c);
+}
+__global__ void __launch_bounds__(kBlock) k_phenology(const Cols S, const PhenSeries P, const int m, const double wt1,
+                                                      const double wt2)
+{
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  if (c >= S.ncols) return;
+  column_phenology(S, P, m, wt1, wt2, c);
+}
+
 typedef void (*GroupKernel)(const Cols, const Tables*, const StepArgs);
 struct Launch { uint32_t mask; GroupKernel fn; const char* name; int cols_per_block; int block; };
 #define ELMK_LAUNCH(M, NAME) {(M), k_groups<(M)>, NAME, kBlock, kBlock}
@@ -517,6 +533,10 @@ struct Ctx {
   double* d_table_data = nullptr;
   char* stage[2] = {nullptr, nullptr};
   int stage_next = 0;
+  double* atm[ATM_NVARS] = {};     // raw forcing series [ntimes][np], resident (elmk_atm_series)
+  int atm_ntimes[ATM_NVARS] = {};
+  double* phen[PHEN_NVARS] = {};   // monthly phenology values [nmonths][np] (elmk_phen_series)
+  int phen_nmonths[PHEN_NVARS] = {};
   CanfluxQueue cq = {nullptr, nullptr, nullptr, 0};   // CanopyFluxes re-packing scratch (allocated on first use)
   int iterate_blocks = 0, iterate_variant = 0;
   bool repack = true;
@@ -849,6 +869,8 @@ int elmk_destroy(elmk_handle h) {
   cudaFree(c->d_table_data);
   cudaFree(c->d_err);
   cudaFree(c->d_diag);
+  for (double* p : c->atm) cudaFree(p);
+  for (double* p : c->phen) cudaFree(p);
   cudaFree(c->cq.scratch);
   cudaFree(c->cq.list);
   cudaFree(c->cq.counters);
@@ -1075,6 +1097,90 @@ int elmk_exchange_wait(elmk_exchange xh) {
   const int slot = (int)(x->waits & 1);
   CU(cudaEventSynchronize(x->out_done[slot]));
   x->waits += 1;
+  return ELMK_OK;
+}
+
+// ---- per-step producers of the forcing and phenology inputs ----
+namespace {
+int set_series(Ctx* c, double** slot, int* count, const double* host, int n) {
+  if (!host || n < 2) {
+    c->last_error = "series need a host pointer and at least two time levels";
+    return ELMK_EINVAL;
+  }
+  if (*slot && *count != n) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(*slot));
+    *slot = nullptr;
+  }
+  if (!*slot) {
+    CU(cudaMalloc(slot, sizeof(double) * (size_t)n * c->np));
+    CU(cudaMemsetAsync(*slot, 0, sizeof(double) * (size_t)n * c->np, c->stream));
+  }
+  *count = n;
+  // host rows of ncols values -> device rows of np values
+  CU(cudaMemcpy2DAsync(*slot, sizeof(double) * c->np, host, sizeof(double) * c->ncols, sizeof(double) * c->ncols, n,
+                       cudaMemcpyHostToDevice, c->stream));
+  return ELMK_OK;
+}
+} // namespace
+
+int elmk_atm_series(elmk_handle h, int var, const double* host, int ntimes) {
+  Ctx* c = ctx(h);
+  if (!c || var < 0 || var >= ATM_NVARS) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  return set_series(c, &c->atm[var], &c->atm_ntimes[var], host, ntimes);
+}
+
+int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_is_rh) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  AtmSeries A;
+  A.stride = c->np;
+  for (int v = 0; v < ATM_NVARS; ++v) {
+    if (!c->atm[v] || t_idx < 0 || t_idx + 1 >= c->atm_ntimes[v]) {
+      c->last_error = "elmk_atm_forcing: series missing or t_idx + 1 outside it";
+      return ELMK_EINVAL;
+    }
+    A.v[v] = c->atm[v];
+  }
+  const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
+  {
+    TimedScope ts(c, "atm_forcing", 0u);
+    k_atm_forcing<<<grid, kBlock, 0, c->stream>>>(c->cols, A, t_idx, wt1, wt2, qbot_is_rh);
+  }
+  c->launches += 1;
+  CU(cudaGetLastError());
+  return ELMK_OK;
+}
+
+int elmk_phen_series(elmk_handle h, int var, const double* host, int nmonths) {
+  Ctx* c = ctx(h);
+  if (!c || var < 0 || var >= PHEN_NVARS) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  return set_series(c, &c->phen[var], &c->phen_nmonths[var], host, nmonths);
+}
+
+int elmk_phenology(elmk_handle h, int start_idx, double wt1, double wt2) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  PhenSeries P;
+  P.stride = c->np;
+  for (int v = 0; v < PHEN_NVARS; ++v) {
+    if (!c->phen[v] || start_idx < 0 || start_idx + 1 >= c->phen_nmonths[v]) {
+      c->last_error = "elmk_phenology: series missing or start_idx + 1 outside it";
+      return ELMK_EINVAL;
+    }
+    P.v[v] = c->phen[v];
+  }
+  const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
+  {
+    TimedScope ts(c, "phenology", 0u);
+    k_phenology<<<grid, kBlock, 0, c->stream>>>(c->cols, P, start_idx, wt1, wt2);
+  }
+  c->launches += 1;
+  CU(cudaGetLastError());
   return ELMK_OK;
 }
 

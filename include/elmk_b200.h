@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ELMK_ABI_VERSION 2
+#define ELMK_ABI_VERSION 3
 
 /* ---- dimensions (reference src/data/elm_constants.h:84-98) ---- */
 #define ELMK_NLEVSNO 5
@@ -178,6 +178,38 @@ int elmk_exchange_post(elmk_exchange x, const void* const* in_hosts);
 int elmk_exchange_commit(elmk_exchange x);
 int elmk_exchange_fetch(elmk_exchange x, void* const* out_hosts);
 int elmk_exchange_wait(elmk_exchange x);
+
+/* ---- producers of the per-step inputs, on the device (the step before the chain in kokkos_init_timestep,
+ *      init_timestep_kokkos.cc:39-47).
+ *      elmk_atm_series: one raw forcing series, host[t * ncols + col] - the layout of AtmDataManager::data
+ *        (ntimes, ncells), src/data/atm_data.h; it stays resident on the device until replaced
+ *        (replaces read_atm_data's deep_copy, atm_forcing_kokkos.cc:15-27).
+ *      elmk_atm_forcing: the eight forcing functors of ELM::get_forcing (atm_forcing_kokkos.cc:48-63,
+ *        src/physics/atm_physics_impl.hh:40-211) in one pass: forc_tbot/thbot, forc_pbot, forc_qbot, forc_lwrad,
+ *        forc_solad/solai (reads the coszen field), forc_rain/snow, forc_u/v, forc_hgt*.  t_idx, wt1, wt2 are what
+ *        AtmDataManager::forc_t_idx_check_bounds / forcing_time_weights (atm_data_impl.hh:147-199) return for the
+ *        step's centred time; qbot_is_rh selects AtmForcType::RH (series in percent) over AtmForcType::QBOT.
+ *      elmk_phen_series / elmk_phenology: monthly LAI, SAI, canopy top and bottom height, host[m * ncols + col]
+ *        (PhenologyDataManager::mlai..mhbot), and ComputePhenology (src/physics/phenology_physics_impl.hh:20-69):
+ *        tlai, tsai, htop, hbot, elai, esai, frac_veg_nosno_alb from snow_depth, frac_sno, vtype; start_idx, wt1,
+ *        wt2 as from monthly_data::first_month_idx / monthly_data_weights (phenology_data_impl.hh:46-63). ---- */
+#define ELMK_ATM_TBOT 0
+#define ELMK_ATM_PBOT 1
+#define ELMK_ATM_QBOT 2
+#define ELMK_ATM_FLDS 3
+#define ELMK_ATM_FSDS 4
+#define ELMK_ATM_PREC 5
+#define ELMK_ATM_WIND 6
+#define ELMK_ATM_NVARS 7
+#define ELMK_PHEN_MLAI 0
+#define ELMK_PHEN_MSAI 1
+#define ELMK_PHEN_MHTOP 2
+#define ELMK_PHEN_MHBOT 3
+#define ELMK_PHEN_NVARS 4
+int elmk_atm_series(elmk_handle h, int var, const double* host, int ntimes);
+int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_is_rh);
+int elmk_phen_series(elmk_handle h, int var, const double* host, int nmonths);
+int elmk_phenology(elmk_handle h, int start_idx, double wt1, double wt2);
 
 /* ---- the per-column part of kokkos_init_timestep (init_timestep_kokkos.cc:53-72):
  *      h2osno_old, dtbegin_column_h2o, ELM::init_timestep; resets forc_hgt_*_patch to

@@ -46,7 +46,7 @@ def newer(target, sources):
 def build_lib(force=False):
     lib = OUT / "libelmref.so"
     srcs = [REF / f"driver/kokkos/{w}_kokkos.cc" for w in WRAPPERS] + [REF / e for e in EXTRA] + [HERE / "ref_capi.cc"]
-    deps = srcs + [HERE / "shim/Kokkos_Core.hpp", HERE / "shim/netcdf.h", HERE.parent / "include/elmk_b200.h",
+    deps = srcs + [HERE / "shim/Kokkos_Core.hpp", HERE / "shim/netcdf.h", HERE / "exchange_host.h", HERE.parent / "include/elmk_b200.h",
                    HERE.parent / "include/elmk_fields.def"]
     if not force and newer(lib, deps):
         return lib

@@ -19,6 +19,7 @@
 #include "../../elmkernels_b200/csrc/phys_bareground.h"
 #include "../../elmkernels_b200/csrc/phys_canflux.h"
 #include "../../elmkernels_b200/csrc/phys_cantemp.h"
+#include "../../elmkernels_b200/csrc/phys_forcing.h"
 #include "../../elmkernels_b200/csrc/phys_hydrology.h"
 #include "../../elmkernels_b200/csrc/phys_radiation.h"
 #include "../../elmkernels_b200/csrc/phys_snow.h"
@@ -50,6 +51,7 @@ struct PortCtx {
   Tables tab;
   std::vector<void*> base;
   std::vector<double> snw[2][3], snowage[3];
+  std::vector<double> atm[ATM_NVARS], phen[PHEN_NVARS];   // [ntimes][ncols]
   bool tables_set = false;
   int64_t launches = 0;
   std::string last_error;
@@ -186,6 +188,41 @@ int elmk_fill(elmk_handle h, int field, double value) {
   if (kSpecs[field].dtype == ELMK_F64) std::fill_n(static_cast<double*>(c.base[field]), count, value);
   else if (kSpecs[field].dtype == ELMK_I32) std::fill_n(static_cast<int*>(c.base[field]), count, static_cast<int>(value));
   else std::fill_n(static_cast<unsigned char*>(c.base[field]), count, static_cast<unsigned char>(value != 0.0));
+  return ELMK_OK;
+}
+
+int elmk_atm_series(elmk_handle h, int var, const double* host, int ntimes) {
+  PortCtx& c = *ctx(h);
+  if (var < 0 || var >= ATM_NVARS || !host || ntimes < 2) return ELMK_EINVAL;
+  c.atm[var].assign(host, host + (size_t)ntimes * c.ncols);
+  return ELMK_OK;
+}
+int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_is_rh) {
+  PortCtx& c = *ctx(h);
+  AtmSeries A;
+  A.stride = c.ncols;
+  for (int v = 0; v < ATM_NVARS; ++v) {
+    if (t_idx < 0 || (size_t)(t_idx + 2) * c.ncols > c.atm[v].size()) return ELMK_EINVAL;
+    A.v[v] = c.atm[v].data();
+  }
+  for_columns(c, [&](int i) { column_atm_forcing(c.cols, A, t_idx, wt1, wt2, qbot_is_rh != 0, i); });
+  return ELMK_OK;
+}
+int elmk_phen_series(elmk_handle h, int var, const double* host, int nmonths) {
+  PortCtx& c = *ctx(h);
+  if (var < 0 || var >= PHEN_NVARS || !host || nmonths < 2) return ELMK_EINVAL;
+  c.phen[var].assign(host, host + (size_t)nmonths * c.ncols);
+  return ELMK_OK;
+}
+int elmk_phenology(elmk_handle h, int start_idx, double wt1, double wt2) {
+  PortCtx& c = *ctx(h);
+  PhenSeries P;
+  P.stride = c.ncols;
+  for (int v = 0; v < PHEN_NVARS; ++v) {
+    if (start_idx < 0 || (size_t)(start_idx + 2) * c.ncols > c.phen[v].size()) return ELMK_EINVAL;
+    P.v[v] = c.phen[v].data();
+  }
+  for_columns(c, [&](int i) { column_phenology(c.cols, P, start_idx, wt1, wt2, i); });
   return ELMK_OK;
 }
 

@@ -41,6 +41,8 @@
 #include "surface_fluxes_kokkos.hh"
 #include "surface_radiation_kokkos.hh"
 
+#include "atm_physics.h"
+#include "phenology_physics.h"
 #include "conserved_quantity_evaluators.h"
 #include "init_snow_state.h"
 #include "init_soil_state.h"
@@ -68,6 +70,8 @@ struct RefCtx {
   // the eight wrapper-local diagnostics + error word, owned here
   ViewD1 dtend_column_h2o, errh2o, errh2osno, dwb, errsol, errlon, errseb, netrad;
   ViewI1 errmask;
+  // raw forcing series and monthly phenology values, as the reference's data managers hold them: (ntimes, ncells)
+  ViewD2 atm[ELMK_ATM_NVARS], phen[ELMK_PHEN_NVARS];
   bool tables_set = false;
   int64_t launches = 0;
   std::string last_error;
@@ -355,6 +359,71 @@ int elmk_fill(elmk_handle h, int field, double value) {
   if (f.dtype == ELMK_F64) std::fill_n(static_cast<double*>(f.base), count, value);
   else if (f.dtype == ELMK_I32) std::fill_n(static_cast<int*>(f.base), count, static_cast<int>(value));
   else std::fill_n(static_cast<unsigned char*>(f.base), count, static_cast<unsigned char>(value != 0.0));
+  return ELMK_OK;
+}
+
+// ---- forcing and phenology producers: the reference's own functors (src/physics/atm_physics.h,
+//      phenology_physics.h) launched in the order of ELM::get_forcing (atm_forcing_kokkos.cc:48-63) and
+//      PhenologyDataManager::get_data (phenology_data_impl.hh:46-63) ----
+static int ref_set_series(RefCtx& c, ViewD2& v, const char* label, const double* host, int n) {
+  if (!host || n < 2) return ELMK_EINVAL;
+  v = ViewD2(label, static_cast<size_t>(n), static_cast<size_t>(c.ncols));
+  std::memcpy(v.data(), host, sizeof(double) * static_cast<size_t>(n) * c.ncols);
+  return ELMK_OK;
+}
+int elmk_atm_series(elmk_handle h, int var, const double* host, int ntimes) {
+  RefCtx& c = *ctx(h);
+  if (var < 0 || var >= ELMK_ATM_NVARS) return ELMK_EINVAL;
+  return ref_set_series(c, c.atm[var], "atm_series", host, ntimes);
+}
+int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_is_rh) {
+  RefCtx& c = *ctx(h);
+  ELMStateType& S = *c.S;
+  for (int v = 0; v < ELMK_ATM_NVARS; ++v)
+    if (t_idx < 0 || static_cast<size_t>(t_idx) + 2 > c.atm[v].extent(0)) return ELMK_EINVAL;
+  namespace ap = ELM::atm_forcing_physics;
+  const int n = static_cast<int>(c.ncols);
+  Kokkos::parallel_for("ComputeAtmForcing_TBOT", n,
+                       ap::ProcessTBOT<ViewD1, ViewD2>(t_idx, wt1, wt2, c.atm[ELMK_ATM_TBOT], S.forc_tbot, S.forc_thbot));
+  Kokkos::parallel_for("ComputeAtmForcing_PBOT", n,
+                       ap::ProcessPBOT<ViewD1, ViewD2>(t_idx, wt1, wt2, c.atm[ELMK_ATM_PBOT], S.forc_pbot));
+  if (qbot_is_rh)
+    Kokkos::parallel_for("ComputeAtmForcing_RH", n,
+                         ap::ProcessQBOT<ViewD1, ViewD2, ELM::AtmForcType::RH>(t_idx, wt1, wt2, c.atm[ELMK_ATM_QBOT], S.forc_tbot,
+                                                                                S.forc_pbot, S.forc_qbot));
+  else
+    Kokkos::parallel_for("ComputeAtmForcing_QBOT", n,
+                         ap::ProcessQBOT<ViewD1, ViewD2, ELM::AtmForcType::QBOT>(t_idx, wt1, wt2, c.atm[ELMK_ATM_QBOT], S.forc_tbot,
+                                                                                  S.forc_pbot, S.forc_qbot));
+  Kokkos::parallel_for("ComputeAtmForcing_FLDS", n,
+                       ap::ProcessFLDS<ViewD1, ViewD2>(t_idx, wt1, wt2, c.atm[ELMK_ATM_FLDS], S.forc_pbot, S.forc_qbot, S.forc_tbot,
+                                                       S.forc_lwrad));
+  Kokkos::parallel_for("ComputeAtmForcing_FSDS", n,
+                       ap::ProcessFSDS<ViewD1, ViewD2>(t_idx, c.atm[ELMK_ATM_FSDS], S.coszen, S.forc_solai, S.forc_solad));
+  Kokkos::parallel_for("ComputeAtmForcing_PREC", n,
+                       ap::ProcessPREC<ViewD1, ViewD2>(t_idx, c.atm[ELMK_ATM_PREC], S.forc_tbot, S.forc_rain, S.forc_snow));
+  Kokkos::parallel_for("ComputeAtmForcing_WIND", n,
+                       ap::ProcessWIND<ViewD1, ViewD2>(t_idx, wt1, wt2, c.atm[ELMK_ATM_WIND], S.forc_u, S.forc_v));
+  Kokkos::parallel_for("ComputeAtmForcing_ZBOT", n,
+                       ap::ProcessZBOT<ViewD1>(S.forc_hgt, S.forc_hgt_u_patch, S.forc_hgt_t_patch, S.forc_hgt_q_patch));
+  c.launches += 8;
+  return ELMK_OK;
+}
+int elmk_phen_series(elmk_handle h, int var, const double* host, int nmonths) {
+  RefCtx& c = *ctx(h);
+  if (var < 0 || var >= ELMK_PHEN_NVARS) return ELMK_EINVAL;
+  return ref_set_series(c, c.phen[var], "phen_series", host, nmonths);
+}
+int elmk_phenology(elmk_handle h, int start_idx, double wt1, double wt2) {
+  RefCtx& c = *ctx(h);
+  ELMStateType& S = *c.S;
+  for (int v = 0; v < ELMK_PHEN_NVARS; ++v)
+    if (start_idx < 0 || static_cast<size_t>(start_idx) + 2 > c.phen[v].extent(0)) return ELMK_EINVAL;
+  ELM::phenology::ComputePhenology<ViewI1, ViewD1, ViewD2> compute_phen(
+      c.phen[ELMK_PHEN_MLAI], c.phen[ELMK_PHEN_MSAI], c.phen[ELMK_PHEN_MHTOP], c.phen[ELMK_PHEN_MHBOT], S.snow_depth,
+      S.frac_sno, S.vtype, wt1, wt2, start_idx, S.elai, S.esai, S.htop, S.hbot, S.tlai, S.tsai, S.frac_veg_nosno_alb);
+  Kokkos::parallel_for("ComputePhenology", static_cast<int>(c.ncols), compute_phen);
+  c.launches += 1;
   return ELMK_OK;
 }
 

@@ -45,6 +45,16 @@ def port_lib():
 
 
 @pytest.fixture(scope="session")
+def checker(request):
+    """What the CUDA library is compared with: the reference itself when oracle/_ref is present, else the pinned port."""
+    from elmkernels_b200 import abi
+    path = os.path.join(ROOT, "oracle", "_ref", "libelmref.so")
+    if os.path.exists(path):
+        return abi.Library(path)
+    return request.getfixturevalue("port_lib")
+
+
+@pytest.fixture(scope="session")
 def cuda_lib():
     import elmkernels_b200
     return elmkernels_b200.load()

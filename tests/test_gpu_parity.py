@@ -19,14 +19,6 @@ CLOSED_FORM = [abi.G_FRAC_WET, abi.G_ALBEDO, abi.G_CANOPY_HYDROLOGY, abi.G_SURFA
                abi.G_CONSERVATION]
 
 
-@pytest.fixture(scope="module")
-def checker(request):
-    path = os.path.join(ROOT, "oracle", "_ref", "libelmref.so")
-    if os.path.exists(path):
-        return abi.Library(path)
-    return request.getfixturevalue("port_lib")
-
-
 def test_backend_is_cuda(cuda_lib):
     assert cuda_lib.backend == "cuda-sm100a"
 
