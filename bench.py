@@ -359,6 +359,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         gb = json.load(open(os.path.join(ROOT, "elmkernels_b200", "data", "group_bytes.json")))
+        other = {k[0]: k[2] / k[3] for k in kern if not k[1]}   # init_timestep (and, with ELMK_TIMING_DETAIL, sub-launches)
         kern = [k for k in kern if k[1]]   # launches of elmk_step (init_timestep has mask 0)
         total_kernel_ms = sum(k[2] for k in kern) or 1.0
         top = max(kern, key=lambda k: k[2])
@@ -407,7 +408,7 @@ def main():
                                      for k in kern}},
             "e2e": {"value": e2e, "unit": "column-steps/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "errors": {"any": any_err, "first_column": first},
+            "other_launches_ms": other, "gpu_launches": launches, "clocks": clocks, "errors": {"any": any_err, "first_column": first},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(P, args.cpu_cols)

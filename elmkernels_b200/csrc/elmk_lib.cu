@@ -234,7 +234,7 @@ __device__ __forceinline__ void canflux_load(const CanfluxQueue& Q, const int c,
 #undef X
 }
 
-__global__ void __launch_bounds__(kBlock) k_canflux_begin(const Cols S, const Tables* __restrict__ Tp, const StepArgs A,
+__global__ void __launch_bounds__(kBlock, 8) k_canflux_begin(const Cols S, const Tables* __restrict__ Tp, const StepArgs A,
                                                           const CanfluxQueue Q)
 {
   const int c = blockIdx.x * kBlock + threadIdx.x;
@@ -584,12 +584,12 @@ struct TimedScope {
   Ctx* c;
   Ctx::Timed t;
   TimedScope(Ctx* c_, const char* name, uint32_t mask) : c(c_) {
-    if (!c->timing) return;
+    if (!c->timing) { c = nullptr; return; }
     t = {name, mask, take_event(c), take_event(c)};
     cudaEventRecord(t.t0, c->stream);
   }
   ~TimedScope() {
-    if (!c->timing) return;
+    if (!c) return;   // timing off, or the scope was closed / discarded by hand
     cudaEventRecord(t.t1, c->stream);
     c->timed.push_back(t);
   }
@@ -705,7 +705,20 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
   }
   const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
   CU(cudaMemsetAsync(c->cq.counters, 0, sizeof(int) * 4, c->stream));
+  static const bool detail = std::getenv("ELMK_TIMING_DETAIL") != nullptr;   // development: time the three launches apart
+  const bool split = detail && c->timing;
+  auto mark = [&](Ctx::Timed& t, const char* name) {
+    t = {name, 0u, take_event(c), take_event(c)};
+    cudaEventRecord(t.t0, c->stream);
+  };
+  auto done = [&](Ctx::Timed& t) {
+    cudaEventRecord(t.t1, c->stream);
+    c->timed.push_back(t);
+  };
+  Ctx::Timed tb{}, ti{}, te{};
+  if (split) mark(tb, "canopy_fluxes:begin");
   k_canflux_begin<<<grid, kBlock, 0, c->stream>>>(c->cols, c->d_tables, A, c->cq);
+  if (split) done(tb), mark(ti, "canopy_fluxes:iterate");
   const unsigned persistent = (unsigned)std::min<int64_t>(c->iterate_blocks, (c->ncols + kBlock - 1) / kBlock);
   switch (c->iterate_variant) {
     case 1: k_canflux_iterate<128, true><<<persistent, 128, 0, c->stream>>>(c->cols, c->cq); break;
@@ -718,7 +731,9 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
     case 8: k_canflux_iterate<448, true><<<persistent, 448, 0, c->stream>>>(c->cols, c->cq); break;
     default: k_canflux_iterate<128, false><<<persistent, 128, 0, c->stream>>>(c->cols, c->cq); break;
   }
+  if (split) done(ti), mark(te, "canopy_fluxes:end");
   k_canflux_end<<<grid, kBlock, 0, c->stream>>>(c->cols, c->cq);
+  if (split) done(te);
   c->launches += 3;
   CU(cudaGetLastError());
   return ELMK_OK;

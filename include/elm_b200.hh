@@ -146,6 +146,24 @@ public:
     return out;
   }
 
+  // ---- per-step input producers on the device (ELM::get_forcing, atm_forcing_kokkos.cc:48-63; ComputePhenology via
+  //      PhenologyDataManager::get_data, phenology_data_impl.hh:46-63).  `data` is the manager's (ntimes, ncells)
+  //      array - AtmDataManager::data, PhenologyDataManager::mlai/msai/mhtop/mhbot - read through operator()(t, i). ----
+  template <class Arr2> void set_atm_series(int var, const Arr2& data, int ntimes) {
+    const std::vector<double> b = flatten2(data, ntimes);
+    check(elmk_atm_series(h_, var, b.data(), ntimes), "elmk_atm_series");
+  }
+  template <class Arr2> void set_phen_series(int var, const Arr2& data, int nmonths) {
+    const std::vector<double> b = flatten2(data, nmonths);
+    check(elmk_phen_series(h_, var, b.data(), nmonths), "elmk_phen_series");
+  }
+  // t_idx, wt1, wt2: AtmDataManager::forc_t_idx_check_bounds / forcing_time_weights for the centred step time
+  void atm_forcing(int t_idx, double wt1, double wt2, bool qbot_is_rh = true) {
+    check(elmk_atm_forcing(h_, t_idx, wt1, wt2, qbot_is_rh ? 1 : 0), "elmk_atm_forcing");
+  }
+  // start_idx, wt1, wt2: monthly_data::first_month_idx / monthly_data_weights
+  void phenology(int start_idx, double wt1, double wt2) { check(elmk_phenology(h_, start_idx, wt1, wt2), "elmk_phenology"); }
+
   // ---- stepping ----
   // per-column part of kokkos_init_timestep (init_timestep_kokkos.cc:53-72) incl. the reset of forc_hgt_*_patch
   void init_timestep(bool reset_forc_hgt = true) { check(elmk_init_timestep(h_, reset_forc_hgt ? 1 : 0), "elmk_init_timestep"); }
@@ -177,6 +195,12 @@ private:
   }
   void check(int rc, const char* what) {
     if (rc != ELMK_OK) throw std::runtime_error(std::string("ELM::b200: ") + what + " failed: " + elmk_last_error(h_));
+  }
+  template <class Arr2> std::vector<double> flatten2(const Arr2& a, int n0) {
+    std::vector<double> b(static_cast<size_t>(n0) * ncols_);
+    for (int t = 0; t < n0; ++t)
+      for (int64_t i = 0; i < ncols_; ++i) b[static_cast<size_t>(t) * ncols_ + i] = a(t, static_cast<int>(i));
+    return b;
   }
   // gather one array of S through its element accessor into a dense host buffer in the reference's
   // layout (column outer) and hand it to the ABI; works for any ArrayType with operator()(i[, lev])

@@ -3,5 +3,5 @@
 N=${1:-2097152}; shift
 for so in "$@"; do
   echo "== $so"
-  ELMK_LIB=$PWD/$so python bench.py --ncols $N --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python tools/show_bench.py
+  ELMK_LIB=$PWD/$so ELMK_TIMING_DETAIL=1 python bench.py --ncols $N --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python tools/show_bench.py
 done
