@@ -369,12 +369,12 @@ constexpr uint32_t M_RAD = ELMK_G_FRAC_WET | ELMK_G_ALBEDO;
 constexpr uint32_t M_SFC = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | ELMK_G_CANOPY_TEMPERATURE |
                            ELMK_G_BAREGROUND_FLUXES;
 constexpr uint32_t M_END = ELMK_G_SNOW_HYDROLOGY | ELMK_G_SURFACE_FLUXES | ELMK_G_CONSERVATION;
-// (register caps: measured on B200, 512k columns - 0.74 -> 0.64 ms, 2.66 -> 2.58 ms, 1.30 -> 1.11 ms)
+// (register caps: blocks per SM chosen by A/B runs on B200 at 2M columns - 10 / 5 / 6 were the fastest of 2..10)
 const Launch kFused[] = {
     ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo", 128, false),
-    ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 8),
+    ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 10),
     ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes", 128, false),
-    ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 3),
+    ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 5),
     ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 6),
 };
 // development: alternative launch configurations of the radiative-transfer launch (ELMK_RAD_VARIANT=1..)
@@ -387,6 +387,19 @@ const Launch kRadVariants[] = {
     ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 256, true, 1),
     ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 512, true, 1),
 };
+// development: register caps of the three unsorted launches (ELMK_OCC_SFC / _SOIL / _END = blocks per SM)
+template <uint32_t M> GroupKernel occ_variant(int minblocks) {
+  switch (minblocks) {
+    case 2: return k_groups_occ<M, 2>;
+    case 3: return k_groups_occ<M, 3>;
+    case 4: return k_groups_occ<M, 4>;
+    case 5: return k_groups_occ<M, 5>;
+    case 6: return k_groups_occ<M, 6>;
+    case 8: return k_groups_occ<M, 8>;
+    case 10: return k_groups_occ<M, 10>;
+    default: return nullptr;
+  }
+}
 // plan "unsorted": the fused cut without work-class ordering (for A/B measurements)
 const Launch kFusedUnsorted[] = {
     ELMK_LAUNCH(M_RAD, "fracwet+albedo"),
@@ -860,11 +873,23 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
   }
   const char* rp = std::getenv("ELMK_CANFLUX_REPACK");
   if (rp && rp[0] == '0') c->repack = false;
+  {
+    const char* e1 = std::getenv("ELMK_OCC_SFC");
+    const char* e2 = std::getenv("ELMK_OCC_SOIL");
+    const char* e3 = std::getenv("ELMK_OCC_END");
+    if ((e1 || e2 || e3) && c->plan == kFused) {
+      c->plan_own.assign(kFused, kFused + c->plan_len);
+      GroupKernel k;
+      if (e1 && (k = occ_variant<M_SFC>(std::atoi(e1)))) c->plan_own[1].fn = k;
+      if (e2 && (k = occ_variant<ELMK_G_SOIL_TEMPERATURE>(std::atoi(e2)))) c->plan_own[3].fn = k;
+      if (e3 && (k = occ_variant<M_END>(std::atoi(e3)))) c->plan_own[4].fn = k;
+    }
+  }
   const char* rv = std::getenv("ELMK_RAD_VARIANT");
   if (rv && c->plan == kFused) {
     const int v = std::atoi(rv);
     if (v >= 1 && v <= (int)(sizeof(kRadVariants) / sizeof(kRadVariants[0]))) {
-      c->plan_own.assign(kFused, kFused + c->plan_len);
+      if (c->plan_own.empty()) c->plan_own.assign(kFused, kFused + c->plan_len);
       c->plan_own[0] = kRadVariants[v - 1];
     }
   }
