@@ -48,6 +48,21 @@ ELMK_HD_NOINLINE double m_div(double a, double b)
 #endif
   return a / b;
 }
+
+// Two independent divisions in one call.  As separate calls of m_div two divisions run strictly one after the other
+// - ~9 dependent FP64 operations each - although neither needs the other's result; inside one function ptxas
+// interleaves the two Newton sequences, so the pair costs about the latency of one division and one call overhead.
+// The build pairs neighbouring independent `/` of the device code (ptx_rewrite.py); results are those of a / b.
+struct Div2 {
+  double q0, q1;
+};
+ELMK_HD_NOINLINE Div2 m_div2(double a0, double b0, double a1, double b1)
+{
+#if defined(__CUDA_ARCH__)
+  if (__builtin_expect(a0 == 0.0 || a1 == 0.0, 0)) return {m_div(a0, b0), m_div(a1, b1)};
+#endif
+  return {a0 / b0, a1 / b1};
+}
 } // namespace elmk
 
 namespace elmk {

@@ -60,12 +60,13 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
     if (i >= NLEVSNO) {
       const int k = i - NLEVSNO;
       const double watsat = C2(watsat, k);
-      double satw = m_div(liq / DENH2O + ice / DENICE, dz * watsat);   // (explicit use keeps m_div in the module)
+      const Div2 hold = m_div2(liq, DENH2O * dz, ice, DENICE * dz);   // (explicit uses keep m_div / m_div2 in the module)
+      double satw = m_div(liq / DENH2O + ice / DENICE, dz * watsat);
       satw = dmin(1.0, satw);
       const double tkdry = C2(tkdry, k);
       if (satw > 1.0e-6) {
         const double dke = (t[i] >= TFRZ) ? dmax(0.0, m_log10(satw) + 1.0) : satw;
-        const double fl = (liq / (DENH2O * dz)) / (liq / (DENH2O * dz) + ice / (DENICE * dz));
+        const double fl = hold.q0 / (hold.q0 + hold.q1);
         const double dksat = C2(tkmg, k) * pow_cbase(TKWAT, ELMK_LN_TKWAT, fl * watsat) * pow_cbase(TKICE, ELMK_LN_TKICE, (1.0 - fl) * watsat);
         thk[i] = dke * dksat + (1.0 - dke) * tkdry;
       } else {
