@@ -31,6 +31,68 @@ constexpr int MIE_N = 1471;
 // SNICAR for one incident-flux type.  flg = 1 direct beam, 2 diffuse.
 // cnc[i][j]: aerosol mass concentrations per snow slot.  Outputs: alb_out[2] (VIS, NIR) and
 // flx_abs[6][2] (five snow slots + ground, VIS/NIR), both already zero on entry.
+// Two Gauss points of the diffuse delta-Eddington integration (snow_snicar_impl.hh:459-478) in one called function
+// with its divisions and exponentials IN LINE (the build leaves functions named *_inl alone, ptx_rewrite.py): the
+// 2 x (three divisions + one exp) are independent of each other, so ptxas interleaves eight dependent chains
+// where the loop body, written with called m_div / m_exp, ran them one after the other.  None of the numerators
+// can be zero (optical depth > 0, 1 + g (1 - w) >= 1), so the in-line divisions stay on their fast path.
+// Direct-beam delta-Eddington solution of one layer (snow_snicar_impl.hh:430-457), same arrangement: one called
+// function, divisions / exponentials / square root in line, so that the independent ones overlap.
+struct LayerDirect {
+  double lm, rdif_a, tdif_a, trnlay, rdir, tdir;
+};
+ELMK_HD_NOINLINE LayerDirect snicar_layer_direct_inl(const double ts, const double ws, const double gs, const double mu_not,
+                                                     const double exp_min)
+{
+  LayerDirect o;
+  const double lm = sqrt(3.0 * (1.0 - ws) * (1.0 - ws * gs));
+  const double ue = 1.5 * (1.0 - ws * gs) / lm;
+  const double extins = dmax(exp_min, exp(-lm * ts));
+  const double ne = ((ue + 1.0) * (ue + 1.0) / extins) - ((ue - 1.0) * (ue - 1.0) * extins);
+  o.lm = lm;
+  o.rdif_a = (sq(ue) - 1.0) * (1.0 / extins - extins) / ne;
+  o.tdif_a = 4.0 * ue / ne;
+  o.trnlay = dmax(exp_min, exp(-ts / mu_not));
+  const double alp = 0.75 * ws * mu_not * ((1.0 + gs * (1.0 - ws)) / (1.0 - lm * lm * mu_not * mu_not));
+  const double gam = 0.5 * ws * ((1.0 + 3.0 * gs * (1.0 - ws) * mu_not * mu_not) / (1.0 - lm * lm * mu_not * mu_not));
+  const double apg = alp + gam;
+  const double amg = alp - gam;
+  o.rdir = apg * o.rdif_a + amg * (o.tdif_a * o.trnlay - 1.0);
+  o.tdir = apg * o.tdif_a + (amg * o.rdif_a - apg + 1.0) * o.trnlay;
+  return o;
+}
+
+struct GaussPair {
+  double rdr0, tdr0, rdr1, tdr1;
+};
+ELMK_HD_NOINLINE GaussPair snicar_gauss_pair_inl(const double ts, const double ws, const double gs, const double lm,
+                                                 const double R1, const double T1, const double mu0, const double mu1,
+                                                 const double exp_min)
+{
+  GaussPair g;
+  {
+    const double mu = mu0;
+    const double trn = dmax(exp_min, exp(-ts / mu));
+    const double alp = 0.75 * ws * mu * ((1.0 + gs * (1.0 - ws)) / (1.0 - lm * lm * mu * mu));
+    const double gam = 0.5 * ws * ((1.0 + 3.0 * gs * (1.0 - ws) * mu * mu) / (1.0 - lm * lm * mu * mu));
+    const double apg = alp + gam;
+    const double amg = alp - gam;
+    g.rdr0 = apg * R1 + amg * T1 * trn - amg;
+    g.tdr0 = apg * T1 + amg * R1 * trn - apg * trn + trn;
+  }
+  {
+    const double mu = mu1;
+    const double trn = dmax(exp_min, exp(-ts / mu));
+    const double alp = 0.75 * ws * mu * ((1.0 + gs * (1.0 - ws)) / (1.0 - lm * lm * mu * mu));
+    const double gam = 0.5 * ws * ((1.0 + 3.0 * gs * (1.0 - ws) * mu * mu) / (1.0 - lm * lm * mu * mu));
+    const double apg = alp + gam;
+    const double amg = alp - gam;
+    g.rdr1 = apg * R1 + amg * T1 * trn - amg;
+    g.tdr1 = apg * T1 + amg * R1 * trn - apg * trn + trn;
+  }
+  return g;
+}
+
 ELMK_HD_NOINLINE void snicar_solve(const Cols& S, const Tables& T, const int c, const int flg, const double coszen,
                           const double h2osno, const int snl, const double (&albsoi)[NUMRAD],
                           const double (&cnc)[NLEVSNO][NAER], double (&alb_out)[NUMRAD],
@@ -163,36 +225,26 @@ ELMK_HD_NOINLINE void snicar_solve(const Cols& S, const Tables& T, const int c, 
       if (i >= top) {
         if (trntdr[i] > trmin) {
           const double ts = ts_[i], ws = ws_[i], gs = gs_[i];
-          const double lm = sqrt(3.0 * (1.0 - ws) * (1.0 - ws * gs));
-          const double ue = 1.5 * (1.0 - ws * gs) / lm;
-          const double extins = dmax(exp_min, m_exp(-lm * ts));
-          const double ne = ((ue + 1.0) * (ue + 1.0) / extins) - ((ue - 1.0) * (ue - 1.0) * extins);
-          rdif_a[i] = (sq(ue) - 1.0) * (1.0 / extins - extins) / ne;
-          tdif_a[i] = 4.0 * ue / ne;
-          trnlay[i] = dmax(exp_min, m_exp(-ts / mu_not));
-          double alp = 0.75 * ws * mu_not * ((1.0 + gs * (1.0 - ws)) / (1.0 - lm * lm * mu_not * mu_not));
-          double gam = 0.5 * ws * ((1.0 + 3.0 * gs * (1.0 - ws) * mu_not * mu_not) / (1.0 - lm * lm * mu_not * mu_not));
-          double apg = alp + gam;
-          double amg = alp - gam;
-          rdir[i] = apg * rdif_a[i] + amg * (tdif_a[i] * trnlay[i] - 1.0);
-          tdir[i] = apg * tdif_a[i] + (amg * rdif_a[i] - apg + 1.0) * trnlay[i];
+          const LayerDirect ld = snicar_layer_direct_inl(ts, ws, gs, mu_not, exp_min);
+          const double lm = ld.lm;
+          rdif_a[i] = ld.rdif_a;
+          tdif_a[i] = ld.tdif_a;
+          trnlay[i] = ld.trnlay;
+          rdir[i] = ld.rdir;
+          tdir[i] = ld.tdir;
           const double R1 = rdif_a[i];
           const double T1 = tdif_a[i];
           double swt = 0.0, smr = 0.0, smt = 0.0;
 #pragma unroll 1
-          for (int ng = 0; ng < 8; ++ng) {
-            const double mu = gauspt[ng];
-            const double gwt = gauswt[ng];
-            swt = swt + mu * gwt;
-            const double trn = dmax(exp_min, m_exp(-ts / mu));
-            alp = 0.75 * ws * mu * ((1.0 + gs * (1.0 - ws)) / (1.0 - lm * lm * mu * mu));
-            gam = 0.5 * ws * ((1.0 + 3.0 * gs * (1.0 - ws) * mu * mu) / (1.0 - lm * lm * mu * mu));
-            apg = alp + gam;
-            amg = alp - gam;
-            const double rdr = apg * R1 + amg * T1 * trn - amg;
-            const double tdr = apg * T1 + amg * R1 * trn - apg * trn + trn;
-            smr = smr + mu * rdr * gwt;
-            smt = smt + mu * tdr * gwt;
+          for (int ng = 0; ng < 8; ng += 2) {
+            const double mu0 = gauspt[ng], gwt0 = gauswt[ng], mu1 = gauspt[ng + 1], gwt1 = gauswt[ng + 1];
+            const GaussPair g = snicar_gauss_pair_inl(ts, ws, gs, lm, R1, T1, mu0, mu1, exp_min);
+            swt = swt + mu0 * gwt0;
+            smr = smr + mu0 * g.rdr0 * gwt0;
+            smt = smt + mu0 * g.tdr0 * gwt0;
+            swt = swt + mu1 * gwt1;
+            smr = smr + mu1 * g.rdr1 * gwt1;
+            smt = smt + mu1 * g.tdr1 * gwt1;
           }
           rdif_a[i] = smr / swt;
           tdif_a[i] = smt / swt;

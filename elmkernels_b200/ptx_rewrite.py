@@ -59,6 +59,7 @@ REG = re.compile(r"%[a-z]+\d+")
 # a division may move up across anything but the end of its basic block (it reads registers only)
 BARRIER = re.compile(r"^\s*(?:\$[\w$]+:|(?:@!?%p\d+\s+)?bra\b|ret\b|exit\b|bar\b|trap\b)")
 SKIP = re.compile(r"^\s*(?:\{|\}|//|\.loc|\.param|\(|\)|param\d+|[\w$]+,\s*$)")
+INLINE_FUNCS = re.compile(r"\w+_inlE")   # device functions (mangled ..._inlE<args>) that keep their divisions in line
 PAIR_IN = re.compile(r"k_groups(?:_occ|_sorted)?ILj128E")   # mangled names of the soil-temperature launches
 PAIR_WINDOW = 48   # instructions looked at after a division for an independent partner
 
@@ -134,7 +135,7 @@ DEST = re.compile(r"^\s*(?:@!?%p\d+\s+)?[a-z][\w.]*\s+(%fd\d+)\s*[,;]")
 
 def _rewrite_function(name: str, body: list[str], counter: list[int], stats: dict) -> list[str]:
     """body: the lines of one .func / .entry, from its header to its closing brace."""
-    if name in (M_DIV, M_DIV2) or name.startswith("__internal") or name.startswith("__nv_"):
+    if name in (M_DIV, M_DIV2) or name.startswith("__internal") or name.startswith("__nv_") or INLINE_FUNCS.search(name):
         return body
     # pairing pays where the launch is FP64-latency bound and not register-capped (A/B on B200: soil temperature
     # 5.85 -> 5.29 ms; snow hydrology and the surface chain, capped at 80 / 48 registers, lose 4-5 % to the extra live
