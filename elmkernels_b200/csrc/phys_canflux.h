@@ -57,6 +57,8 @@ ELMK_HD double psn_fth25(const double hd, const double se)
   return 1.0 + m_exp((-hd + se * (TFRZ + 25.0)) / (RGAS * 1.0e-3 * (TFRZ + 25.0)));
 }
 
+// ELMK_INLINE_DIV_BEGIN  (the quadratics and ci_func: eleven divisions per evaluation, pairwise independent - see
+//                          elmkernels_b200/ptx_rewrite.py, marked_ranges)
 // roots of a x^2 + b x + c, numerically stable form; a == 0 is an error in the reference
 ELMK_HD void psn_quadratic(const double a, const double b, const double cc, double& r1, double& r2, uint32_t& err)
 {
@@ -116,6 +118,7 @@ ELMK_HD double psn_ci_func(const double ci, LeafPsn& L, uint32_t& err)
   L.gs_mol = dmax(r1, r2);
   return ci - L.cair + L.an * L.pbot * (1.4 * L.gs_mol + L.gb16) / (L.gb_mol * L.gs_mol);
 }
+// ELMK_INLINE_DIV_END
 
 // Root of ci_func: secant search for a sign change, Brent's method (Numerical Recipes form) once a root is
 // bracketed; leaves the side outputs of the last ci_func evaluation in L.  Reference: hybrid

@@ -55,6 +55,19 @@ def _call2(ind: str, d0: str, a0: str, b0: str, d1: str, a1: str, b1: str) -> st
             f"{ind}ld.param.v2.f64 \t{{{d0}, {d1}}}, [retval0];\n{ind}}}")
 
 
+def _guarded_inline(ind: str, d: str, a: str, b: str, k: int) -> str:
+    """The division stays in line (ptxas' own sequence, free to overlap with its neighbours); only a zero numerator -
+    which would send that sequence through its slow path - takes the m_div call."""
+    return (f"{ind}{{ // elmk in-line division, zero numerators to m_div\n{ind}.reg .pred %pz;\n"
+            f"{ind}setp.eq.f64 \t%pz, {a}, 0d0000000000000000;\n"
+            f"{ind}@%pz bra \t$L__elmk_z{k};\n"
+            f"{ind}div.rn.f64 \t{d}, {a}, {b};\n"
+            f"{ind}bra \t$L__elmk_e{k};\n"
+            f"$L__elmk_z{k}:\n" + _call(ind, d, a, b) + f"\n$L__elmk_e{k}:\n{ind}}}")
+
+
+LOC = re.compile(r"^\s*\.loc\s+(\d+)\s+(\d+)\s")
+FILEDEF = re.compile(r'^\s*\.file\s+(\d+)\s+"([^"]+)"')
 REG = re.compile(r"%[a-z]+\d+")
 # a division may move up across anything but the end of its basic block (it reads registers only)
 BARRIER = re.compile(r"^\s*(?:\$[\w$]+:|(?:@!?%p\d+\s+)?bra\b|ret\b|exit\b|bar\b|trap\b)")
@@ -167,6 +180,8 @@ def _rewrite_function(name: str, body: list[str], counter: list[int], stats: dic
             return not (c == c and 2.0 ** -100 < abs(c) < 2.0 ** 100)
         return b not in params
 
+    inline_ranges = stats.get("inline_ranges", {})   # file index -> [(first line, last line)]
+    cur_loc = (0, 0)
     skip = set()
     moved_down = {}   # index of the partner -> (d, a, b) of the earlier division evaluated there
     for idx, l in enumerate(body):
@@ -180,9 +195,17 @@ def _rewrite_function(name: str, body: list[str], counter: list[int], stats: dic
             continue
         m = DIV.match(l)
         if not m:
+            ml = LOC.match(l)
+            if ml:
+                cur_loc = (int(ml.group(1)), int(ml.group(2)))
             out.append(l)
             continue
         ind, d, a, b = (x.strip() if i else x for i, x in enumerate(m.groups()))
+        if any(lo <= cur_loc[1] <= hi for lo, hi in inline_ranges.get(cur_loc[0], ())) and not a.startswith("0d"):
+            out.append(_guarded_inline(ind, d, a, b, counter[0]))
+            counter[0] += 1
+            stats["inline"] += 1
+            continue
         if b.startswith("0d") and not a.startswith("0d"):
             c = struct.unpack("<d", struct.pack("<Q", int(b[2:], 16)))[0]
             if c == c and 2.0 ** -100 < abs(c) < 2.0 ** 100:
@@ -230,13 +253,36 @@ def _rewrite_function(name: str, body: list[str], counter: list[int], stats: dic
     return out
 
 
-def rewrite(text: str) -> tuple[str, dict]:
+def marked_ranges(csrc_dir: str) -> dict:
+    """{file name: [(first, last)]} of the source stretches between `// ELMK_INLINE_DIV_BEGIN` and `// ELMK_INLINE_DIV_END`:
+    short, hot, branch-free stretches with several independent divisions, which gain more from overlapping their
+    in-line Newton sequences than they lose in instruction-cache footprint."""
+    import glob, os
+    res = {}
+    for path in sorted(glob.glob(os.path.join(csrc_dir, "*.h")) + glob.glob(os.path.join(csrc_dir, "*.cu"))):
+        first = None
+        for n, line in enumerate(open(path), 1):
+            if "ELMK_INLINE_DIV_BEGIN" in line and "define" not in line:
+                first = n
+            elif "ELMK_INLINE_DIV_END" in line and first is not None:
+                res.setdefault(os.path.basename(path), []).append((first, n))
+                first = None
+    return res
+
+
+def rewrite(text: str, ranges_by_name: dict | None = None) -> tuple[str, dict]:
     """Returns (new text, counts of divisions by kind)."""
     if f"{M_DIV}(" not in text:
         raise RuntimeError(f"ptx_rewrite: {M_DIV} is not defined in the PTX (elmk::m_div must be used at least once)")
     lines = text.split("\n")
     have_proto = any(l.startswith(".func") and l.rstrip().endswith(M_DIV) for l in lines[:400])
-    out, stats, counter = [], {"call": 0, "const": 0, "param": 0, "pair": 0,
+    files = {}
+    for l in text.split("\n"):
+        mf = FILEDEF.match(l)
+        if mf:
+            files[mf.group(2).split("/")[-1]] = int(mf.group(1))
+    inline_ranges = {files[n]: r for n, r in (ranges_by_name or {}).items() if n in files}
+    out, stats, counter = [], {"call": 0, "const": 0, "param": 0, "pair": 0, "inline": 0, "inline_ranges": inline_ranges,
                                "have": {M_DIV2} if f"{M_DIV2}(" in text else set()}, [0]
     i = 0
     while i < len(lines):
@@ -264,11 +310,12 @@ def rewrite(text: str) -> tuple[str, dict]:
 
 
 def main(path: str) -> None:
+    import os
     text = open(path).read()
-    new, st = rewrite(text)
+    new, st = rewrite(text, marked_ranges(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")))
     open(path, "w").write(new)
     print(f"ptx_rewrite: {st['call']} double divisions routed through elmk::m_div, {st['pair']} pairwise through "
-          f"elmk::m_div2, {st['const']} by literals and {st['param']} by kernel parameters through exact reciprocal "
+          f"elmk::m_div2, {st['inline']} kept in line (marked stretches), {st['const']} by literals and {st['param']} by kernel parameters through exact reciprocal "
           f"sequences, in {path}")
 
 
