@@ -108,6 +108,7 @@ class Library:
             "elmk_exchange_commit": (C.c_int, [H]),
             "elmk_exchange_fetch": (C.c_int, [H, C.POINTER(C.c_void_p)]),
             "elmk_exchange_wait": (C.c_int, [H]),
+            "elmk_init_columns": (C.c_int, [H, _PD, _PD, _PD, C.c_double, _PD]),
             "elmk_atm_series": (C.c_int, [H, C.c_int, _PD, C.c_int]),
             "elmk_atm_forcing": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_int]),
             "elmk_phen_series": (C.c_int, [H, C.c_int, _PD, C.c_int]),
@@ -303,6 +304,21 @@ class Columns:
         x = Exchange(self, in_names, out_names)
         self._exchanges.append(x)
         return x
+
+    def init_columns(self, pct_sand: np.ndarray, pct_clay: np.ndarray, organic: np.ndarray, organic_max: float,
+                     snow_depth: np.ndarray):
+        """One-time cold start of every column (initialize_elm_kokkos.cc:374-431) from soil texture (ncols, 15) and the
+        initial snow depth (ncols,); vtype, topo_slope, topo_std and the soil grid must be in the state already."""
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (pct_sand, pct_clay, organic)]
+        d = np.ascontiguousarray(snow_depth, dtype=np.float64)
+        for x in a:
+            if x.shape != (self.ncols, 15):
+                raise ElmkError(f"soil texture arrays must have shape ({self.ncols}, 15), got {x.shape}")
+        if d.shape != (self.ncols,):
+            raise ElmkError("snow_depth must have one value per column")
+        self._check(self.lib.dll.elmk_init_columns(self._h, a[0].ctypes.data_as(_PD), a[1].ctypes.data_as(_PD),
+                                                   a[2].ctypes.data_as(_PD), float(organic_max), d.ctypes.data_as(_PD)),
+                    "elmk_init_columns")
 
     # -- per-step input producers on the device (forcing functors, phenology) --
     ATM_VARS = ("TBOT", "PBOT", "QBOT", "FLDS", "FSDS", "PREC", "WIND")

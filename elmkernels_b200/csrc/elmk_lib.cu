@@ -27,6 +27,7 @@
 #include "phys_cantemp.h"
 #include "phys_forcing.h"
 #include "phys_hydrology.h"
+#include "phys_init.h"
 #include "phys_radiation.h"
 #include "phys_snow.h"
 #include "phys_soiltemp.h"
@@ -327,6 +328,12 @@ __global__ void __launch_bounds__(kBlock) k_init_timestep(const Cols S, const Ta
   column_init_timestep(S, *Tp, reset, c);
 }
 
+__global__ void __launch_bounds__(kBlock) k_init_columns(const Cols S, const Tables* __restrict__ Tp, const InitInputs X)
+{
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  if (c >= S.ncols) return;
+  column_init(S, *Tp, X, c);
+}
 __global__ void __launch_bounds__(kBlock) k_atm_forcing(const Cols S, const AtmSeries A, const int t, const double wt1,
                                                         const double wt2, const int qbot_is_rh)
 {
@@ -642,16 +649,18 @@ int convert(Ctx* c, bool up, const T* staged_or_field, T* dst, int64_t n, int nl
 }
 
 // host <-> device movement of one field; asynchronous on the stream when the host buffer is pinned
+int move_raw(Ctx* c, char* dev, int dt, int nlev, void* host, int64_t col0, int64_t n, int layout, bool up);
 int move_field(Ctx* c, int field, void* host, int64_t col0, int64_t n, int layout, bool up) {
   if (field < 0 || field >= kNumFields || col0 < 0 || n < 0 || col0 + n > c->ncols || !host) {
     c->last_error = "bad field / column range";
     return ELMK_EINVAL;
   }
   if (n == 0) return ELMK_OK;
-  const int nlev = kSpecs[field].nlev;
-  const int dt = kSpecs[field].dtype;
+  return move_raw(c, static_cast<char*>(c->base[field]), kSpecs[field].dtype, kSpecs[field].nlev, host, col0, n, layout, up);
+}
+// the same for any device array laid out like a field ([nlev][np])
+int move_raw(Ctx* c, char* dev, int dt, int nlev, void* host, int64_t col0, int64_t n, int layout, bool up) {
   const size_t es = esize(dt);
-  char* dev = static_cast<char*>(c->base[field]);
   char* hb = static_cast<char*>(host);
   const cudaMemcpyKind kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
   if (nlev == 1) {
@@ -944,6 +953,9 @@ int elmk_set_tables(elmk_handle h, const elmk_tables* t) {
     T.rhos[v][0] = t->pft[34][v]; T.rhos[v][1] = t->pft[35][v];
     T.taul[v][0] = t->pft[36][v]; T.taul[v][1] = t->pft[37][v];
     T.taus[v][0] = t->pft[38][v]; T.taus[v][1] = t->pft[39][v];
+    for (int k = 0; k < 26; ++k) T.psn[k][v] = t->pft[k][v];
+    T.psn[26][v] = t->pft[26][0];
+    T.roota[v] = t->pft[30][v]; T.rootb[v] = t->pft[31][v];
   }
   std::memcpy(T.albsat, t->albsat, sizeof(T.albsat));
   std::memcpy(T.albdry, t->albdry, sizeof(T.albdry));
@@ -1163,6 +1175,38 @@ int set_series(Ctx* c, double** slot, int* count, const double* host, int n) {
   return ELMK_OK;
 }
 } // namespace
+
+// ---- one-time cold-start initialisation of every column ----
+int elmk_init_columns(elmk_handle h, const double* pct_sand, const double* pct_clay, const double* organic,
+                      double organic_max, const double* snow_depth) {
+  Ctx* c = ctx(h);
+  if (!c || !pct_sand || !pct_clay || !organic || !snow_depth) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (!c->tables_set) return ELMK_ENOTABLES;
+  double* buf = nullptr;
+  const size_t per = (size_t)NLEVGRND * c->np;
+  CU(cudaMalloc(&buf, sizeof(double) * (3 * per + c->np)));
+  int rc = ELMK_OK;
+  const double* hosts[3] = {pct_sand, pct_clay, organic};
+  for (int k = 0; k < 3 && rc == ELMK_OK; ++k)
+    rc = move_raw(c, reinterpret_cast<char*>(buf + k * per), ELMK_F64, NLEVGRND, const_cast<double*>(hosts[k]), 0, c->ncols,
+                  ELMK_COL_OUTER, true);
+  if (rc == ELMK_OK) {
+    cudaError_t e = cudaMemcpyAsync(buf + 3 * per, snow_depth, sizeof(double) * c->ncols, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) rc = fail(c, e, "cudaMemcpyAsync(snow_depth)");
+  }
+  if (rc == ELMK_OK) {
+    const InitInputs X{buf, buf + per, buf + 2 * per, buf + 3 * per, c->np, organic_max};
+    const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
+    TimedScope ts(c, "init_columns", 0u);
+    k_init_columns<<<grid, kBlock, 0, c->stream>>>(c->cols, c->d_tables, X);
+    c->launches += 1;
+  }
+  cudaStreamSynchronize(c->stream);
+  cudaFree(buf);
+  if (rc == ELMK_OK) CU(cudaGetLastError());
+  return rc;
+}
 
 int elmk_atm_series(elmk_handle h, int var, const double* host, int ntimes) {
   Ctx* c = ctx(h);

@@ -33,6 +33,9 @@ struct Tables {
   double z0mr[17], displar[17];
   double xl[17], rhol[17][2], rhos[17][2], taul[17][2], taus[17][2];
   double albsat[20][2], albdry[20][2];
+  // photosynthesis constants per PFT in the member order of PFTDataPSN (row 26 = tc_stress, one value for all) and the
+  // root-profile parameters: only the one-time column initialisation reads them (phys_init.h)
+  double psn[27][17], roota[17], rootb[17];
   // SNICAR optics (snicar_data.h:40-70)
   double aer_band[6][3][NBND_SNW];       // [oc1,oc2,dst1..dst4][ss_alb,asm_prm,ext_cff_mss][band]
   double bc[2][3][10][NBND_SNW];         // [bc1,bc2][ss_alb,asm_prm,ext_cff_mss][nclrds][band]

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ELMK_ABI_VERSION 3
+#define ELMK_ABI_VERSION 4
 
 /* ---- dimensions (reference src/data/elm_constants.h:84-98) ---- */
 #define ELMK_NLEVSNO 5
@@ -178,6 +178,15 @@ int elmk_exchange_post(elmk_exchange x, const void* const* in_hosts);
 int elmk_exchange_commit(elmk_exchange x);
 int elmk_exchange_fetch(elmk_exchange x, void* const* out_hosts);
 int elmk_exchange_wait(elmk_exchange x);
+
+/* ---- one-time cold-start initialisation of every column: the per-column lambda of initialize_kokkos_elm
+ *      (driver/kokkos/initialize_elm_kokkos.cc:374-431) - psn_pft from vtype, init_topo_slope, init_melt_factor,
+ *      init_micro_sigma, init_snow_layers, init_soil_hydraulics, init_vegrootfr, init_soil_temp, init_snow_state,
+ *      init_soilh2o_state.  Needs elmk_set_tables and, in the state, vtype, the raw topo_slope, topo_std and the soil
+ *      part of dz / zsoi / zisoi (elm_kokkos_interface.cc:137-184).  pct_sand, pct_clay, organic: host[col * 15 + lev]
+ *      (ViewD2(ncols, nlevgrnd)); snow_depth: host[col], the depth the snow layers are built from. ---- */
+int elmk_init_columns(elmk_handle h, const double* pct_sand, const double* pct_clay, const double* organic,
+                      double organic_max, const double* snow_depth);
 
 /* ---- producers of the per-step inputs, on the device (the step before the chain in kokkos_init_timestep,
  *      init_timestep_kokkos.cc:39-47).

@@ -21,6 +21,7 @@
 #include "../../elmkernels_b200/csrc/phys_cantemp.h"
 #include "../../elmkernels_b200/csrc/phys_forcing.h"
 #include "../../elmkernels_b200/csrc/phys_hydrology.h"
+#include "../../elmkernels_b200/csrc/phys_init.h"
 #include "../../elmkernels_b200/csrc/phys_radiation.h"
 #include "../../elmkernels_b200/csrc/phys_snow.h"
 #include "../../elmkernels_b200/csrc/phys_soiltemp.h"
@@ -127,6 +128,9 @@ int elmk_set_tables(elmk_handle h, const elmk_tables* t) {
     T.rhos[v][0] = t->pft[34][v]; T.rhos[v][1] = t->pft[35][v];
     T.taul[v][0] = t->pft[36][v]; T.taul[v][1] = t->pft[37][v];
     T.taus[v][0] = t->pft[38][v]; T.taus[v][1] = t->pft[39][v];
+    for (int k = 0; k < 26; ++k) T.psn[k][v] = t->pft[k][v];
+    T.psn[26][v] = t->pft[26][0];
+    T.roota[v] = t->pft[30][v]; T.rootb[v] = t->pft[31][v];
   }
   std::memcpy(T.albsat, t->albsat, sizeof(T.albsat));
   std::memcpy(T.albdry, t->albdry, sizeof(T.albdry));
@@ -188,6 +192,23 @@ int elmk_fill(elmk_handle h, int field, double value) {
   if (kSpecs[field].dtype == ELMK_F64) std::fill_n(static_cast<double*>(c.base[field]), count, value);
   else if (kSpecs[field].dtype == ELMK_I32) std::fill_n(static_cast<int*>(c.base[field]), count, static_cast<int>(value));
   else std::fill_n(static_cast<unsigned char*>(c.base[field]), count, static_cast<unsigned char>(value != 0.0));
+  return ELMK_OK;
+}
+
+int elmk_init_columns(elmk_handle h, const double* pct_sand, const double* pct_clay, const double* organic,
+                      double organic_max, const double* snow_depth) {
+  PortCtx& c = *ctx(h);
+  if (!c.tables_set) return ELMK_ENOTABLES;
+  // host[col][lev] -> [lev][ncols], the layout column_init reads
+  std::vector<double> t[3];
+  const double* src[3] = {pct_sand, pct_clay, organic};
+  for (int k = 0; k < 3; ++k) {
+    t[k].resize((size_t)NLEVGRND * c.ncols);
+    for (int64_t i = 0; i < c.ncols; ++i)
+      for (int l = 0; l < NLEVGRND; ++l) t[k][(size_t)l * c.ncols + i] = src[k][(size_t)i * NLEVGRND + l];
+  }
+  const InitInputs X{t[0].data(), t[1].data(), t[2].data(), snow_depth, (long long)c.ncols, organic_max};
+  for_columns(c, [&](int i) { column_init(c.cols, c.tab, X, i); });
   return ELMK_OK;
 }
 

@@ -570,6 +570,12 @@ int elmref_init_columns(elmk_handle h, const double* pct_sand, const double* pct
   return ELMK_OK;
 }
 
+// the same entry point under the product's name (include/elmk_b200.h)
+int elmk_init_columns(elmk_handle h, const double* pct_sand, const double* pct_clay, const double* organic,
+                      double organic_max, const double* snow_depth) {
+  return elmref_init_columns(h, pct_sand, pct_clay, organic, organic_max, snow_depth);
+}
+
 #include "exchange_host.h"
 
 } // extern "C"
