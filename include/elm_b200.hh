@@ -146,6 +146,22 @@ public:
     return out;
   }
 
+  // ---- one-time cold start of every column: the per-column lambda of initialize_kokkos_elm
+  //      (initialize_elm_kokkos.cc:374-431).  Texture arrays are read as a(col, lev), snow depth as a(col). ----
+  template <class Arr2, class Arr1>
+  void init_columns(const Arr2& pct_sand, const Arr2& pct_clay, const Arr2& organic, double organic_max, const Arr1& snow_depth) {
+    auto rows = [this](const Arr2& a) {
+      std::vector<double> b(static_cast<size_t>(ncols_) * ELMK_NLEVGRND);
+      for (int64_t i = 0; i < ncols_; ++i)
+        for (int l = 0; l < ELMK_NLEVGRND; ++l) b[static_cast<size_t>(i) * ELMK_NLEVGRND + l] = a(static_cast<int>(i), l);
+      return b;
+    };
+    const std::vector<double> s = rows(pct_sand), c = rows(pct_clay), o = rows(organic);
+    std::vector<double> d(static_cast<size_t>(ncols_));
+    for (int64_t i = 0; i < ncols_; ++i) d[static_cast<size_t>(i)] = snow_depth(static_cast<int>(i));
+    check(elmk_init_columns(h_, s.data(), c.data(), o.data(), organic_max, d.data()), "elmk_init_columns");
+  }
+
   // ---- per-step input producers on the device (ELM::get_forcing, atm_forcing_kokkos.cc:48-63; ComputePhenology via
   //      PhenologyDataManager::get_data, phenology_data_impl.hh:46-63).  `data` is the manager's (ntimes, ncells)
   //      array - AtmDataManager::data, PhenologyDataManager::mlai/msai/mhtop/mhbot - read through operator()(t, i). ----
