@@ -49,10 +49,19 @@ ELMK_HD void column_bareground_fluxes(const Cols& S, const Tables&, const int c)
 
   // -- stability_iteration: exactly three passes, no convergence test --
   double z0hg = C1(z0hg), z0qg = C1(z0qg);
+  // (friction velocity and the temperature relation are evaluated together; the 2 m relations, which the reference
+  //  evaluates in every pass but reads after the last one only, once after the loop from that pass's inputs)
   MoProfiles p;
+  double obu_p = obu, z0h_p = z0hg, z0q_p = z0qg;
 #pragma unroll 1
   for (int it = 0; it < 3; ++it) {
-    p = mo_profiles(hgt_u, hgt_t, hgt_q, displa, um, obu, z0mg, z0hg, z0qg);
+    obu_p = obu; z0h_p = z0hg; z0q_p = z0qg;
+    {
+      const MoPair mp = mo_pair_inl(hgt_u - displa, hgt_t - displa, um, obu, z0mg, z0hg);
+      p.ustar = mp.ustar;
+      p.temp1 = mp.temp;
+    }
+    p.temp2 = (hgt_q == hgt_t && z0qg == z0hg) ? p.temp1 : mo_scalar_profile(hgt_q - displa, obu, z0qg);
     const double tstar = p.temp1 * dth;
     const double qstar = p.temp2 * dqh;
     const double thvstar = tstar * (1.0 + 0.61 * forc_q) + 0.61 * forc_th * qstar;
@@ -71,6 +80,8 @@ ELMK_HD void column_bareground_fluxes(const Cols& S, const Tables&, const int c)
   }
   C1(z0hg) = z0hg;
   C1(z0qg) = z0qg;
+  p.temp12m = mo_scalar_profile(2.0 + z0h_p, obu_p, z0h_p, true);
+  p.temp22m = (z0q_p == z0h_p) ? p.temp12m : mo_scalar_profile(2.0 + z0q_p, obu_p, z0q_p);
 
   // -- compute_flux --
   const double rah = 1.0 / (p.temp1 * p.ustar);

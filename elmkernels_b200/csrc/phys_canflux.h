@@ -317,6 +317,17 @@ struct PsnPass {
   double kc, ko, cp;                         // Michaelis-Menten constants and CO2 compensation point
 };
 
+// ELMK_INLINE_DIV_BEGIN
+// the same two with the exponential in line: psn_pass evaluates up to eleven of them at one leaf temperature, all
+// independent - called, they would run one after the other (elmk_common.h, m_div2)
+ELMK_HD double psn_ft_i(const double tl, const double ha)
+{
+  return exp(ha / (RGAS * 1.0e-3 * (TFRZ + 25.0)) * (1.0 - (TFRZ + 25.0) / tl));
+}
+ELMK_HD double psn_fth_i(const double tl, const double hd, const double se, const double scale)
+{
+  return scale / (1.0 + exp((-hd + se * tl) / (RGAS * 1.0e-3 * tl)));
+}
 ELMK_HD PsnPass psn_pass(const PsnPft& P, const PsnColumn& C, const double t_veg, const bool day)
 {
   PsnPass T;
@@ -324,29 +335,30 @@ ELMK_HD PsnPass psn_pass(const PsnPft& P, const PsnColumn& C, const double t_veg
   T.vc_a = 0.0; T.vc_b = 0.0; T.jm_a = 0.0; T.jm_b = 0.0; T.tp_a = 0.0; T.tp_b = 0.0;
   if (!C.c3 || day) T.p2 = pow_cbase(2.0, ELMK_LN_2, ((t_veg - (TFRZ + 25.0)) / 10.0));
   if (C.c3) {
-    T.lmr_a = psn_ft(t_veg, P.lmrha);
-    T.lmr_b = psn_fth(t_veg, P.lmrhd, P.lmrse, C.lmrc);
+    T.lmr_a = psn_ft_i(t_veg, P.lmrha);
+    T.lmr_b = psn_fth_i(t_veg, P.lmrhd, P.lmrse, C.lmrc);
   } else {
     T.lmr_a = T.p2;
-    T.lmr_b = (1.0 + m_exp(1.3 * (t_veg - (TFRZ + 55.0))));
+    T.lmr_b = (1.0 + exp(1.3 * (t_veg - (TFRZ + 55.0))));
   }
   if (day) {
-    T.vc_a = psn_ft(t_veg, P.vcmaxha);
-    T.vc_b = psn_fth(t_veg, P.vcmaxhd, C.vcmaxse, C.vcmaxc);
-    T.jm_a = psn_ft(t_veg, P.jmaxha);
-    T.jm_b = psn_fth(t_veg, P.jmaxhd, C.jmaxse, C.jmaxc);
-    T.tp_a = psn_ft(t_veg, P.tpuha);
-    T.tp_b = psn_fth(t_veg, P.tpuhd, C.tpuse, C.tpuc);
+    T.vc_a = psn_ft_i(t_veg, P.vcmaxha);
+    T.vc_b = psn_fth_i(t_veg, P.vcmaxhd, C.vcmaxse, C.vcmaxc);
+    T.jm_a = psn_ft_i(t_veg, P.jmaxha);
+    T.jm_b = psn_fth_i(t_veg, P.jmaxhd, C.jmaxse, C.jmaxc);
+    T.tp_a = psn_ft_i(t_veg, P.tpuha);
+    T.tp_b = psn_fth_i(t_veg, P.tpuhd, C.tpuse, C.tpuc);
     if (!C.c3) {
-      T.c4d1 = (1.0 + m_exp(0.2 * ((TFRZ + 15.0) - t_veg)));
-      T.c4d2 = (1.0 + m_exp(0.3 * (t_veg - (TFRZ + 40.0))));
+      T.c4d1 = (1.0 + exp(0.2 * ((TFRZ + 15.0) - t_veg)));
+      T.c4d2 = (1.0 + exp(0.3 * (t_veg - (TFRZ + 40.0))));
     }
   }
-  T.kc = C.kc25 * psn_ft(t_veg, P.kcha);
-  T.ko = C.ko25 * psn_ft(t_veg, P.koha);
-  T.cp = C.cp25 * psn_ft(t_veg, P.cpha);
+  T.kc = C.kc25 * psn_ft_i(t_veg, P.kcha);
+  T.ko = C.ko25 * psn_ft_i(t_veg, P.koha);
+  T.cp = C.cp25 * psn_ft_i(t_veg, P.cpha);
   return T;
 }
+// ELMK_INLINE_DIV_END
 
 // stomatal resistance of the sunlit or the shaded canopy fraction (nlevcan == 1, nrad == 1)
 ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const PsnColumn& C, const PsnPass& T, const int nrad,
@@ -596,8 +608,11 @@ ELMK_HD bool canflux_iterate(const PsnPft& P, const PsnColumn& PC, CanopyIter& I
   // reference also evaluates the 2 m relations in every pass (canopy_fluxes_impl.hh:232-240) but only reads those of the last one
   // (t_ref2m, q_ref2m): they are evaluated once, in canflux_end, from the Obukhov length this pass started with.
   MoProfiles p;
-  p.ustar = mo_ustar(I.hgt_u, I.displa, I.um, I.obu, I.z0mv);
-  p.temp1 = mo_scalar_profile(I.hgt_t - I.displa, I.obu, I.z0mv);
+  {
+    const MoPair mp = mo_pair_inl(I.hgt_u - I.displa, I.hgt_t - I.displa, I.um, I.obu, I.z0mv, I.z0mv);
+    p.ustar = mp.ustar;
+    p.temp1 = mp.temp;
+  }
   p.temp2 = (I.hgt_q == I.hgt_t) ? p.temp1 : mo_scalar_profile(I.hgt_q - I.displa, I.obu, I.z0mv);
   I.p_ustar = p.ustar; I.p_temp1 = p.temp1; I.p_temp2 = p.temp2; I.p_obu = I.obu;
   double t_veg = I.t_veg;

@@ -116,6 +116,68 @@ ELMK_HD_NOINLINE double mo_scalar_profile(const double zldis, const double obu, 
   return VKC / den;
 }
 
+// Friction velocity and one scalar profile relation at the same Obukhov length in ONE called function whose
+// logarithms, arctangents, square roots and divisions are in line (`_inl`: the build leaves its divisions alone).
+// Called one after the other, mo_ustar and mo_scalar_profile are two strings of up to six serial transcendental
+// calls; here the two leading logarithms, the four stability corrections of the unstable case and the quotients
+// are independent chains that ptxas interleaves.  Same operations per value as the two functions above; for a
+// very unstable lane psi is evaluated at the constant argument instead of being a stored constant.
+struct MoPair {
+  double ustar, temp;
+};
+ELMK_HD double mo_psi_m_i(const double zeta)
+{
+  const double chik2 = sqrt(1.0 - 16.0 * zeta);
+  const double chik = sqrt(chik2);
+  return 2.0 * log((1.0 + chik) * 0.5) + log((1.0 + chik2) * 0.5) - 2.0 * atan(chik) + PI * 0.5;
+}
+ELMK_HD double mo_psi_h_i(const double zeta)
+{
+  const double chik2 = sqrt(1.0 - 16.0 * zeta);
+  return 2.0 * log((1.0 + chik2) * 0.5);
+}
+ELMK_HD_NOINLINE MoPair mo_pair_inl(const double zldis_u, const double zldis_s, const double um, const double obu,
+                                    const double z0m, const double z0s)
+{
+  constexpr double zetam = 1.574, zetat = 0.465;
+  const double zeta_u = zldis_u / obu, zeta_s = zldis_s / obu;
+  const bool un_u = (zeta_u < 0.0), un_s = (zeta_s < 0.0);
+  if (un_u != un_s) {   // (cannot happen for heights above the displacement height; keeps the semantics anyway)
+    MoPair r;
+    r.ustar = mo_ustar(zldis_u, 0.0, um, obu, z0m);
+    r.temp = mo_scalar_profile(zldis_s, obu, z0s);
+    return r;
+  }
+  const bool far_u = un_u ? (zeta_u < (-zetam)) : !(zeta_u <= 1.0);
+  const bool far_s = un_s ? (zeta_s < (-zetat)) : !(zeta_s <= 1.0);
+  const double num_u = far_u ? (un_u ? -zetam * obu : obu) : zldis_u;
+  const double num_s = far_s ? (un_s ? -zetat * obu : obu) : zldis_s;
+  const double lead_u = log(num_u / z0m);
+  const double lead_s = log(num_s / z0s);
+  double den_u, den_s;
+  if (un_u) {
+    const double p1u = mo_psi_m_i(far_u ? -zetam : zeta_u);
+    const double p2u = mo_psi_m_i(z0m / obu);
+    const double p1s = mo_psi_h_i(far_s ? -zetat : zeta_s);
+    const double p2s = mo_psi_h_i(z0s / obu);
+    den_u = lead_u - p1u + p2u;
+    den_s = lead_s - p1s + p2s;
+    if (far_u) den_u = den_u + 1.14 * (m_pow((-zeta_u), 0.333) - ELMK_MO_POW_ZETAM);
+    if (far_s) den_s = den_s + 0.8 * (ELMK_MO_POW_ZETAT - m_pow((-zeta_s), -0.333));
+  } else {
+    const double tu = 5.0 * z0m / obu;
+    const double ts = 5.0 * z0s / obu;
+    if (far_u) den_u = lead_u + 5.0 - tu + (5.0 * log(zeta_u) + zeta_u - 1.0);
+    else den_u = lead_u + 5.0 * zeta_u - tu;
+    if (far_s) den_s = lead_s + 5.0 - ts + (5.0 * log(zeta_s) + zeta_s - 1.0);
+    else den_s = lead_s + 5.0 * zeta_s - ts;
+  }
+  MoPair r;
+  r.ustar = VKC * um / den_u;
+  r.temp = VKC / den_s;
+  return r;
+}
+
 // the five profile quantities of one stability iteration
 struct MoProfiles {
   double ustar, temp1, temp2, temp12m, temp22m;

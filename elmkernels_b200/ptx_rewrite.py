@@ -201,11 +201,6 @@ def _rewrite_function(name: str, body: list[str], counter: list[int], stats: dic
             out.append(l)
             continue
         ind, d, a, b = (x.strip() if i else x for i, x in enumerate(m.groups()))
-        if any(lo <= cur_loc[1] <= hi for lo, hi in inline_ranges.get(cur_loc[0], ())) and not a.startswith("0d"):
-            out.append(_guarded_inline(ind, d, a, b, counter[0]))
-            counter[0] += 1
-            stats["inline"] += 1
-            continue
         if b.startswith("0d") and not a.startswith("0d"):
             c = struct.unpack("<d", struct.pack("<Q", int(b[2:], 16)))[0]
             if c == c and 2.0 ** -100 < abs(c) < 2.0 ** 100:
@@ -219,6 +214,11 @@ def _rewrite_function(name: str, body: list[str], counter: list[int], stats: dic
             out.append(_recip_div(ind, d, a, f"%elmk_rc{i}", f"%elmk_nc{i}", counter[0], b, f"%elmk_pc{i}"))
             counter[0] += 1
             stats["param"] += 1
+            continue
+        if any(lo <= cur_loc[1] <= hi for lo, hi in inline_ranges.get(cur_loc[0], ())) and not a.startswith("0d"):
+            out.append(_guarded_inline(ind, d, a, b, counter[0]))
+            counter[0] += 1
+            stats["inline"] += 1
             continue
         found = _find_partner(body, idx, general) if pair else None
         if found is not None and found[1] == "down" and found[0] not in moved_down:
