@@ -222,8 +222,11 @@ __device__ __forceinline__ void canflux_store(const CanfluxQueue& Q, const int c
   ELMK_CANFLUX_INT(X)
 #undef X
 }
-__device__ __forceinline__ void canflux_load(const CanfluxQueue& Q, const int c, CanopyIter& I)
+__device__ __forceinline__ void canflux_load(const Cols& S, const CanfluxQueue& Q, const int c, CanopyIter& I)
 {
+#define X(n, e) I.n = e;
+  ELMK_CANFLUX_STATE(X)
+#undef X
   const double* p = Q.scratch + c;
   long long k = 0;
 #define X(n) I.n = p[k * Q.np]; ++k;
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
         const int q = base + __popc(need & below);
         if (q < total) {
           c = (q < nday) ? Q.list[q] : Q.list[Q.np - 1 - (q - nday)];
-          canflux_load(Q, c, I);
+          canflux_load(S, Q, c, I);
           P = load_psn_pft(S, c);
           PC = psn_column(P, I.t10, I.pbot, I.thm, I.forc_po2, I.dayl_factor);
           have = true;
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(kBlock) k_canflux_end(const Cols S, const Canf
   const int c = blockIdx.x * kBlock + threadIdx.x;
   if (c >= S.ncols || S.frac_veg_nosno[c] == 0) return;
   CanopyIter I;
-  canflux_load(Q, c, I);
+  canflux_load(S, Q, c, I);
   canflux_end(S, c, I);
 }
 

@@ -448,13 +448,22 @@ ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const PsnColumn& C, cons
 // column_canopy_fluxes = begin; while (!iterate) ; end  - the reference's control flow, used by the host
 // port and by the one-launch-per-group plan.
 
-// doubles of the iteration state: per-column constants first, then the loop-carried values
+// doubles of the iteration state.  STATE: plain copies of per-column state fields that CanopyFluxes does not change
+// before its last phase (the re-packed kernels re-read them from the state instead of carrying them through
+// scratch memory); CONST: values derived once in canflux_begin; CARRIED: the loop-carried values.
+#define ELMK_CANFLUX_STATE(X)                                                                                     \
+  X(pbot, C1(forc_pbot)) X(forc_q, C1(forc_qbot)) X(forc_th, C1(forc_thbot)) X(forc_lwrad, C1(forc_lwrad))        \
+  X(thm, C1(thm)) X(thv, C1(thv)) X(tg, C1(t_grnd)) X(qg, C1(qg)) X(elai, C1(elai)) X(esai, C1(esai))             \
+  X(emv, C1(emv)) X(emg, C1(emg)) X(z0mg, C1(z0mg)) X(hgt_u, C1(forc_hgt_u_patch)) X(hgt_t, C1(forc_hgt_t_patch)) \
+  X(hgt_q, C1(forc_hgt_q_patch)) X(displa, C1(displa)) X(z0mv, C1(z0mv)) X(fwet, C1(fwet)) X(fdry, C1(fdry))      \
+  X(laisun, C1(laisun)) X(laisha, C1(laisha)) X(snow_depth, C1(snow_depth)) X(soilbeta, C1(soilbeta))             \
+  X(fsno, C1(frac_sno)) X(fsfc, C1(frac_h2osfc)) X(sabv, C1(sabv)) X(htop, C1(htop)) X(t10, C1(t10))              \
+  X(h2ocan0, C1(h2ocan)) X(vcsha, C1(vcmaxcintsha)) X(vcsun, C1(vcmaxcintsun)) X(parsha, C2(parsha_z, 0))         \
+  X(parsun, C2(parsun_z, 0)) X(laisha_z, C2(laisha_z, 0)) X(laisun_z, C2(laisun_z, 0))                            \
+  X(t_soil1, C2(t_soisno, NLEVSNO)) X(t_sfc, C1(t_h2osfc))
 #define ELMK_CANFLUX_CONST(X)                                                                                     \
-  X(pbot) X(forc_q) X(forc_th) X(forc_lwrad) X(thm) X(thv) X(tg) X(qg) X(elai) X(esai) X(emv) X(emg) X(z0mg)     \
-  X(hgt_u) X(hgt_t) X(hgt_q) X(forc_po2) X(forc_pco2) X(forc_rho) X(dayl_factor) X(displa) X(z0mv) X(air) X(bir) \
-  X(cir) X(ur) X(zldis) X(fwet) X(fdry) X(laisun) X(laisha) X(snow_depth) X(soilbeta) X(fsno) X(fsfc) X(sabv)    \
-  X(htop) X(t10) X(h2ocan0) X(vcsha) X(vcsun) X(parsha) X(parsun) X(laisha_z) X(laisun_z) X(lw_grnd)             \
-  X(t_snotop) X(t_soil1) X(t_sfc) X(dtime)
+  X(forc_po2) X(forc_pco2) X(forc_rho) X(dayl_factor) X(air) X(bir) X(cir) X(ur) X(zldis) X(lw_grnd) X(t_snotop)  \
+  X(dtime)
 #define ELMK_CANFLUX_CARRIED(X)                                                                                   \
   X(btran) X(t_veg) X(el) X(qsatl) X(qsatldT) X(taf) X(qaf) X(dth) X(dqh) X(delq) X(um) X(obu) X(obuold) X(del)  \
   X(efeb) X(qflx_tran_veg) X(qflx_evap_veg) X(eflx_sh_veg) X(wtg) X(wtl0) X(wta0) X(wtal) X(wtgq) X(wtalq)       \
@@ -462,6 +471,9 @@ ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const PsnColumn& C, cons
 #define ELMK_CANFLUX_INT(X) X(nrad) X(veg) X(soybean) X(itlef) X(nmozsgn) X(err)
 
 struct CanopyIter {
+#define X(n, e) double n;
+  ELMK_CANFLUX_STATE(X)
+#undef X
 #define X(n) double n;
   ELMK_CANFLUX_CONST(X)
   ELMK_CANFLUX_CARRIED(X)
