@@ -1,0 +1,84 @@
+"""The PTX pass of the build (elmkernels_b200/ptx_rewrite.py): what it turns divisions into, and that the
+constant-divisor sequence it emits is IEEE division for every literal divisor of the device code."""
+import os
+import re
+import shutil
+import struct
+import subprocess
+
+import pytest
+
+from elmkernels_b200 import ptx_rewrite as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SNIPPET = """.version 8.8
+.target sm_100a
+.address_size 64
+
+.func  (.param .b64 func_retval0) _ZN4elmk5m_divEdd(
+	.param .b64 _ZN4elmk5m_divEdd_param_0,
+	.param .b64 _ZN4elmk5m_divEdd_param_1
+)
+{
+	.reg .f64 	%fd<4>;
+	ld.param.f64 	%fd1, [_ZN4elmk5m_divEdd_param_0];
+	ld.param.f64 	%fd2, [_ZN4elmk5m_divEdd_param_1];
+	div.rn.f64 	%fd3, %fd1, %fd2;
+	st.param.f64 	[func_retval0], %fd3;
+	ret;
+}
+.entry k_test(
+	.param .u64 k_test_param_0,
+	.param .f64 k_test_param_1
+)
+{
+	.reg .f64 	%fd<20>;
+	.reg .b64 	%rd<4>;
+	ld.param.u64 	%rd1, [k_test_param_0];
+	ld.param.f64 	%fd9, [k_test_param_1];
+	ld.global.f64 	%fd1, [%rd1];
+	ld.global.f64 	%fd2, [%rd1+8];
+	div.rn.f64 	%fd3, %fd1, %fd2;
+	div.rn.f64 	%fd4, %fd1, 0d408F400000000000;
+	div.rn.f64 	%fd5, %fd2, %fd9;
+	add.rn.f64 	%fd6, %fd3, %fd4;
+	st.global.f64 	[%rd1], %fd6;
+	ret;
+}
+"""
+
+
+def test_rewrite_forms():
+    out, st = R.rewrite(SNIPPET)
+    assert (st["call"], st["const"], st["param"]) == (1, 1, 1)
+    body = out[out.index(".entry k_test"):]
+    # general division -> call; its operands and destination survive
+    assert "_ZN4elmk5m_divEdd" in body and "ld.param.f64 \t%fd3, [retval0]" in body
+    # literal divisor 1000 -> multiply by RN(1/1000), two fused corrections, guarded
+    y = "0d%016X" % struct.unpack("<Q", struct.pack("<d", 1.0 / 1000.0))[0]
+    assert f"mul.rn.f64 \t%q, %fd1, {y}" in body and "fma.rn.f64 \t%fd4, %r, " + y in body
+    # kernel-parameter divisor -> reciprocal computed once after the parameter load
+    assert "rcp.rn.f64 \t%elmk_rc0, %fd9" in body and "fma.rn.f64 \t%fd5, %r, %elmk_rc0, %q" in body
+    # m_div's own division is left alone
+    assert "div.rn.f64 \t%fd3, %fd1, %fd2;" in out[:out.index(".entry k_test")]
+
+
+def test_missing_m_div_is_an_error():
+    with pytest.raises(RuntimeError):
+        R.rewrite(".version 8.8\n.target sm_100a\n.address_size 64\n")
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None or shutil.which("gcc") is None, reason="needs nvcc and gcc")
+def test_constant_divisor_sequence_equals_ieee_division(tmp_path):
+    ptx = tmp_path / "elmk.ptx"
+    from elmkernels_b200 import build
+    flags = [f for f in build.FLAGS if f not in ("-shared", "-Xcompiler", "-fPIC")]
+    subprocess.check_call([build.NVCC] + flags + ["-ptx", "-o", str(ptx), str(build.CSRC / "elmk_lib.cu")])
+    lits = sorted(set(re.findall(r"div\.rn\.f64\s+%fd\d+, %fd\d+, (0d[0-9A-F]{16});", ptx.read_text())))
+    assert len(lits) >= 10
+    exe = tmp_path / "check_constdiv"
+    subprocess.check_call(["gcc", "-O2", "-mfma", "-o", str(exe), os.path.join(ROOT, "tools", "check_constdiv.c"), "-lm"])
+    r = subprocess.run([str(exe), "-n1500000"] + lits, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "0 mismatches" in r.stdout.splitlines()[-1]
