@@ -150,6 +150,15 @@ ELMK_HD double pow_cbase(const double base, const double ln_hi, const double ln_
 #define ELMK_LN_TKICE 0x1.a837f19ef9d69p-1, 0x1.2e2416a47afa1p-55
 #define ELMK_LN_2 0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56
 
+// Re-alignment point for the warps of a block inside a long straight-line kernel body (device only, and only in the
+// instantiation whose launch keeps every thread of the block alive to the end): the soil-temperature body is ~270 KB
+// of SASS executed once from top to bottom, and warps that walk it together share each instruction-cache line.
+#if defined(__CUDA_ARCH__)
+#define ELMK_REALIGN(on) do { if (on) __syncthreads(); } while (0)
+#else
+#define ELMK_REALIGN(on) ((void)0)
+#endif
+
 // ---- arithmetic helpers ----
 // The reference is written with std::min/std::max; their NaN and signed-zero behaviour
 // ((b < a) ? b : a and (a < b) ? b : a) differs from fmin/fmax, so it is spelled out.

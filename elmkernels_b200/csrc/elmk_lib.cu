@@ -61,7 +61,11 @@ constexpr size_t kStageBytes = 64u << 20; // device staging buffer for layout co
 // ------------------------------------------------------------------------------------------------
 // column kernels
 // ------------------------------------------------------------------------------------------------
-template <uint32_t MASK>
+// kernels that run the soil-temperature group alone keep the threads of the padding columns (ncols..np, zero-filled,
+// never downloaded) alive, so that the block barriers inside that group's body are legal (ELMK_REALIGN)
+template <uint32_t MASK> constexpr bool kWholeBlocks = (MASK == ELMK_G_SOIL_TEMPERATURE);
+
+template <uint32_t MASK, bool REALIGN = false>
 __device__ __forceinline__ void run_groups(const Cols& S, const Tables& T, const StepArgs& A, const int c)
 {
   if (MASK & ELMK_G_FRAC_WET) column_frac_wet(S, T, c);
@@ -71,7 +75,7 @@ __device__ __forceinline__ void run_groups(const Cols& S, const Tables& T, const
   if (MASK & ELMK_G_CANOPY_TEMPERATURE) column_canopy_temperature(S, T, c);
   if (MASK & ELMK_G_BAREGROUND_FLUXES) column_bareground_fluxes(S, T, c);
   if (MASK & ELMK_G_CANOPY_FLUXES) column_canopy_fluxes(S, T, A, c);
-  if (MASK & ELMK_G_SOIL_TEMPERATURE) column_soil_temperature(S, T, A.dtime, c);
+  if (MASK & ELMK_G_SOIL_TEMPERATURE) column_soil_temperature<REALIGN>(S, T, A.dtime, c);
   if (MASK & ELMK_G_SNOW_HYDROLOGY) column_snow_hydrology(S, T, A.dtime, c);
   if (MASK & ELMK_G_SURFACE_FLUXES) column_surface_fluxes(S, T, A.dtime, c);
   if (MASK & ELMK_G_CONSERVATION) column_conservation(S, T, A.dtime, c);
@@ -81,16 +85,16 @@ template <uint32_t MASK>
 __global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
 {
   const int c = blockIdx.x * kBlock + threadIdx.x;
-  if (c >= S.ncols) return;
-  run_groups<MASK>(S, *Tp, A, c);
+  if (kWholeBlocks<MASK> ? (c >= S.np) : (c >= S.ncols)) return;
+  run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c);
 }
 // same, with a floor on the resident blocks per SM (caps the registers per thread)
 template <uint32_t MASK, int MINBLOCKS>
 __global__ void __launch_bounds__(kBlock, MINBLOCKS) k_groups_occ(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
 {
   const int c = blockIdx.x * kBlock + threadIdx.x;
-  if (c >= S.ncols) return;
-  run_groups<MASK>(S, *Tp, A, c);
+  if (kWholeBlocks<MASK> ? (c >= S.np) : (c >= S.ncols)) return;
+  run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c);
 }
 
 // ---- work-class sorted variant ------------------------------------------------------------------
@@ -379,12 +383,13 @@ constexpr uint32_t M_RAD = ELMK_G_FRAC_WET | ELMK_G_ALBEDO;
 constexpr uint32_t M_SFC = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | ELMK_G_CANOPY_TEMPERATURE |
                            ELMK_G_BAREGROUND_FLUXES;
 constexpr uint32_t M_END = ELMK_G_SNOW_HYDROLOGY | ELMK_G_SURFACE_FLUXES | ELMK_G_CONSERVATION;
-// (register caps: blocks per SM chosen by A/B runs on B200 at 2M columns - 10 / 5 / 6 were the fastest of 2..10)
+// (register caps: blocks per SM chosen by A/B runs on B200 at 2M columns - 10 / 8 / 6 were the fastest of 2..10;
+//  soil temperature at 8 only together with its block re-alignment points, 5 without)
 const Launch kFused[] = {
     ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo", 128, false),
     ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 10),
     ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes", 128, false),
-    ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 5),
+    ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 8),
     ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 6),
 };
 // development: alternative launch configurations of the radiative-transfer launch (ELMK_RAD_VARIANT=1..)

@@ -31,6 +31,7 @@ constexpr double TKICE = 2.290, TKWAT = 0.57, TKAIR = 0.023, THIN_SFCLAYER = 1.0
 constexpr double CNFAC = 0.5, CAPR = 0.34;
 } // namespace st
 
+template <bool REALIGN = false>
 ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double dtime, const int c)
 {
   using namespace st;
@@ -55,6 +56,7 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
   double thk[NLEVTOT], fact[NLEVTOT];
 #pragma unroll
   for (int i = 0; i < NLEVTOT; ++i) {
+    if (i % 5 == 0 && i > 0) ELMK_REALIGN(REALIGN);
     const double liq = C2(h2osoi_liq, i), ice = C2(h2osoi_ice, i), dz = C2(dz, i);
     double cv;
     if (i >= NLEVSNO) {
@@ -88,6 +90,7 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
     else fact[i] = dtime / cv;
     C2(fact, i) = fact[i];
   }
+  ELMK_REALIGN(REALIGN);
   // conductivity at the interfaces and the diffusive heat flux through them
   double tk[NLEVTOT], fn[NLEVTOT];
 #pragma unroll
@@ -130,6 +133,7 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
                              (C1(eflx_sh_snow) + C1(qflx_ev_snow) * htvp);
   const double dhsdT = -C1(cgrnd) - 4.0 * emg * STEBOL * cube(C1(t_grnd));
 
+  ELMK_REALIGN(REALIGN);
   // ---- pass 2: one row of the band system at a time (rows 0-4 snow, row 5 surface water, rows 6-20 soil;
   //      band k of row i multiplies unknown i + 2 - k), eliminated as soon as it is built (PDMA forward
   //      sweep).  Rows above the first active one leave A = B = Z = 0; with those zeros the general
@@ -140,6 +144,7 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
   const double fn_sfc = tk_sfc * (t[NLEVSNO] - t_sfc) / (0.5 * dz_sfc + z[NLEVSNO]);
 #pragma unroll
   for (int r = 0; r < N; ++r) {
+    if (r % 5 == 0 && r > 0) ELMK_REALIGN(REALIGN);
     double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, b4 = 0.0, rhs = 0.0;
     bool active = true;
     if (r < NLEVSNO) {
@@ -231,6 +236,7 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
       Z[r] = (rhs - Zm1 * b4 - Zm1 * Y2) * U2;
     }
   }
+  ELMK_REALIGN(REALIGN);
   // back substitution; the solution overwrites Z
   double sol[N];
   sol[N - 1] = Z[N - 1];
@@ -301,12 +307,14 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
   C1(qflx_h2osfc_ice) = q_sfc_ice;
   C1(eflx_h2osfc_snow) = e_sfc_snow;
 
+  ELMK_REALIGN(REALIGN);
   // ---- pass 3: phase change in snow and soil layers, one layer at a time; the water state of a layer is
   //      read only now (the solve does not need it) and written back at once ----
   double xmf = 0.0, q_snomelt = 0.0, q_snow_melt = 0.0, q_snofrz = 0.0;
   double t_new_top = 0.0, t_new_soil1 = 0.0;
 #pragma unroll
   for (int i = 0; i < NLEVTOT; ++i) {
+    if (i % 5 == 0 && i > 0) ELMK_REALIGN(REALIGN);
     if (i < top) {
       // rows above the snow pack are untouched (their melt flags stay stale, quirk 13), except the bottom
       // snow slot, which the surface-water phase change may have initialised (phase_change_impl.hh:79-83,123-125)
