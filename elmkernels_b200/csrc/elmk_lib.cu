@@ -61,40 +61,51 @@ constexpr size_t kStageBytes = 64u << 20; // device staging buffer for layout co
 // ------------------------------------------------------------------------------------------------
 // column kernels
 // ------------------------------------------------------------------------------------------------
-// kernels that run the soil-temperature group alone keep the threads of the padding columns (ncols..np, zero-filled,
-// never downloaded) alive, so that the block barriers inside that group's body are legal (ELMK_REALIGN)
-template <uint32_t MASK> constexpr bool kWholeBlocks = (MASK == ELMK_G_SOIL_TEMPERATURE);
+// launches whose blocks re-align their warps (instruction-cache sharing, see ELMK_REALIGN in elmk_common.h): soil
+// temperature alone (barriers inside its body) and the fused unsorted launches (barriers between their groups)
+template <uint32_t MASK> constexpr bool kWholeBlocks = (MASK == ELMK_G_SOIL_TEMPERATURE) || ((MASK & (MASK - 1u)) != 0 && !(MASK & ELMK_G_SOIL_TEMPERATURE));
 
+// `live`: the thread owns a real column.  With REALIGN the threads of a block meet again between the groups of a fused
+// launch (and, for soil temperature, inside the group's body), so threads without a column stay until the end.
 template <uint32_t MASK, bool REALIGN = false>
-__device__ __forceinline__ void run_groups(const Cols& S, const Tables& T, const StepArgs& A, const int c)
+__device__ __forceinline__ void run_groups(const Cols& S, const Tables& T, const StepArgs& A, const int c, const bool live = true)
 {
-  if (MASK & ELMK_G_FRAC_WET) column_frac_wet(S, T, c);
-  if (MASK & ELMK_G_ALBEDO) column_albedo(S, T, c);
-  if (MASK & ELMK_G_CANOPY_HYDROLOGY) column_canopy_hydrology(S, T, A.dtime, c);
-  if (MASK & ELMK_G_SURFACE_RADIATION) column_surface_radiation(S, T, c);
-  if (MASK & ELMK_G_CANOPY_TEMPERATURE) column_canopy_temperature(S, T, c);
-  if (MASK & ELMK_G_BAREGROUND_FLUXES) column_bareground_fluxes(S, T, c);
-  if (MASK & ELMK_G_CANOPY_FLUXES) column_canopy_fluxes(S, T, A, c);
-  if (MASK & ELMK_G_SOIL_TEMPERATURE) column_soil_temperature<REALIGN>(S, T, A.dtime, c);
-  if (MASK & ELMK_G_SNOW_HYDROLOGY) column_snow_hydrology(S, T, A.dtime, c);
-  if (MASK & ELMK_G_SURFACE_FLUXES) column_surface_fluxes(S, T, A.dtime, c);
-  if (MASK & ELMK_G_CONSERVATION) column_conservation(S, T, A.dtime, c);
+#define ELMK_GROUP(BIT, CALL)                                        \
+  if (MASK & (BIT)) {                                                \
+    if (live) { CALL; }                                              \
+    if (REALIGN && (MASK & ~(((BIT) << 1) - 1u))) __syncthreads();   \
+  }
+  ELMK_GROUP(ELMK_G_FRAC_WET, column_frac_wet(S, T, c))
+  ELMK_GROUP(ELMK_G_ALBEDO, column_albedo(S, T, c))
+  ELMK_GROUP(ELMK_G_CANOPY_HYDROLOGY, column_canopy_hydrology(S, T, A.dtime, c))
+  ELMK_GROUP(ELMK_G_SURFACE_RADIATION, column_surface_radiation(S, T, c))
+  ELMK_GROUP(ELMK_G_CANOPY_TEMPERATURE, column_canopy_temperature(S, T, c))
+  ELMK_GROUP(ELMK_G_BAREGROUND_FLUXES, column_bareground_fluxes(S, T, c))
+  ELMK_GROUP(ELMK_G_CANOPY_FLUXES, column_canopy_fluxes(S, T, A, c))
+  if (MASK & ELMK_G_SOIL_TEMPERATURE) {
+    // barriers inside the body: every thread runs it, the padding columns (ncols..np, zero-filled, never downloaded) included
+    if (REALIGN || live) column_soil_temperature<REALIGN>(S, T, A.dtime, c);
+  }
+  ELMK_GROUP(ELMK_G_SNOW_HYDROLOGY, column_snow_hydrology(S, T, A.dtime, c))
+  ELMK_GROUP(ELMK_G_SURFACE_FLUXES, column_surface_fluxes(S, T, A.dtime, c))
+  ELMK_GROUP(ELMK_G_CONSERVATION, column_conservation(S, T, A.dtime, c))
+#undef ELMK_GROUP
 }
 
 template <uint32_t MASK>
 __global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
 {
   const int c = blockIdx.x * kBlock + threadIdx.x;
-  if (kWholeBlocks<MASK> ? (c >= S.np) : (c >= S.ncols)) return;
-  run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c);
+  if (!kWholeBlocks<MASK> && c >= S.ncols) return;
+  run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c, c < S.ncols);
 }
 // same, with a floor on the resident blocks per SM (caps the registers per thread)
 template <uint32_t MASK, int MINBLOCKS>
 __global__ void __launch_bounds__(kBlock, MINBLOCKS) k_groups_occ(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
 {
   const int c = blockIdx.x * kBlock + threadIdx.x;
-  if (kWholeBlocks<MASK> ? (c >= S.np) : (c >= S.ncols)) return;
-  run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c);
+  if (!kWholeBlocks<MASK> && c >= S.ncols) return;
+  run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c, c < S.ncols);
 }
 
 // ---- work-class sorted variant ------------------------------------------------------------------
