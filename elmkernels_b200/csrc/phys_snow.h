@@ -634,8 +634,9 @@ ELMK_HD void column_snow_hydrology(const Cols& S, const Tables& T, const double 
 
   // -- launch 4: update_aerosol_mass_and_concen --
   const double q_snwcp_ice = C1(qflx_snwcp_ice);
-  double cnc[NMSS][NS];
   {
+    // (masses and concentrations are final here - snow_aging does not touch them - and go straight to memory:
+    //  thirty fewer doubles to carry through the last stage)
     const int snotop = NS - P.snl;
 #pragma unroll
     for (int sl = 0; sl < NS; ++sl) {
@@ -643,11 +644,15 @@ ELMK_HD void column_snow_hydrology(const Cols& S, const Tables& T, const double 
       const double scl = (sl == snotop && capsnow) ? (snowmass / (snowmass + q_snwcp_ice * dtime))
                                                    : ((sl < snotop) ? 0.0 : 1.0);
       const double inv = 1.0 / snowmass;
+      double m[NMSS];
 #pragma unroll
-      for (int a = 0; a < NMSS; ++a) {
-        P.mss[a][sl] *= scl;
-        cnc[a][sl] = P.mss[a][sl] * inv;
-      }
+      for (int a = 0; a < NMSS; ++a) m[a] = P.mss[a][sl] * scl;
+      C2(mss_bcphi, sl) = m[0]; C2(cnc_bcphi, sl) = m[0] * inv;
+      C2(mss_bcpho, sl) = m[1]; C2(cnc_bcpho, sl) = m[1] * inv;
+      C2(mss_dst1, sl) = m[2]; C2(cnc_dst1, sl) = m[2] * inv;
+      C2(mss_dst2, sl) = m[3]; C2(cnc_dst2, sl) = m[3] * inv;
+      C2(mss_dst3, sl) = m[4]; C2(cnc_dst3, sl) = m[4] * inv;
+      C2(mss_dst4, sl) = m[5]; C2(cnc_dst4, sl) = m[5] * inv;
     }
   }
 
@@ -673,12 +678,6 @@ ELMK_HD void column_snow_hydrology(const Cols& S, const Tables& T, const double 
     C2(zsoi, i) = P.z[i];
     C2(zisoi, i) = P.zi[i];
     C2(snw_rds, i) = P.rds[i];
-    C2(mss_bcphi, i) = P.mss[0][i]; C2(cnc_bcphi, i) = cnc[0][i];
-    C2(mss_bcpho, i) = P.mss[1][i]; C2(cnc_bcpho, i) = cnc[1][i];
-    C2(mss_dst1, i) = P.mss[2][i]; C2(cnc_dst1, i) = cnc[2][i];
-    C2(mss_dst2, i) = P.mss[3][i]; C2(cnc_dst2, i) = cnc[3][i];
-    C2(mss_dst3, i) = P.mss[4][i]; C2(cnc_dst3, i) = cnc[4][i];
-    C2(mss_dst4, i) = P.mss[5][i]; C2(cnc_dst4, i) = cnc[5][i];
   }
   C1(frac_sno_eff) = fse;
   C1(frac_sno) = frac_sno;
