@@ -903,7 +903,10 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
     c->plan = kFusedUnsorted;
     c->plan_len = sizeof(kFusedUnsorted) / sizeof(kFusedUnsorted[0]);
   }
-  if (c->plan == kFused && ncols >= (int64_t)kWideWindow * 296) {   // >= one block per resident slot of a B200 (148 SMs x 2)
+  const char* rw = std::getenv("ELMK_RAD_WINDOW");   // "wide" / "narrow": override for tests and A/B runs
+  const bool wide = rw ? (std::strcmp(rw, "wide") == 0)
+                       : (ncols >= (int64_t)kWideWindow * 296);   // >= one block per resident slot of a B200 (148 SMs x 2)
+  if (c->plan == kFused && wide) {
     c->plan_own.assign(kFused, kFused + c->plan_len);
     c->plan_own[0] = kRadWide;
   }

@@ -126,6 +126,23 @@ def test_split_and_fused_plans_agree(cuda_lib, params, monkeypatch):
     assert pair.b.launch_count < pair.a.launch_count
 
 
+def test_wide_sorting_window_gives_identical_bits(cuda_lib, params, monkeypatch):
+    """Large handles sort 4096-column windows in the radiative-transfer launch; the order in which a block visits its
+    columns must not change any result."""
+    cfg = ensemble.EnsembleConfig(ncols=9000, seed=17, soil_temp_spread=5.0)
+    monkeypatch.setenv("ELMK_RAD_WINDOW", "wide")
+    pair = parity.Pair(cuda_lib, cuda_lib, params, cfg)    # a: wide window
+    monkeypatch.setenv("ELMK_RAD_WINDOW", "narrow")
+    pair.b.close()
+    pair.b = cuda_lib.columns(cfg.ncols)                   # b: 1024-column windows
+    pair.b.set_tables(params)
+    pair.b.upload_state(pair.state0)
+    for _ in range(4):
+        pair.begin_step()
+        pair.run()
+    assert not pair.compare(0.0)
+
+
 def test_golden_vectors(cuda_lib, params):
     """The committed vectors produced by the reference itself (tests/golden/chain_64col.npz)."""
     z = np.load(os.path.join(ROOT, "tests", "golden", "chain_64col.npz"))
