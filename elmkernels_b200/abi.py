@@ -108,6 +108,8 @@ class Library:
             "elmk_exchange_commit": (C.c_int, [H]),
             "elmk_exchange_fetch": (C.c_int, [H, C.POINTER(C.c_void_p)]),
             "elmk_exchange_wait": (C.c_int, [H]),
+            "elmk_exchange_post_wait": (C.c_int, [H]),
+            "elmk_math_eval": (C.c_int, [H, C.c_int, C.c_int64, _PD, _PD, _PD]),
             "elmk_init_columns": (C.c_int, [H, _PD, _PD, _PD, C.c_double, _PD]),
             "elmk_atm_series": (C.c_int, [H, C.c_int, _PD, C.c_int]),
             "elmk_atm_forcing": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_int]),
@@ -167,6 +169,10 @@ class Exchange:
 
     def wait(self):
         self.cols._check(self.cols.lib.dll.elmk_exchange_wait(self._x), "elmk_exchange_wait")
+
+    def post_wait(self):
+        """Block until the oldest post has left its host buffers (they may then be refilled)."""
+        self.cols._check(self.cols.lib.dll.elmk_exchange_post_wait(self._x), "elmk_exchange_post_wait")
 
     def close(self):
         if self._x:
@@ -365,6 +371,21 @@ class Columns:
 
     def clear_errors(self):
         self._check(self.lib.dll.elmk_clear_errors(self._h), "elmk_clear_errors")
+
+    MATH = {"exp": 0, "log": 1, "log10": 2, "pow": 3, "atan": 4, "cos": 5, "tanh": 6, "erf": 7, "acos": 8, "div": 9}
+
+    def math_eval(self, fn: str, x: np.ndarray, y: Optional[np.ndarray] = None) -> np.ndarray:
+        """The library's own transcendental `fn` at x (and y), evaluated where the library computes."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        yp = None
+        if y is not None:
+            y = np.ascontiguousarray(y, dtype=np.float64)
+            assert y.shape == x.shape
+            yp = y.ctypes.data_as(_PD)
+        self._check(self.lib.dll.elmk_math_eval(self._h, self.MATH[fn], x.size, x.ctypes.data_as(_PD), yp,
+                                                out.ctypes.data_as(_PD)), "elmk_math_eval")
+        return out
 
     def diag_reduce(self) -> np.ndarray:
         out = np.zeros(24)

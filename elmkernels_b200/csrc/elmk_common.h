@@ -7,6 +7,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "elmk_libm.h"
+
 #if defined(__CUDACC__)
 #define ELMK_HD __host__ __device__ __forceinline__
 #define ELMK_HD_NOINLINE __host__ __device__ __noinline__
@@ -22,15 +24,40 @@
 // "no_instruction" stall, profiles/r1_baseline_raw.csv).  One shared copy per function keeps the loop
 // bodies cache-resident.
 namespace elmk {
+// On the device exp / log / log10 / pow / atan / cos / acos / tanh / erf are the restatements of glibc's routines in
+// elmk_libm.h: the same bits as the libm the reference calls (pinned by tests/test_libm_cpu.py), so that threshold tests downstream take the
+// reference's branch.  The host checker build (oracle/port) calls libm itself.
+#if defined(__CUDA_ARCH__)
+ELMK_HD_NOINLINE double m_exp(double x) { return lm::g_exp(x); }
+ELMK_HD_NOINLINE double m_log(double x) { return lm::g_log(x); }
+ELMK_HD_NOINLINE double m_log10(double x) { return lm::g_log10(x); }
+ELMK_HD_NOINLINE double m_pow(double x, double y) { return lm::g_pow(x, y); }
+ELMK_HD_NOINLINE double m_atan(double x) { return lm::g_atan(x); }
+ELMK_HD_NOINLINE double m_cos(double x) { return lm::g_cos(x); }
+ELMK_HD_NOINLINE double m_acos(double x) { return lm::g_acos(x); }
+ELMK_HD_NOINLINE double m_tanh(double x) { return lm::g_tanh(x); }
+ELMK_HD_NOINLINE double m_erf(double x) { return lm::g_erf(x); }
+#else
 ELMK_HD_NOINLINE double m_exp(double x) { return exp(x); }
 ELMK_HD_NOINLINE double m_log(double x) { return log(x); }
 ELMK_HD_NOINLINE double m_log10(double x) { return log10(x); }
 ELMK_HD_NOINLINE double m_pow(double x, double y) { return pow(x, y); }
 ELMK_HD_NOINLINE double m_atan(double x) { return atan(x); }
+ELMK_HD_NOINLINE double m_cos(double x) { return cos(x); }
 ELMK_HD_NOINLINE double m_acos(double x) { return acos(x); }
 ELMK_HD_NOINLINE double m_tanh(double x) { return tanh(x); }
 ELMK_HD_NOINLINE double m_erf(double x) { return erf(x); }
-ELMK_HD_NOINLINE double m_cos(double x) { return cos(x); }
+#endif
+// the same, in line (for the called functions named *_inl, whose independent transcendentals ptxas interleaves)
+#if defined(__CUDA_ARCH__)
+ELMK_HD double i_exp(double x) { return lm::g_exp(x); }
+ELMK_HD double i_log(double x) { return lm::g_log(x); }
+ELMK_HD double i_atan(double x) { return lm::g_atan(x); }
+#else
+ELMK_HD double i_exp(double x) { return exp(x); }
+ELMK_HD double i_log(double x) { return log(x); }
+ELMK_HD double i_atan(double x) { return atan(x); }
+#endif
 
 // IEEE double division with a short cut for a zero numerator.  ptxas expands every `a / b` inline into a
 // Newton sequence whose fast path excludes zero and subnormal numerators; those go through a ~70-instruction
@@ -134,7 +161,7 @@ constexpr uint32_t ERR_DIVIDE_RADIUS = 1u << 11;
 // general pow; the host checker build keeps the reference's pow call.
 ELMK_HD double pow_cbase(const double base, const double ln_hi, const double ln_lo, const double y)
 {
-#ifdef ELMK_EXACT_POW
+#if defined(ELMK_EXACT_POW) || !defined(ELMK_FAST_POW)
   (void)ln_hi; (void)ln_lo;
   return m_pow(base, y);
 #else
@@ -173,7 +200,7 @@ ELMK_HD int imax(int a, int b) { return (a < b) ? b : a; }
 // the libm call so that the checker can be compared bit-for-bit with the reference; the CUDA
 // build uses multiplications (3 DMUL instead of a ~100-instruction pow), inside the 1e-12 bar.
 ELMK_HD double sq(double x) { return x * x; }
-#ifdef ELMK_EXACT_POW
+#if defined(ELMK_EXACT_POW) || !defined(ELMK_FAST_POW)
 ELMK_HD double cube(double x) { return m_pow(x, 3.0); }
 ELMK_HD double pow4(double x) { return m_pow(x, 4.0); }
 #else

@@ -368,6 +368,29 @@ __global__ void __launch_bounds__(kBlock) k_phenology(const Cols S, const PhenSe
   column_phenology(S, P, m, wt1, wt2, c);
 }
 
+// elmk_math_eval: the library's transcendentals at caller-given arguments (parity diagnostic)
+__global__ void __launch_bounds__(256) k_math_eval(const int fn, const long long n, const double* __restrict__ x,
+                                                   const double* __restrict__ y, double* __restrict__ out)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = x[i];
+  double r;
+  switch (fn) {
+    case ELMK_MATH_EXP: r = m_exp(a); break;
+    case ELMK_MATH_LOG: r = m_log(a); break;
+    case ELMK_MATH_LOG10: r = m_log10(a); break;
+    case ELMK_MATH_POW: r = m_pow(a, y[i]); break;
+    case ELMK_MATH_ATAN: r = m_atan(a); break;
+    case ELMK_MATH_COS: r = m_cos(a); break;
+    case ELMK_MATH_TANH: r = m_tanh(a); break;
+    case ELMK_MATH_ERF: r = m_erf(a); break;
+    case ELMK_MATH_ACOS: r = m_acos(a); break;
+    default: r = a / y[i]; break;
+  }
+  out[i] = r;
+}
+
 typedef void (*GroupKernel)(const Cols, const Tables*, const StepArgs);
 struct Launch { uint32_t mask; GroupKernel fn; const char* name; int cols_per_block; int block; };
 #define ELMK_LAUNCH(M, NAME) {(M), k_groups<(M)>, NAME, kBlock, kBlock}
@@ -797,7 +820,7 @@ struct Exchange {
   cudaEvent_t in_consumed[2] = {nullptr, nullptr};  // commit has read the slot            (recorded on the step stream)
   cudaEvent_t out_ready[2] = {nullptr, nullptr};    // snapshot written into the slot      (recorded on the step stream)
   cudaEvent_t out_done[2] = {nullptr, nullptr};     // D2H of the slot finished            (recorded on s_out)
-  int64_t posts = 0, commits = 0, fetches = 0, waits = 0;
+  int64_t posts = 0, commits = 0, fetches = 0, waits = 0, post_waits = 0;
 };
 Exchange* xch(elmk_exchange x) { return reinterpret_cast<Exchange*>(x); }
 
@@ -1180,6 +1203,40 @@ int elmk_exchange_wait(elmk_exchange xh) {
   CU(cudaEventSynchronize(x->out_done[slot]));
   x->waits += 1;
   return ELMK_OK;
+}
+
+int elmk_exchange_post_wait(elmk_exchange xh) {
+  Exchange* x = xch(xh);
+  if (!x) return ELMK_EINVAL;
+  Ctx* c = x->c;
+  if (int rc = bind(c)) return rc;
+  if (x->post_waits < x->posts - 2) x->post_waits = x->posts - 2;   // older slots were reused: their copies are done
+  if (x->post_waits >= x->posts) return ELMK_OK;                     // nothing outstanding
+  const int slot = (int)(x->post_waits & 1);
+  CU(cudaEventSynchronize(x->in_ready[slot]));
+  x->post_waits += 1;
+  return ELMK_OK;
+}
+
+int elmk_math_eval(elmk_handle h, int fn, int64_t n, const double* x, const double* y, double* out) {
+  Ctx* c = ctx(h);
+  if (!c || !x || !out || fn < 0 || fn >= ELMK_MATH_COUNT || n < 0) return ELMK_EINVAL;
+  if ((fn == ELMK_MATH_POW || fn == ELMK_MATH_DIV) && !y) return ELMK_EINVAL;
+  if (n == 0) return ELMK_OK;
+  if (int rc = bind(c)) return rc;
+  double* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(double) * 3 * (size_t)n));
+  cudaError_t e = cudaMemcpyAsync(d, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess && y) e = cudaMemcpyAsync(d + n, y, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    k_math_eval<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(fn, n, d, d + n, d + 2 * n);
+    c->launches += 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  return e == cudaSuccess ? ELMK_OK : fail(c, e, "elmk_math_eval");
 }
 
 // ---- per-step producers of the forcing and phenology inputs ----

@@ -47,12 +47,12 @@ ELMK_HD_NOINLINE LayerDirect snicar_layer_direct_inl(const double ts, const doub
   LayerDirect o;
   const double lm = sqrt(3.0 * (1.0 - ws) * (1.0 - ws * gs));
   const double ue = 1.5 * (1.0 - ws * gs) / lm;
-  const double extins = dmax(exp_min, exp(-lm * ts));
+  const double extins = dmax(exp_min, i_exp(-lm * ts));
   const double ne = ((ue + 1.0) * (ue + 1.0) / extins) - ((ue - 1.0) * (ue - 1.0) * extins);
   o.lm = lm;
   o.rdif_a = (sq(ue) - 1.0) * (1.0 / extins - extins) / ne;
   o.tdif_a = 4.0 * ue / ne;
-  o.trnlay = dmax(exp_min, exp(-ts / mu_not));
+  o.trnlay = dmax(exp_min, i_exp(-ts / mu_not));
   const double alp = 0.75 * ws * mu_not * ((1.0 + gs * (1.0 - ws)) / (1.0 - lm * lm * mu_not * mu_not));
   const double gam = 0.5 * ws * ((1.0 + 3.0 * gs * (1.0 - ws) * mu_not * mu_not) / (1.0 - lm * lm * mu_not * mu_not));
   const double apg = alp + gam;
@@ -72,7 +72,7 @@ ELMK_HD_NOINLINE GaussPair snicar_gauss_pair_inl(const double ts, const double w
   GaussPair g;
   {
     const double mu = mu0;
-    const double trn = dmax(exp_min, exp(-ts / mu));
+    const double trn = dmax(exp_min, i_exp(-ts / mu));
     const double alp = 0.75 * ws * mu * ((1.0 + gs * (1.0 - ws)) / (1.0 - lm * lm * mu * mu));
     const double gam = 0.5 * ws * ((1.0 + 3.0 * gs * (1.0 - ws) * mu * mu) / (1.0 - lm * lm * mu * mu));
     const double apg = alp + gam;
@@ -82,7 +82,7 @@ ELMK_HD_NOINLINE GaussPair snicar_gauss_pair_inl(const double ts, const double w
   }
   {
     const double mu = mu1;
-    const double trn = dmax(exp_min, exp(-ts / mu));
+    const double trn = dmax(exp_min, i_exp(-ts / mu));
     const double alp = 0.75 * ws * mu * ((1.0 + gs * (1.0 - ws)) / (1.0 - lm * lm * mu * mu));
     const double gam = 0.5 * ws * ((1.0 + 3.0 * gs * (1.0 - ws) * mu * mu) / (1.0 - lm * lm * mu * mu));
     const double apg = alp + gam;
@@ -148,7 +148,7 @@ ELMK_HD_NOINLINE void snicar_solve(const Cols& S, const Tables& T, const int c, 
   const double gauspt[8] = {0.9894009, 0.9445750, 0.8656312, 0.7554044, 0.6178762, 0.4580168, 0.2816036, 0.0950125};
   const double gauswt[8] = {0.0271525, 0.0622535, 0.0951585, 0.1246290, 0.1495960, 0.1691565, 0.1826034, 0.1894506};
   constexpr double puny = 1.0e-11;
-  constexpr double exp_min = 0x1.7cd79b5647c9bp-15;   // exp(-10), the reference's constant-folded value (:357)
+  constexpr double exp_min = 0x1.7cd79b5647c9bp-15;   // i_exp(-10), the reference's constant-folded value (:357)
   constexpr double trmin = 0.001;
 
   double albout_lcl[NBND_SNW];

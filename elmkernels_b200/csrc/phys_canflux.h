@@ -311,7 +311,7 @@ ELMK_HD PsnColumn psn_column(const PsnPft& P, const double t10, const double pbo
 // Leaf-temperature response factors of one stability pass: the sunlit and the shaded call see the same leaf
 // temperature, so the (up to 11) exponentials are evaluated once per pass instead of twice.
 struct PsnPass {
-  double lmr_a, lmr_b;                       // C3: ft, fth;  C4: 2^((T-25)/10), 1 + exp(1.3 (T-55))
+  double lmr_a, lmr_b;                       // C3: ft, fth;  C4: 2^((T-25)/10), 1 + i_exp(1.3 (T-55))
   double vc_a, vc_b, jm_a, jm_b, tp_a, tp_b; // ft, fth of vcmax, jmax, tpu (daytime only)
   double p2, c4d1, c4d2;                     // 2^((T-25)/10) and the two C4 vcmax inhibition denominators
   double kc, ko, cp;                         // Michaelis-Menten constants and CO2 compensation point
@@ -322,11 +322,11 @@ struct PsnPass {
 // independent - called, they would run one after the other (elmk_common.h, m_div2)
 ELMK_HD double psn_ft_i(const double tl, const double ha)
 {
-  return exp(ha / (RGAS * 1.0e-3 * (TFRZ + 25.0)) * (1.0 - (TFRZ + 25.0) / tl));
+  return i_exp(ha / (RGAS * 1.0e-3 * (TFRZ + 25.0)) * (1.0 - (TFRZ + 25.0) / tl));
 }
 ELMK_HD double psn_fth_i(const double tl, const double hd, const double se, const double scale)
 {
-  return scale / (1.0 + exp((-hd + se * tl) / (RGAS * 1.0e-3 * tl)));
+  return scale / (1.0 + i_exp((-hd + se * tl) / (RGAS * 1.0e-3 * tl)));
 }
 ELMK_HD PsnPass psn_pass(const PsnPft& P, const PsnColumn& C, const double t_veg, const bool day)
 {
@@ -339,7 +339,7 @@ ELMK_HD PsnPass psn_pass(const PsnPft& P, const PsnColumn& C, const double t_veg
     T.lmr_b = psn_fth_i(t_veg, P.lmrhd, P.lmrse, C.lmrc);
   } else {
     T.lmr_a = T.p2;
-    T.lmr_b = (1.0 + exp(1.3 * (t_veg - (TFRZ + 55.0))));
+    T.lmr_b = (1.0 + i_exp(1.3 * (t_veg - (TFRZ + 55.0))));
   }
   if (day) {
     T.vc_a = psn_ft_i(t_veg, P.vcmaxha);
@@ -349,8 +349,8 @@ ELMK_HD PsnPass psn_pass(const PsnPft& P, const PsnColumn& C, const double t_veg
     T.tp_a = psn_ft_i(t_veg, P.tpuha);
     T.tp_b = psn_fth_i(t_veg, P.tpuhd, C.tpuse, C.tpuc);
     if (!C.c3) {
-      T.c4d1 = (1.0 + exp(0.2 * ((TFRZ + 15.0) - t_veg)));
-      T.c4d2 = (1.0 + exp(0.3 * (t_veg - (TFRZ + 40.0))));
+      T.c4d1 = (1.0 + i_exp(0.2 * ((TFRZ + 15.0) - t_veg)));
+      T.c4d2 = (1.0 + i_exp(0.3 * (t_veg - (TFRZ + 40.0))));
     }
   }
   T.kc = C.kc25 * psn_ft_i(t_veg, P.kcha);

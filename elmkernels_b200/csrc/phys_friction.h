@@ -129,12 +129,12 @@ ELMK_HD double mo_psi_m_i(const double zeta)
 {
   const double chik2 = sqrt(1.0 - 16.0 * zeta);
   const double chik = sqrt(chik2);
-  return 2.0 * log((1.0 + chik) * 0.5) + log((1.0 + chik2) * 0.5) - 2.0 * atan(chik) + PI * 0.5;
+  return 2.0 * i_log((1.0 + chik) * 0.5) + i_log((1.0 + chik2) * 0.5) - 2.0 * i_atan(chik) + PI * 0.5;
 }
 ELMK_HD double mo_psi_h_i(const double zeta)
 {
   const double chik2 = sqrt(1.0 - 16.0 * zeta);
-  return 2.0 * log((1.0 + chik2) * 0.5);
+  return 2.0 * i_log((1.0 + chik2) * 0.5);
 }
 ELMK_HD_NOINLINE MoPair mo_pair_inl(const double zldis_u, const double zldis_s, const double um, const double obu,
                                     const double z0m, const double z0s)
@@ -152,8 +152,8 @@ ELMK_HD_NOINLINE MoPair mo_pair_inl(const double zldis_u, const double zldis_s, 
   const bool far_s = un_s ? (zeta_s < (-zetat)) : !(zeta_s <= 1.0);
   const double num_u = far_u ? (un_u ? -zetam * obu : obu) : zldis_u;
   const double num_s = far_s ? (un_s ? -zetat * obu : obu) : zldis_s;
-  const double lead_u = log(num_u / z0m);
-  const double lead_s = log(num_s / z0s);
+  const double lead_u = i_log(num_u / z0m);
+  const double lead_s = i_log(num_s / z0s);
   double den_u, den_s;
   if (un_u) {
     const double p1u = mo_psi_m_i(far_u ? -zetam : zeta_u);
@@ -167,9 +167,9 @@ ELMK_HD_NOINLINE MoPair mo_pair_inl(const double zldis_u, const double zldis_s, 
   } else {
     const double tu = 5.0 * z0m / obu;
     const double ts = 5.0 * z0s / obu;
-    if (far_u) den_u = lead_u + 5.0 - tu + (5.0 * log(zeta_u) + zeta_u - 1.0);
+    if (far_u) den_u = lead_u + 5.0 - tu + (5.0 * i_log(zeta_u) + zeta_u - 1.0);
     else den_u = lead_u + 5.0 * zeta_u - tu;
-    if (far_s) den_s = lead_s + 5.0 - ts + (5.0 * log(zeta_s) + zeta_s - 1.0);
+    if (far_s) den_s = lead_s + 5.0 - ts + (5.0 * i_log(zeta_s) + zeta_s - 1.0);
     else den_s = lead_s + 5.0 * zeta_s - ts;
   }
   MoPair r;

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ELMK_ABI_VERSION 4
+#define ELMK_ABI_VERSION 5
 
 /* ---- dimensions (reference src/data/elm_constants.h:84-98) ---- */
 #define ELMK_NLEVSNO 5
@@ -168,8 +168,16 @@ int elmk_download_many(elmk_handle h, int nfields, const int* fields, void* cons
  *        elmk_exchange_fetch(x, out_hosts)  snapshot the output fields (ordered after everything issued so far)
  *                                           and start their asynchronous copy to out_hosts;
  *        elmk_exchange_wait(x)              block until the oldest unfinished fetch has arrived on the host.
+ *        elmk_exchange_post_wait(x)         block until the oldest post whose copy may still be reading its host
+ *                                           buffers has left the host (the buffers may then be refilled).
  *      At most two posts and two fetches can be in flight.  Host buffers should be pinned
- *      (cudaHostAlloc / cudaHostRegister); pageable memory works but does not overlap. ---- */
+ *      (cudaHostAlloc / cudaHostRegister); pageable memory works but does not overlap.
+ *      LIFETIME OF HOST BUFFERS: with pinned memory every copy of this interface is asynchronous.  The buffers given
+ *      to elmk_exchange_post must stay untouched until elmk_exchange_post_wait has returned for that post (or
+ *      elmk_sync after the matching commit); those given to elmk_upload / elmk_upload_many / elmk_atm_series /
+ *      elmk_phen_series until elmk_sync (or any blocking call: elmk_download*, elmk_errors, elmk_diag_reduce);
+ *      elmk_set_tables and elmk_init_columns block before they return.  Pageable host memory is consumed before
+ *      the call returns (the driver stages it). ---- */
 typedef struct elmk_exchange_s* elmk_exchange;
 int elmk_exchange_create(elmk_handle h, int n_in, const int* in_fields, int n_out, const int* out_fields,
                          elmk_exchange* out);
@@ -178,6 +186,7 @@ int elmk_exchange_post(elmk_exchange x, const void* const* in_hosts);
 int elmk_exchange_commit(elmk_exchange x);
 int elmk_exchange_fetch(elmk_exchange x, void* const* out_hosts);
 int elmk_exchange_wait(elmk_exchange x);
+int elmk_exchange_post_wait(elmk_exchange x);
 
 /* ---- one-time cold-start initialisation of every column: the per-column lambda of initialize_kokkos_elm
  *      (driver/kokkos/initialize_elm_kokkos.cc:374-431) - psn_pft from vtype, init_topo_slope, init_melt_factor,
@@ -256,6 +265,23 @@ const char* elmk_error_text(uint32_t bit); /* the reference's message for one er
  *      Counterpart of ELMKokkos::min_max_sum (src/utils/kokkos_utils.hh:13-58); the cross-rank
  *      reduction of the 24 doubles is done by the caller (NCCL all-reduce in the Python host). ---- */
 int elmk_diag_reduce(elmk_handle h, double out[24]);
+
+/* ---- the library's transcendental functions, evaluated where the library computes (the product: on the device):
+ *      out[i] = fn(x[i]) or fn(x[i], y[i]).  exp, log, log10, pow, atan, cos, tanh, erf and acos return the bits of
+ *      the libm the reference is built against (csrc/elmk_libm.h); this entry point exists so that a parity test
+ *      can check that on the device itself.  y may be NULL for one-argument functions. ---- */
+#define ELMK_MATH_EXP 0
+#define ELMK_MATH_LOG 1
+#define ELMK_MATH_LOG10 2
+#define ELMK_MATH_POW 3
+#define ELMK_MATH_ATAN 4
+#define ELMK_MATH_COS 5
+#define ELMK_MATH_TANH 6
+#define ELMK_MATH_ERF 7
+#define ELMK_MATH_ACOS 8
+#define ELMK_MATH_DIV 9 /* x / y through the library's division */
+#define ELMK_MATH_COUNT 10
+int elmk_math_eval(elmk_handle h, int fn, int64_t n, const double* x, const double* y, double* out);
 
 /* raw device pointer + level stride of a field (for zero-copy interop with torch tensors) */
 int elmk_device_ptr(elmk_handle h, int field, void** ptr, int64_t* level_stride);

@@ -58,3 +58,27 @@ int elmk_exchange_fetch(elmk_exchange xh, void* const* out_hosts) {
   return ELMK_OK;
 }
 int elmk_exchange_wait(elmk_exchange) { return ELMK_OK; }
+int elmk_exchange_post_wait(elmk_exchange) { return ELMK_OK; }   // posts copy synchronously here
+
+// elmk_math_eval for the CPU checkers: the host's libm, i.e. what the reference itself calls
+#include <cmath>
+int elmk_math_eval(elmk_handle h, int fn, int64_t n, const double* x, const double* y, double* out) {
+  if (!h || !x || !out || fn < 0 || fn >= ELMK_MATH_COUNT || n < 0) return ELMK_EINVAL;
+  if ((fn == ELMK_MATH_POW || fn == ELMK_MATH_DIV) && !y) return ELMK_EINVAL;
+  for (int64_t i = 0; i < n; ++i) {
+    volatile double a = x[i];
+    switch (fn) {
+      case ELMK_MATH_EXP: out[i] = std::exp(a); break;
+      case ELMK_MATH_LOG: out[i] = std::log(a); break;
+      case ELMK_MATH_LOG10: out[i] = std::log10(a); break;
+      case ELMK_MATH_POW: { volatile double b = y[i]; out[i] = std::pow(a, b); } break;
+      case ELMK_MATH_ATAN: out[i] = std::atan(a); break;
+      case ELMK_MATH_COS: out[i] = std::cos(a); break;
+      case ELMK_MATH_TANH: out[i] = std::tanh(a); break;
+      case ELMK_MATH_ERF: out[i] = std::erf(a); break;
+      case ELMK_MATH_ACOS: out[i] = std::acos(a); break;
+      default: { volatile double b = y[i]; out[i] = a / b; } break;
+    }
+  }
+  return ELMK_OK;
+}

@@ -34,13 +34,15 @@ def replay(lib, params):
             cols.upload(name, a.reshape(n) if nl == 1 else a)
     cols.step(dtime=1800.0, groups=abi.G_CANOPY_HYDROLOGY)
     cols.step(dtime=1800.0, groups=abi.G_FRAC_WET)
-    worst = {}
+    worst, got_all = {}, {}
     for v in COMPARED:
         ref = z["out_" + v]
         got = cols.download(RENAME.get(v, v)).astype(np.float64).reshape(ref.shape)
+        got_all[v] = got
         d = np.abs(got - ref)
         s = np.maximum(np.abs(ref), 1e-300)
         worst[v] = float(np.max(np.where(d == 0, 0.0, d / s)))
+    replay.last = got_all   # the replayed values themselves, for library-against-library comparisons
     return worst
 
 
@@ -74,12 +76,14 @@ def replay_canopy_fluxes(lib, params):
     cols.fill("veg_active", 1)
     cols.step(dtime=1800.0, dayl=float(z["in_dayl"][0, 0]), max_dayl=float(z["in_max_dayl"][0, 0]), groups=abi.G_CANOPY_FLUXES)
     assert cols.errors() == (0, -1)
-    worst = {}
+    worst, got_all = {}, {}
     for v in CANFLUX_COMPARED:
         ref = z["out_" + v][night]
         got = cols.download(v).astype(np.float64).reshape(ref.shape)
+        got_all[v] = got
         d = np.abs(got - ref)
         s = np.maximum(np.abs(ref), 1e-300)
         # canopy water is ~1e-19..1e-6 kg/m2 in these records: differences below 1e-15 kg/m2 are rounding residue
         worst[v] = float(np.max(np.where(d <= 1e-15, 0.0, d / s)))
+    replay_canopy_fluxes.last = got_all
     return n, worst

@@ -15,5 +15,5 @@ def test_cuda_forcing_and_phenology_match_the_reference(cuda_lib, checker, param
     a, b = F.run(checker, params, n, rh), F.run(cuda_lib, params, n, rh)
     for sa, sb in zip(a, b):
         for k in sa:
-            bad = parity.mismatch(sa[k], sb[k], parity.RTOL_CLOSED)
+            bad = parity.mismatch(sa[k], sb[k])
             assert not bad.any(), f"{k}: {int(bad.sum())} elements differ, e.g. {sa[k][bad][:3]} vs {sb[k][bad][:3]}"
