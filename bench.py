@@ -292,7 +292,7 @@ def main():
     # ---- timed region: K steps, forcing resident in HBM ----
     sampler = ClockSampler(local)
     sampler.start()
-    cols.timing(True)
+    cols.timing(2 if os.environ.get("ELMK_TIMING_DETAIL") else True)
     l0 = cols.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

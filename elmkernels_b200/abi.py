@@ -95,6 +95,7 @@ class Library:
             "elmk_init_timestep": (C.c_int, [H, C.c_int]),
             "elmk_step": (C.c_int, [H, C.c_double, C.c_double, C.c_double, C.c_uint32]),
             "elmk_sync": (C.c_int, [H]),
+            "elmk_set_plan": (C.c_int, [H, C.c_int]),
             "elmk_launch_count": (C.c_int64, [H]),
             "elmk_errors": (C.c_int, [H, C.POINTER(C.c_uint32), C.POINTER(C.c_int64)]),
             "elmk_clear_errors": (C.c_int, [H]),
@@ -357,6 +358,10 @@ class Columns:
     def step(self, dtime: float = 1800.0, dayl: float = 50000.0, max_dayl: float = 86400.0, groups: int = G_ALL):
         self._check(self.lib.dll.elmk_step(self._h, dtime, dayl, max_dayl, groups), "elmk_step")
 
+    def set_plan(self, plan: str):
+        """'fused' (default, production) or 'split' (one launch per kernel group, one thread per column)."""
+        self._check(self.lib.dll.elmk_set_plan(self._h, {"fused": 0, "split": 1}[plan]), "elmk_set_plan")
+
     def sync(self):
         self._check(self.lib.dll.elmk_sync(self._h), "elmk_sync")
 
@@ -398,7 +403,8 @@ class Columns:
         self._check(self.lib.dll.elmk_stream(self._h, C.byref(p)), "elmk_stream")
         return p.value or 0
 
-    def timing(self, on: bool):
+    def timing(self, on):
+        """False / True / 2 (also the sub-launches of the composite launches)."""
         self._check(self.lib.dll.elmk_timing_enable(self._h, int(on)), "elmk_timing_enable")
 
     def timing_read(self):

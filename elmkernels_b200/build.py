@@ -69,11 +69,15 @@ def pipeline(cmd, keep: pathlib.Path):
     return "\n".join(script) + "\n"
 
 
-def build(force: bool = False, verbose: bool = False, out: pathlib.Path | None = None) -> pathlib.Path:
-    if out is None and not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, out: pathlib.Path | None = None, defines=()) -> pathlib.Path:
+    """defines: extra -D macros.  ELMK_DEV_VARIANTS compiles the development switches (register caps selected by
+    environment variables for A/B runs) - never into the product library: use --dev, which writes
+    elmkernels_b200/_variants/libelmk_b200_dev.so."""
+    if out is None and not force and not defines and up_to_date():
         return LIB
     out = out or LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(out), str(CSRC / "elmk_lib.cu")]
+    cmd = ([NVCC] + FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+           ["-o", str(out), str(CSRC / "elmk_lib.cu")])
     with tempfile.TemporaryDirectory(prefix="elmk_build_") as keep:
         script = pipeline(cmd, pathlib.Path(keep))
         r = subprocess.run(["bash", "-c", script], capture_output=True, text=True, cwd=str(HERE.parent))
@@ -86,4 +90,10 @@ def build(force: bool = False, verbose: bool = False, out: pathlib.Path | None =
 
 if __name__ == "__main__":
     _out = [a[6:] for a in sys.argv if a.startswith("--out=")]
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=pathlib.Path(_out[0]) if _out else None))
+    _defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    if "--dev" in sys.argv:
+        (HERE / "_variants").mkdir(exist_ok=True)
+        _out = _out or [str(HERE / "_variants" / "libelmk_b200_dev.so")]
+        _defs.append("ELMK_DEV_VARIANTS")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=pathlib.Path(_out[0]) if _out else None,
+                defines=_defs))

@@ -49,7 +49,11 @@ ELMK_HD_NOINLINE double m_tanh(double x) { return tanh(x); }
 ELMK_HD_NOINLINE double m_erf(double x) { return erf(x); }
 #endif
 // the same, in line (for the called functions named *_inl, whose independent transcendentals ptxas interleaves)
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(ELMK_INLINE_LIBM_CALLED)   // experiment: one shared copy after all
+ELMK_HD double i_exp(double x) { return m_exp(x); }
+ELMK_HD double i_log(double x) { return m_log(x); }
+ELMK_HD double i_atan(double x) { return m_atan(x); }
+#elif defined(__CUDA_ARCH__)
 ELMK_HD double i_exp(double x) { return lm::g_exp(x); }
 ELMK_HD double i_log(double x) { return lm::g_log(x); }
 ELMK_HD double i_atan(double x) { return lm::g_atan(x); }
@@ -156,26 +160,20 @@ constexpr uint32_t ERR_NEG_STOMATAL = 1u << 9;
 constexpr uint32_t ERR_SNOWAGE_DR = 1u << 10;
 constexpr uint32_t ERR_DIVIDE_RADIUS = 1u << 11;
 
-// base^y for a constant base whose natural logarithm is given as a double-double (hi + lo): exp of the
-// exactly split product.  Two roundings (exp <= 1 ulp, final multiply-add) instead of the ~350-instruction
-// general pow; the host checker build keeps the reference's pow call.
-ELMK_HD double pow_cbase(const double base, const double ln_hi, const double ln_lo, const double y)
+// base^y for a constant base: pow with its logarithm half folded (elmk_libm.h, g_pow_cbase) - the value is pow's own.
+// The host checker build keeps the reference's pow call.
+ELMK_HD double pow_cbase(const double base, const double lhi, const double llo, const double y)
 {
-#if defined(ELMK_EXACT_POW) || !defined(ELMK_FAST_POW)
-  (void)ln_hi; (void)ln_lo;
-  return m_pow(base, y);
+#if defined(__CUDA_ARCH__)
+  return lm::g_pow_cbase(base, lhi, llo, y);
 #else
-  (void)base;
-  const double hi = y * ln_hi;
-  const double lo = fma(y, ln_hi, -hi) + y * ln_lo;
-  const double e = m_exp(hi);
-  return fma(e, lo, e);
+  (void)lhi; (void)llo;
+  return m_pow(base, y);
 #endif
 }
-// ln(0.57), ln(2.29), ln(2) of the double constants, to double-double precision
-#define ELMK_LN_TKWAT -0x1.1fce0d03dd5e6p-1, 0x1.a4ee550808e41p-57
-#define ELMK_LN_TKICE 0x1.a837f19ef9d69p-1, 0x1.2e2416a47afa1p-55
-#define ELMK_LN_2 0x1.62e42fefa39efp-1, 0x1.abc9e3b39803fp-56
+#define ELMK_LN_TKWAT ELMK_POWLOG_0_57
+#define ELMK_LN_TKICE ELMK_POWLOG_2_29
+#define ELMK_LN_2 ELMK_POWLOG_2_0
 
 // Re-alignment point for the warps of a block inside a long straight-line kernel body (device only, and only in the
 // instantiation whose launch keeps every thread of the block alive to the end): the soil-temperature body is ~270 KB

@@ -67,6 +67,10 @@ template <uint32_t MASK> constexpr bool kWholeBlocks = (MASK == ELMK_G_SOIL_TEMP
 
 // `live`: the thread owns a real column.  With REALIGN the threads of a block meet again between the groups of a fused
 // launch (and, for soil temperature, inside the group's body), so threads without a column stay until the end.
+// internal launch-mask bit (never part of the public group mask): the albedo group for columns whose SNICAR results the
+// SNICAR kernel has already stored (k_snicar below)
+constexpr uint32_t G_ALBEDO_REST = 1u << 20;
+
 template <uint32_t MASK, bool REALIGN = false>
 __device__ __forceinline__ void run_groups(const Cols& S, const Tables& T, const StepArgs& A, const int c, const bool live = true)
 {
@@ -76,7 +80,8 @@ __device__ __forceinline__ void run_groups(const Cols& S, const Tables& T, const
     if (REALIGN && (MASK & ~(((BIT) << 1) - 1u))) __syncthreads();   \
   }
   ELMK_GROUP(ELMK_G_FRAC_WET, column_frac_wet(S, T, c))
-  ELMK_GROUP(ELMK_G_ALBEDO, column_albedo(S, T, c))
+  ELMK_GROUP(ELMK_G_ALBEDO, column_albedo<false>(S, T, c))
+  ELMK_GROUP(G_ALBEDO_REST, column_albedo<true>(S, T, c))
   ELMK_GROUP(ELMK_G_CANOPY_HYDROLOGY, column_canopy_hydrology(S, T, A.dtime, c))
   ELMK_GROUP(ELMK_G_SURFACE_RADIATION, column_surface_radiation(S, T, c))
   ELMK_GROUP(ELMK_G_CANOPY_TEMPERATURE, column_canopy_temperature(S, T, c))
@@ -108,91 +113,146 @@ __global__ void __launch_bounds__(kBlock, MINBLOCKS) k_groups_occ(const Cols S, 
   run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c, c < S.ncols);
 }
 
-// ---- work-class sorted variant ------------------------------------------------------------------
-// The heavy groups branch on column type: CanopyFluxes does nothing for bare columns, skips the
-// photosynthesis root-find at night; SNICAR runs only for sunlit snow and costs in proportion to the number
-// of snow layers.  With one thread per consecutive column, a warp holds every type and executes the union of
-// their paths (ncu: 5-6 active lanes per instruction, profiles/r1_baseline_raw.csv).  Here a block owns a
-// window of kWindow consecutive columns, orders them by a cheap work-class key in shared memory (counting
-// sort, heaviest class first) and its warps pull 32-column chunks of the ordered list from a shared counter,
-// so that a warp sees one class (except at the few class boundaries) and the warps of a block stay
-// balanced.  The window keeps the scattered 8-byte accesses of a warp inside 8 KB per field row.
-constexpr int kWindow = 1024;
-constexpr int kWideWindow = 4096;   // for large handles: fewer chunks that straddle two classes (albedo 5.6 -> 5.3 ms at 2M columns)
-constexpr int kClasses = 8;
-
-template <uint32_t MASK> __device__ __forceinline__ int work_class(const Cols& S, const int c)
+// ---- SNICAR with one warp-task per (32 columns, incident-flux type, spectral band) -------------------------------
+// kokkos_albedo_snicar spends ~85 % of its instructions in the snow radiative transfer (round-1 ncu source view), and
+// that part is ten independent solves per column: direct / diffuse x five bands (snow_snicar_impl.hh:313-670), each a
+// loop over up to five layers with eight Gauss points per layer.  One thread per column ran them one after the other
+// with the union of their arrays live (246 registers, 2.7 KB of local memory, 7 warps per SM).  Here a block owns a
+// window of columns, lists its sunlit snow columns in shared memory ordered by their number of layers, and its warps
+// pull work items (chunk of 32 listed columns, flg, band) from a shared counter: lane = column, the whole warp in
+// the same band.  (Layers below the depth where a band's transmission falls under 0.001 skip their solve; that cut-off
+// depends mostly on the band, so lanes of one band stay together - with one lane per band of the same column only 17
+// of 30 lanes were active in the layer solve.)  The seven results of a solve go to a scratch slice of the block
+// (L2-resident); after a block barrier one thread per (column, flg) adds the five bands in the reference's order
+// (snow_albedo_radiation_factor :706-760) and stores albsnd / albsni and the absorption factors
+// (flux_absorption_factor :199-207).  Every value is computed by the same operations in the same order as in
+// column_albedo<false>: bit-identical (tests: split plan = one thread per column, fused plan = this kernel).
+constexpr int kSnicarWindow = 1024;
+constexpr int kSnicarBlock = 128;
+constexpr int kSnicarTasks = 2 * NBND_SNW;                    // (flg, band)
+constexpr int kSnicarValues = NLEVSNO + 2;                    // albedo + absorbed flux of five slots and the ground
+constexpr size_t kSnicarSlice = (size_t)kSnicarWindow * kSnicarTasks * kSnicarValues;   // doubles of scratch per block
+template <int MINBLOCKS>
+__global__ void __launch_bounds__(kSnicarBlock, MINBLOCKS) k_snicar(const Cols S, const Tables* __restrict__ Tp,
+                                                                     double* __restrict__ scratch_all, const int nwindows)
 {
-  if (MASK & ELMK_G_CANOPY_FLUXES) {
-    if (S.frac_veg_nosno[c] == 0) return 0;                       // bare: initialise and leave
-    return (S.parsun_z[c] > 0.0 || S.parsha_z[c] > 0.0) ? 2 : 1;  // day: stomatal root-find; night: none
-  }
-  if (MASK & ELMK_G_ALBEDO) {
-    if (!(S.coszen[c] > 0.0)) return 0;                           // night: initial values only
-    if (!(S.h2osno[c] > 1.0e-30)) return 1;                       // sunlit, no snow: two-stream only
-    const int snl = S.snl[c];
-    return 1 + (snl > 0 ? snl : 1);                               // SNICAR over 1..5 layers
-  }
-  if (MASK & ELMK_G_BAREGROUND_FLUXES) return S.frac_veg_nosno[c] == 0 ? 1 : 0;   // bare: three MO passes
-  if (MASK & (ELMK_G_SOIL_TEMPERATURE | ELMK_G_SNOW_HYDROLOGY)) return S.snl[c];   // work grows with snow layers
-  return 0;
-}
-
-// BLOCK threads per block; LOCKSTEP: the warps of a block take their chunks round by round behind a block
-// barrier (instruction-cache locality for the kernels whose body exceeds the 32 KB L1.5 cache), otherwise
-// they pull chunks from a shared counter (load balance).
-template <uint32_t MASK, int BLOCK, bool LOCKSTEP, int MINBLOCKS = 1, int WINDOW = kWindow>
-__global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_groups_sorted(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
-{
-  __shared__ unsigned short order[WINDOW];
-  __shared__ int count[kClasses], start[kClasses], next_chunk;
-  const int base = blockIdx.x * WINDOW;
-  const int nvalid = (S.ncols - base < WINDOW) ? (S.ncols - base) : WINDOW;
-  if (threadIdx.x < kClasses) count[threadIdx.x] = 0;
-  if (threadIdx.x == 0) next_chunk = 0;
-  __syncthreads();
-  constexpr int R = (WINDOW + BLOCK - 1) / BLOCK;
-  int key[R], rank[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int i = r * BLOCK + threadIdx.x;
-    key[r] = -1;
-    if (i < nvalid) {
-      key[r] = work_class<MASK>(S, base + i);
-      rank[r] = atomicAdd(&count[key[r]], 1);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int k = kClasses - 1; k >= 0; --k) {   // heaviest class first
-      start[k] = acc;
-      acc += count[k];
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if (key[r] >= 0) order[start[key[r]] + rank[r]] = (unsigned short)(r * BLOCK + threadIdx.x);
-  __syncthreads();
+  __shared__ unsigned short order[kSnicarWindow];
+  __shared__ int count[8], start[8], next_item, nactive;
   const Tables& T = *Tp;
   const int lane = threadIdx.x & 31;
-  if (LOCKSTEP) {
-    constexpr int WARPS = BLOCK / 32;
-    const int warp = threadIdx.x >> 5;
-    for (int round = 0; round * WARPS * 32 < nvalid; ++round) {
-      __syncthreads();
-      const int i = (round * WARPS + warp) * 32 + lane;
-      if (i < nvalid) run_groups<MASK>(S, T, A, base + order[i]);
+  double* const scratch = scratch_all + (size_t)blockIdx.x * kSnicarSlice;   // [task][value][listed column]
+  for (int w = blockIdx.x; w < nwindows; w += gridDim.x) {
+    const int base = w * kSnicarWindow;
+    const int nvalid = (S.ncols - base < kSnicarWindow) ? (S.ncols - base) : kSnicarWindow;
+    __syncthreads();   // the previous window's list is no longer read
+    if (threadIdx.x < 8) count[threadIdx.x] = 0;
+    if (threadIdx.x == 0) next_item = 0;
+    __syncthreads();
+    constexpr int R = kSnicarWindow / kSnicarBlock;
+    int key[R], rank[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = r * kSnicarBlock + threadIdx.x;
+      key[r] = -1;
+      if (i < nvalid) {
+        const int c = base + i;
+        if (S.coszen[c] > 0.0 && S.h2osno[c] > alb::MIN_SNW) {
+          const int snl = S.snl[c];
+          key[r] = snl > 0 ? snl : 1;          // layers the solve walks through
+          rank[r] = atomicAdd(&count[key[r]], 1);
+        }
+      }
     }
-  } else {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int k = 7; k >= 0; --k) { start[k] = acc; acc += count[k]; }   // deepest snow packs first
+      nactive = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (key[r] >= 0) order[start[key[r]] + rank[r]] = (unsigned short)(r * kSnicarBlock + threadIdx.x);
+    __syncthreads();
+    const int nact = nactive;
+    const int nitems = ((nact + 31) / 32) * kSnicarTasks;
+    // ---- the band solves ----
     while (true) {
-      int chunk = 0;
-      if (lane == 0) chunk = atomicAdd(&next_chunk, 1);
-      chunk = __shfl_sync(0xffffffffu, chunk, 0);
-      const int i = chunk * 32 + lane;
-      if (chunk * 32 >= nvalid) break;
-      if (i < nvalid) run_groups<MASK>(S, T, A, base + order[i]);
+      int item = 0;
+      if (lane == 0) item = atomicAdd(&next_item, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= nitems) break;
+      const int chunk = item / kSnicarTasks, task = item - chunk * kSnicarTasks;   // the tasks of a chunk run side by side
+      const int flg = task / NBND_SNW + 1, b = task - (flg - 1) * NBND_SNW;
+      const int idx = chunk * 32 + lane;
+      if (idx < nact) {
+        const int c = base + order[idx];
+        const double coszen = C1(coszen), h2osno = C1(h2osno);
+        const int snl = C1(snl);
+        // soil_albedo :702-709 (the ground under the snow pack)
+        const int col = C1(isoicol);
+        const double inc = dmax(0.11 - 0.40 * C2(h2osoi_vol, 0), 0.0);
+        double albsoi[NUMRAD];
+#pragma unroll
+        for (int ib = 0; ib < NUMRAD; ++ib) albsoi[ib] = dmin(T.albsat[col][ib] + inc, T.albdry[col][ib]);
+        uint32_t err = 0;
+        SnicarColumn K;
+        snicar_column(S, c, h2osno, snl, K, err);
+        double albedo = 0.0, fb[NLEVSNO + 1];
+#pragma unroll
+        for (int i = 0; i <= NLEVSNO; ++i) fb[i] = 0.0;
+        if (!(err & ERR_SNICAR_RADIUS)) {   // (the reference throws; results stay zero)
+          const auto cnc_of = [&](const int i, double (&cnc)[NAER]) { snicar_cnc(S, c, i, cnc); };
+          snicar_band(T, K, flg, b, dmax(coszen, 0.01), albsoi, cnc_of, albedo, fb, err);
+        }
+        if (err) atomicOr(&S.errmask[c], (int)err);
+        double* out = scratch + (size_t)task * kSnicarValues * kSnicarWindow + idx;
+        out[0] = albedo;
+#pragma unroll
+        for (int i = 0; i <= NLEVSNO; ++i) out[(size_t)(i + 1) * kSnicarWindow] = fb[i];
+      }
+    }
+    __syncthreads();   // (block-scope visibility of the scratch slice)
+    // ---- band weighting to VIS / NIR, one thread per (listed column, flg) ----
+    for (int j = threadIdx.x; j < 2 * nact; j += kSnicarBlock) {
+      const int idx = j >> 1, flg = (j & 1) + 1;
+      const int c = base + order[idx];
+      const double coszen = C1(coszen), h2osno = C1(h2osno);
+      const int snl = C1(snl);
+      uint32_t err = 0;
+      SnicarColumn K;
+      snicar_column(S, c, h2osno, snl, K, err);
+      int rds_top = 0;
+#pragma unroll
+      for (int i = 0; i < NLEVSNO; ++i) if (i == K.top) rds_top = K.rds[i];
+      double albout_lcl[NBND_SNW], flx_abs_lcl[NLEVSNO + 1][NBND_SNW];
+#pragma unroll
+      for (int bb = 0; bb < NBND_SNW; ++bb) {
+        const double* in = scratch + (size_t)((flg - 1) * NBND_SNW + bb) * kSnicarValues * kSnicarWindow + idx;
+        albout_lcl[bb] = in[0];
+#pragma unroll
+        for (int i = 0; i <= NLEVSNO; ++i) flx_abs_lcl[i][bb] = in[(size_t)(i + 1) * kSnicarWindow];
+      }
+      double alb_out[NUMRAD] = {0.0, 0.0}, flx_abs[NLEVSNO + 1][NUMRAD];
+#pragma unroll
+      for (int i = 0; i <= NLEVSNO; ++i) { flx_abs[i][0] = 0.0; flx_abs[i][1] = 0.0; }
+      if (!(err & ERR_SNICAR_RADIUS))
+        snicar_combine(flg, dmax(coszen, 0.01), K.top, rds_top, albout_lcl, flx_abs_lcl, alb_out, flx_abs);
+      if (flg == 1) {
+        C2(albsnd, 0) = alb_out[0]; C2(albsnd, 1) = alb_out[1];
+#pragma unroll
+        for (int i = 0; i <= NLEVSNO; ++i) {
+          C2(flx_absdv, i) = flx_abs[i][0] * (1.0 - alb_out[0]);
+          C2(flx_absdn, i) = flx_abs[i][1] * (1.0 - alb_out[1]);
+        }
+      } else {
+        C2(albsni, 0) = alb_out[0]; C2(albsni, 1) = alb_out[1];
+#pragma unroll
+        for (int i = 0; i <= NLEVSNO; ++i) {
+          C2(flx_absiv, i) = flx_abs[i][0] * (1.0 - alb_out[0]);
+          C2(flx_absin, i) = flx_abs[i][1] * (1.0 - alb_out[1]);
+        }
+      }
     }
   }
 }
@@ -217,6 +277,8 @@ constexpr int kCanfluxDoubles = 0
 #undef X
     ;
 
+// 384-thread lock-step blocks: fastest of 128...768 threads with and without lock-step on B200
+constexpr int kIterBlock = 384;
 struct CanfluxQueue {
   double* scratch;   // [kCanfluxDoubles][np]
   int* list;         // [np]: day columns from the front, night columns from the back
@@ -392,12 +454,14 @@ __global__ void __launch_bounds__(256) k_math_eval(const int fn, const long long
 }
 
 typedef void (*GroupKernel)(const Cols, const Tables*, const StepArgs);
-struct Launch { uint32_t mask; GroupKernel fn; const char* name; int cols_per_block; int block; };
-#define ELMK_LAUNCH(M, NAME) {(M), k_groups<(M)>, NAME, kBlock, kBlock}
-#define ELMK_LAUNCH_OCC(M, NAME, MINBLOCKS) {(M), k_groups_occ<(M), MINBLOCKS>, NAME, kBlock, kBlock}
-#define ELMK_LAUNCH_SORTED(M, NAME, BLOCK, LOCKSTEP) {(M), k_groups_sorted<(M), BLOCK, LOCKSTEP>, NAME, kWindow, BLOCK}
+// kind: how elmk_step issues the launch when all of its groups are requested
+enum LaunchKind { kPlain = 0, kSnicarFirst = 1, kCanfluxRepacked = 2 };
+struct Launch { uint32_t mask; GroupKernel fn; const char* name; int cols_per_block; int block; int kind; };
+#define ELMK_LAUNCH(M, NAME) {(M), k_groups<(M)>, NAME, kBlock, kBlock, kPlain}
+#define ELMK_LAUNCH_OCC(M, NAME, MINBLOCKS) {(M), k_groups_occ<(M), MINBLOCKS>, NAME, kBlock, kBlock, kPlain}
 
-// plan "split": one launch per kernel group (the reference's wrapper granularity)
+// plan "split": one launch per kernel group, one thread per column (the reference's wrapper granularity); the plain
+// form of every group, against which the fused plan is tested for bit-identity
 const Launch kSplit[] = {
     ELMK_LAUNCH(ELMK_G_FRAC_WET, "frac_wet"),
     ELMK_LAUNCH(ELMK_G_ALBEDO, "albedo_snicar"),
@@ -411,33 +475,26 @@ const Launch kSplit[] = {
     ELMK_LAUNCH(ELMK_G_SURFACE_FLUXES, "surface_fluxes"),
     ELMK_LAUNCH(ELMK_G_CONSERVATION, "conservation"),
 };
-// plan "fused": the chain cut where register pressure changes character -
-//   radiative transfer | closed-form hydrology/radiation/temperature + bare-ground fluxes |
-//   canopy-flux iteration | banded solve | snow state machine + flux update + diagnostics
+// plan "fused" (the default): the chain cut where register pressure changes character -
+//   radiative transfer (SNICAR kernel, then soil / ground albedo + two-stream) | closed-form hydrology / radiation /
+//   temperature + bare-ground fluxes | canopy-flux iteration (re-packed) | banded solve | snow state machine + flux
+//   update + diagnostics
 constexpr uint32_t M_RAD = ELMK_G_FRAC_WET | ELMK_G_ALBEDO;
+constexpr uint32_t M_RAD_REST = ELMK_G_FRAC_WET | G_ALBEDO_REST;
 constexpr uint32_t M_SFC = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | ELMK_G_CANOPY_TEMPERATURE |
                            ELMK_G_BAREGROUND_FLUXES;
 constexpr uint32_t M_END = ELMK_G_SNOW_HYDROLOGY | ELMK_G_SURFACE_FLUXES | ELMK_G_CONSERVATION;
-// (register caps: blocks per SM chosen by A/B runs on B200 at 2M columns - 10 / 8 / 6 were the fastest of 2..10;
-//  soil temperature at 8 only together with its block re-alignment points, 5 without)
+// (register caps = resident blocks per SM, chosen by A/B runs on B200 at 2M columns)
 const Launch kFused[] = {
-    ELMK_LAUNCH_SORTED(M_RAD, "fracwet+albedo", 128, false),
+    {M_RAD, k_groups_occ<M_RAD_REST, 6>, "fracwet+albedo", kBlock, kBlock, kSnicarFirst},
     ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 10),
-    ELMK_LAUNCH_SORTED(ELMK_G_CANOPY_FLUXES, "canopy_fluxes", 128, false),
+    {ELMK_G_CANOPY_FLUXES, k_groups<ELMK_G_CANOPY_FLUXES>, "canopy_fluxes", kBlock, kBlock, kCanfluxRepacked},
     ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 8),
     ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 6),
 };
-// development: alternative launch configurations of the radiative-transfer launch (ELMK_RAD_VARIANT=1..)
-#define ELMK_LAUNCH_SORTED_OCC(M, NAME, BLOCK, LOCKSTEP, MINB) {(M), k_groups_sorted<(M), BLOCK, LOCKSTEP, MINB>, NAME, kWindow, BLOCK}
-const Launch kRadVariants[] = {
-    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 128, false, 3),
-    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 128, false, 4),
-    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 256, false, 1),
-    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 256, false, 2),
-    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 256, true, 1),
-    ELMK_LAUNCH_SORTED_OCC(M_RAD, "fracwet+albedo", 512, true, 1),
-};
-// development: register caps of the three unsorted launches (ELMK_OCC_SFC / _SOIL / _END = blocks per SM)
+#ifdef ELMK_DEV_VARIANTS
+// development builds only (elmkernels_b200/build.py --dev): register caps of the unsorted launches selected by
+// environment variables (ELMK_OCC_RAD / _SFC / _SOIL / _END = blocks per SM) for A/B runs
 template <uint32_t M> GroupKernel occ_variant(int minblocks) {
   switch (minblocks) {
     case 2: return k_groups_occ<M, 2>;
@@ -450,17 +507,7 @@ template <uint32_t M> GroupKernel occ_variant(int minblocks) {
     default: return nullptr;
   }
 }
-// the radiative-transfer launch with the wide sorting window, used when the handle has enough columns to fill the GPU
-// with 4096-column blocks
-const Launch kRadWide = {M_RAD, k_groups_sorted<M_RAD, 128, false, 1, kWideWindow>, "fracwet+albedo", kWideWindow, 128};
-// plan "unsorted": the fused cut without work-class ordering (for A/B measurements)
-const Launch kFusedUnsorted[] = {
-    ELMK_LAUNCH(M_RAD, "fracwet+albedo"),
-    ELMK_LAUNCH(M_SFC, "hydrology+radiation+temperature+bareground"),
-    ELMK_LAUNCH(ELMK_G_CANOPY_FLUXES, "canopy_fluxes"),
-    ELMK_LAUNCH(ELMK_G_SOIL_TEMPERATURE, "soil_temperature"),
-    ELMK_LAUNCH(M_END, "snow+surface_fluxes+conservation"),
-};
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // layout conversion between the reference's host layout (column outer) and the device layout
@@ -604,15 +651,20 @@ struct Ctx {
   double* phen[PHEN_NVARS] = {};   // monthly phenology values [nmonths][np] (elmk_phen_series)
   int phen_nmonths[PHEN_NVARS] = {};
   CanfluxQueue cq = {nullptr, nullptr, nullptr, 0};   // CanopyFluxes re-packing scratch (allocated on first use)
-  int iterate_blocks = 0, iterate_variant = 0;
+  int iterate_blocks = 0;
   bool repack = true;
+  void (*snicar_fn)(const Cols, const Tables*, double*, int) = k_snicar<3>;
+  double* snicar_scratch = nullptr;   // kSnicarSlice doubles per resident block (allocated on first use)
+  int snicar_blocks = 0;
+  void (*iterate_fn)(const Cols, const CanfluxQueue) = k_canflux_iterate<kIterBlock, true>;
+  int iterate_block = kIterBlock;
   unsigned int* d_err = nullptr;   // [0] any, then long long first at +8
   double* d_diag = nullptr;
   void* h_pinned = nullptr;        // small pinned buffer for scalar read-backs
   bool tables_set = false;
   int64_t launches = 0;
   // optional per-launch timing
-  bool timing = false;
+  bool timing = false, timing_detail = false;
   struct Timed { const char* name; uint32_t mask; cudaEvent_t t0, t1; };
   std::vector<Timed> timed;          // recorded, not yet accumulated
   std::vector<cudaEvent_t> ev_pool;  // recycled events
@@ -620,7 +672,7 @@ struct Ctx {
   std::vector<Acc> acc;
   const Launch* plan = kFused;
   int plan_len = sizeof(kFused) / sizeof(kFused[0]);
-  std::vector<Launch> plan_own;   // a modified copy of a built-in plan (development variants)
+  std::vector<Launch> plan_own;   // a modified copy of the fused plan (development builds)
   std::string last_error;
 };
 Ctx* ctx(elmk_handle h) { return reinterpret_cast<Ctx*>(h); }
@@ -755,26 +807,13 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
     CU(cudaMalloc(&c->cq.counters, sizeof(int) * 4));
     c->cq.np = c->np;
     int per_sm = 0, sms = 0;
-    const char* v = std::getenv("ELMK_ITER_VARIANT");
-    c->iterate_variant = v ? std::atoi(v) : 4;   // 384-thread blocks, lock-step passes
-    switch (c->iterate_variant) {
-      case 1: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<128, true>, 128, 0)); break;
-      case 2: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<256, true>, 256, 0)); break;
-      case 3: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<256, false>, 256, 0)); break;
-      case 4: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<384, true>, 384, 0)); break;
-      case 5: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<512, true>, 512, 0)); break;
-      case 6: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<768, true>, 768, 0)); break;
-      case 7: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<640, true>, 640, 0)); break;
-      case 8: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<448, true>, 448, 0)); break;
-      default: CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_canflux_iterate<128, false>, 128, 0)); break;
-    }
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->iterate_fn, c->iterate_block, 0));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     c->iterate_blocks = std::max(1, per_sm) * std::max(1, sms);
   }
   const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
   CU(cudaMemsetAsync(c->cq.counters, 0, sizeof(int) * 4, c->stream));
-  static const bool detail = std::getenv("ELMK_TIMING_DETAIL") != nullptr;   // development: time the three launches apart
-  const bool split = detail && c->timing;
+  const bool split = c->timing && c->timing_detail;   // time the three launches apart
   auto mark = [&](Ctx::Timed& t, const char* name) {
     t = {name, 0u, take_event(c), take_event(c)};
     cudaEventRecord(t.t0, c->stream);
@@ -788,17 +827,7 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
   k_canflux_begin<<<grid, kBlock, 0, c->stream>>>(c->cols, c->d_tables, A, c->cq);
   if (split) done(tb), mark(ti, "canopy_fluxes:iterate");
   const unsigned persistent = (unsigned)std::min<int64_t>(c->iterate_blocks, (c->ncols + kBlock - 1) / kBlock);
-  switch (c->iterate_variant) {
-    case 1: k_canflux_iterate<128, true><<<persistent, 128, 0, c->stream>>>(c->cols, c->cq); break;
-    case 2: k_canflux_iterate<256, true><<<persistent, 256, 0, c->stream>>>(c->cols, c->cq); break;
-    case 3: k_canflux_iterate<256, false><<<persistent, 256, 0, c->stream>>>(c->cols, c->cq); break;
-    case 4: k_canflux_iterate<384, true><<<persistent, 384, 0, c->stream>>>(c->cols, c->cq); break;
-    case 5: k_canflux_iterate<512, true><<<persistent, 512, 0, c->stream>>>(c->cols, c->cq); break;
-    case 6: k_canflux_iterate<768, true><<<persistent, 768, 0, c->stream>>>(c->cols, c->cq); break;
-    case 7: k_canflux_iterate<640, true><<<persistent, 640, 0, c->stream>>>(c->cols, c->cq); break;
-    case 8: k_canflux_iterate<448, true><<<persistent, 448, 0, c->stream>>>(c->cols, c->cq); break;
-    default: k_canflux_iterate<128, false><<<persistent, 128, 0, c->stream>>>(c->cols, c->cq); break;
-  }
+  c->iterate_fn<<<persistent, c->iterate_block, 0, c->stream>>>(c->cols, c->cq);
   if (split) done(ti), mark(te, "canopy_fluxes:end");
   k_canflux_end<<<grid, kBlock, 0, c->stream>>>(c->cols, c->cq);
   if (split) done(te);
@@ -918,43 +947,44 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
   if ((e = cudaMallocHost(&c->h_pinned, sizeof(double) * 8 * kDiagSlices * 3)) != cudaSuccess)
     return bail(fail(c, e, "cudaMallocHost"));
   if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail(fail(c, e, "cudaStreamSynchronize"));
-  const char* plan = std::getenv("ELMK_PLAN");
-  if (plan && std::strcmp(plan, "split") == 0) {
-    c->plan = kSplit;
-    c->plan_len = sizeof(kSplit) / sizeof(kSplit[0]);
-  } else if (plan && std::strcmp(plan, "unsorted") == 0) {
-    c->plan = kFusedUnsorted;
-    c->plan_len = sizeof(kFusedUnsorted) / sizeof(kFusedUnsorted[0]);
-  }
-  const char* rw = std::getenv("ELMK_RAD_WINDOW");   // "wide" / "narrow": override for tests and A/B runs
-  const bool wide = rw ? (std::strcmp(rw, "wide") == 0)
-                       : (ncols >= (int64_t)kWideWindow * 296);   // >= one block per resident slot of a B200 (148 SMs x 2)
-  if (c->plan == kFused && wide) {
-    c->plan_own.assign(kFused, kFused + c->plan_len);
-    c->plan_own[0] = kRadWide;
-  }
-  const char* rp = std::getenv("ELMK_CANFLUX_REPACK");
-  if (rp && rp[0] == '0') c->repack = false;
+#ifdef ELMK_DEV_VARIANTS
   {
+    const char* rp = std::getenv("ELMK_CANFLUX_REPACK");
+    if (rp && rp[0] == '0') c->repack = false;
+    const char* sn = std::getenv("ELMK_SNICAR_OCC");
+    if (sn) c->snicar_fn = std::atoi(sn) == 4 ? k_snicar<4> : std::atoi(sn) == 2 ? k_snicar<2> : k_snicar<3>;
+    const char* ib = std::getenv("ELMK_ITER");   // e.g. "256l" = 256-thread lock-step blocks, "128" = 128 threads free-running
+    if (ib) {
+      const int nb = std::atoi(ib);
+      const bool ls = std::strchr(ib, 'l') != nullptr;
+      c->iterate_block = nb;
+      if (nb == 128) c->iterate_fn = ls ? k_canflux_iterate<128, true> : k_canflux_iterate<128, false>;
+      else if (nb == 256) c->iterate_fn = ls ? k_canflux_iterate<256, true> : k_canflux_iterate<256, false>;
+      else if (nb == 512) c->iterate_fn = k_canflux_iterate<512, true>;
+      else { c->iterate_block = kIterBlock; c->iterate_fn = ls ? k_canflux_iterate<384, true> : k_canflux_iterate<384, false>; }
+    }
+    const char* e0 = std::getenv("ELMK_OCC_RAD");
     const char* e1 = std::getenv("ELMK_OCC_SFC");
     const char* e2 = std::getenv("ELMK_OCC_SOIL");
     const char* e3 = std::getenv("ELMK_OCC_END");
-    if ((e1 || e2 || e3) && c->plan == kFused) {
-      if (c->plan_own.empty()) c->plan_own.assign(kFused, kFused + c->plan_len);
+    const char* fz = std::getenv("ELMK_FUSE_RAD_SFC");   // albedo rest + surface chain in one launch
+    if (e0 || e1 || e2 || e3 || fz) {
+      c->plan_own.assign(kFused, kFused + c->plan_len);
       GroupKernel k;
+      if (e0 && (k = occ_variant<M_RAD_REST>(std::atoi(e0)))) c->plan_own[0].fn = k;
       if (e1 && (k = occ_variant<M_SFC>(std::atoi(e1)))) c->plan_own[1].fn = k;
       if (e2 && (k = occ_variant<ELMK_G_SOIL_TEMPERATURE>(std::atoi(e2)))) c->plan_own[3].fn = k;
       if (e3 && (k = occ_variant<M_END>(std::atoi(e3)))) c->plan_own[4].fn = k;
+      if (fz && (k = occ_variant<M_RAD_REST | M_SFC>(std::atoi(fz)))) {
+        c->plan_own[0].fn = k;
+        c->plan_own[0].mask = M_RAD | M_SFC;
+        c->plan_own[0].name = "fracwet+albedo+hydrology+radiation+temperature+bareground";
+        c->plan_own.erase(c->plan_own.begin() + 1);
+        c->plan_len -= 1;
+      }
     }
   }
-  const char* rv = std::getenv("ELMK_RAD_VARIANT");
-  if (rv && c->plan == kFused) {
-    const int v = std::atoi(rv);
-    if (v >= 1 && v <= (int)(sizeof(kRadVariants) / sizeof(kRadVariants[0]))) {
-      if (c->plan_own.empty()) c->plan_own.assign(kFused, kFused + c->plan_len);
-      c->plan_own[0] = kRadVariants[v - 1];
-    }
-  }
+#endif
   *out = reinterpret_cast<elmk_handle>(c);
   return ELMK_OK;
 }
@@ -973,6 +1003,7 @@ int elmk_destroy(elmk_handle h) {
   cudaFree(c->d_diag);
   for (double* p : c->atm) cudaFree(p);
   for (double* p : c->phen) cudaFree(p);
+  cudaFree(c->snicar_scratch);
   cudaFree(c->cq.scratch);
   cudaFree(c->cq.list);
   cudaFree(c->cq.counters);
@@ -1398,12 +1429,32 @@ int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_
   // cover the requested groups, in chain order, with the launches of the plan; a launch whose group
   // set is only partly requested falls back to one launch per requested group
   for (int i = 0; i < c->plan_len; ++i) {
-    const Launch& L = c->plan_own.empty() ? c->plan[i] : c->plan_own[i];
+    const Launch& L = (c->plan == kFused && !c->plan_own.empty()) ? c->plan_own[i] : c->plan[i];
     const uint32_t want = L.mask & mask;
     if (!want) continue;
-    if (want == L.mask && L.mask == ELMK_G_CANOPY_FLUXES && c->repack && c->plan != kSplit && c->plan != kFusedUnsorted) {
+    if (want == L.mask && L.kind == kCanfluxRepacked && c->repack) {
       TimedScope ts(c, L.name, L.mask);
       if (int rc = launch_canflux_repacked(c, A)) return rc;
+    } else if (want == L.mask && L.kind == kSnicarFirst) {
+      // the ten band solves of every sunlit snow column, then the rest of the albedo group for every column
+      TimedScope ts(c, L.name, L.mask);
+      const bool split = c->timing && c->timing_detail;
+      Ctx::Timed t1{}, t2{};
+      if (split) { t1 = {"albedo:snicar", 0u, take_event(c), take_event(c)}; cudaEventRecord(t1.t0, c->stream); }
+      const int nwindows = (int)((c->ncols + kSnicarWindow - 1) / kSnicarWindow);
+      if (!c->snicar_scratch) {
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->snicar_fn, kSnicarBlock, 0));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        c->snicar_blocks = std::min(nwindows, std::max(1, per_sm) * std::max(1, sms));
+        CU(cudaMalloc(&c->snicar_scratch, sizeof(double) * kSnicarSlice * (size_t)c->snicar_blocks));
+      }
+      c->snicar_fn<<<(unsigned)c->snicar_blocks, kSnicarBlock, 0, c->stream>>>(c->cols, c->d_tables, c->snicar_scratch, nwindows);
+      if (split) { cudaEventRecord(t1.t1, c->stream); c->timed.push_back(t1);
+                   t2 = {"albedo:rest", 0u, take_event(c), take_event(c)}; cudaEventRecord(t2.t0, c->stream); }
+      L.fn<<<grid_for(L), L.block, 0, c->stream>>>(c->cols, c->d_tables, A);
+      if (split) { cudaEventRecord(t2.t1, c->stream); c->timed.push_back(t2); }
+      c->launches += 2;
     } else if (want == L.mask) {
       TimedScope ts(c, L.name, L.mask);
       L.fn<<<grid_for(L), L.block, 0, c->stream>>>(c->cols, c->d_tables, A);
@@ -1425,6 +1476,22 @@ int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_
   return ELMK_OK;
 }
 
+int elmk_set_plan(elmk_handle h, int plan) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (plan == ELMK_PLAN_FUSED) {
+    c->plan = kFused;
+    c->plan_len = sizeof(kFused) / sizeof(kFused[0]);
+  } else if (plan == ELMK_PLAN_SPLIT) {
+    c->plan = kSplit;
+    c->plan_len = sizeof(kSplit) / sizeof(kSplit[0]);
+  } else {
+    c->last_error = "elmk_set_plan: unknown plan";
+    return ELMK_EINVAL;
+  }
+  return ELMK_OK;
+}
+
 int elmk_sync(elmk_handle h) {
   Ctx* c = ctx(h);
   if (!c) return ELMK_EINVAL;
@@ -1441,6 +1508,7 @@ int elmk_timing_enable(elmk_handle h, int on) {
   if (int rc = drain_timing(c)) return rc;
   c->acc.clear();
   c->timing = on != 0;
+  c->timing_detail = on > 1;   // 2: also the sub-launches of the composite launches (SNICAR / rest, begin / iterate / end)
   return ELMK_OK;
 }
 int elmk_timing_read(elmk_handle h, int max, const char** names, double* total_ms, int64_t* launches,

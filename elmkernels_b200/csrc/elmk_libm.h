@@ -251,16 +251,9 @@ ELMK_LM_HD double g_log10(double x)
 constexpr double kPowA0 = -0x1p-1, kPowA1 = -0x1.5555555555560p-1, kPowA2 = 0x1.0000000000006p-1, kPowA3 = 0x1.999999959554ep-1,
                  kPowA4 = -0x1.555555529a47ap-1, kPowA5 = -0x1.2495b9b4845e9p0, kPowA6 = 0x1.0002b8b263fc3p0;
 
-ELMK_LM_HD double g_pow(const double x, const double y)
+// log(x) as lhi + llo with ~68 bits (e_pow.c log_inline), x positive and normal
+ELMK_LM_HD void pow_log(const uint64_t ix, double& lhi, double& llo)
 {
-  const uint64_t ix = as_u64(x), iy = as_u64(y);
-  const uint32_t topx = (uint32_t)(ix >> 52), topy = (uint32_t)(iy >> 52) & 0x7ffu;
-  if (topx - 1u > 0x7fdu || topy - 0x3beu > 0x7fu) {
-    if (iy * 2 == 0) return 1.0;
-    if (ix == 0x3ff0000000000000ull) return 1.0;
-    return pow(x, y);   // zero, negative, subnormal or non-finite base, tiny or huge exponent: not on the column path
-  }
-  // log(x) as hi + lo with ~68 bits
   const uint64_t* T = ELMK_LM_TABLE(powlog_tab);
   const uint64_t tmp = ix - 0x3fe6955500000000ull;
   const int i = (int)((tmp >> 45) & 127u);
@@ -289,9 +282,12 @@ ELMK_LM_HD double g_pow(const double x, const double y)
   lo = lo + lo3;
   lo = lo + lo4;
   lo = fma(ar3, p, lo);
-  const double lhi = hi + lo;
-  const double llo = (hi - lhi) + lo;
-  // y * log(x) and its exponential
+  lhi = hi + lo;
+  llo = (hi - lhi) + lo;
+}
+// exp(y * (lhi + llo)) (e_pow.c exp_inline after the product)
+ELMK_LM_HD double pow_exp(const double y, const double lhi, const double llo)
+{
   const double ehi = y * lhi;
   const double elo = fma(y, llo, fma(lhi, y, -ehi));
   uint32_t abstop = (uint32_t)(as_u64(ehi) >> 52) & 0x7ffu;
@@ -302,6 +298,33 @@ ELMK_LM_HD double g_pow(const double x, const double y)
   }
   return exp_core(ehi, elo, true, 0, abstop);
 }
+
+ELMK_LM_HD double g_pow(const double x, const double y)
+{
+  const uint64_t ix = as_u64(x), iy = as_u64(y);
+  const uint32_t topx = (uint32_t)(ix >> 52), topy = (uint32_t)(iy >> 52) & 0x7ffu;
+  if (topx - 1u > 0x7fdu || topy - 0x3beu > 0x7fu) {
+    if (iy * 2 == 0) return 1.0;
+    if (ix == 0x3ff0000000000000ull) return 1.0;
+    return pow(x, y);   // zero, negative, subnormal or non-finite base, tiny or huge exponent: not on the column path
+  }
+  double lhi, llo;
+  pow_log(ix, lhi, llo);
+  return pow_exp(y, lhi, llo);
+}
+
+// pow(c, y) for a constant base c whose (lhi, llo) = pow_log(c) are given as literals: the first half of pow is the
+// same for every call, so it is folded; the value is pow's own (tests/libm/libm_check.cc pins pow_cbase against libm).
+ELMK_LM_HD double g_pow_cbase(const double base, const double lhi, const double llo, const double y)
+{
+  const uint32_t topy = (uint32_t)(as_u64(y) >> 52) & 0x7ffu;
+  if (topy - 0x3beu > 0x7fu) return g_pow(base, y);
+  return pow_exp(y, lhi, llo);
+}
+// pow_log of 0.57, 2.29 and 2.0 (tests/libm/libm_check.cc recomputes them)
+#define ELMK_POWLOG_0_57 -0x1.1fce0d03dd5e6p-1, 0x1.a4ee52p-57
+#define ELMK_POWLOG_2_29 0x1.a837f19ef9d69p-1, 0x1.2e2417cp-55
+#define ELMK_POWLOG_2_0 0x1.62e42fefa39efp-1, 0x1.abc9e3b398p-56
 
 // ---- atan -----------------------------------------------------------------------------------------------------
 ELMK_LM_HD double g_atan(const double x)

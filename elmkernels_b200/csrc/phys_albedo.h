@@ -17,6 +17,12 @@
 #pragma once
 #include "elmk_state.h"
 
+// ELMK_SNICAR_ROLLED (experiment): the layer loops of one band solve stay loops
+#if defined(__CUDA_ARCH__) && defined(ELMK_SNICAR_ROLLED)
+#define ELMK_SNICAR_LOOP _Pragma("unroll 1")
+#else
+#define ELMK_SNICAR_LOOP _Pragma("unroll")
+#endif
 namespace elmk {
 
 namespace alb {
@@ -93,235 +99,248 @@ ELMK_HD_NOINLINE GaussPair snicar_gauss_pair_inl(const double ts, const double w
   return g;
 }
 
-ELMK_HD_NOINLINE void snicar_solve(const Cols& S, const Tables& T, const int c, const int flg, const double coszen,
-                          const double h2osno, const int snl, const double (&albsoi)[NUMRAD],
-                          const double (&cnc)[NLEVSNO][NAER], double (&alb_out)[NUMRAD],
-                          double (&flx_abs)[NLEVSNO + 1][NUMRAD], uint32_t& err)
-{
-  using namespace alb;
-  if (!((coszen > 0.0) && (h2osno > MIN_SNW))) {
-    // snow_albedo_radiation_factor :762-768
-    if ((coszen > 0.0) && (h2osno < MIN_SNW) && (h2osno > 0.0)) {
-      alb_out[0] = albsoi[0];
-      alb_out[1] = albsoi[1];
-    } else {
-      alb_out[0] = 0.0;
-      alb_out[1] = 0.0;
-    }
-    return;
-  }
-
-  // ---- local snow column (snow_snicar::init_timestep :37-100) ----
+// The snow column as SNICAR sees it (snow_snicar::init_timestep :37-100): ice / liquid mass and the grain radius of
+// the five snow slots, top = index of the top slot; a column without explicit layers is one layer of h2osno.
+struct SnicarColumn {
   double ice[NLEVSNO], liq[NLEVSNO];
   int rds[NLEVSNO];
-  int flg_nosnl, snl_lcl;
+  int top;
+};
+ELMK_HD void snicar_column(const Cols& S, const int c, const double h2osno, const int snl, SnicarColumn& K, uint32_t& err)
+{
+  using namespace alb;
+  int snl_lcl;
   if (snl == 0) {
-    flg_nosnl = 1;
     snl_lcl = 1;
 #pragma unroll
-    for (int i = 0; i < NLEVSNO; ++i) { ice[i] = 0.0; liq[i] = 0.0; rds[i] = 0; }
-    ice[NLEVSNO - 1] = h2osno;
-    liq[NLEVSNO - 1] = 0.0;
-    rds[NLEVSNO - 1] = (int)round(SNW_RDS_MIN);
+    for (int i = 0; i < NLEVSNO; ++i) { K.ice[i] = 0.0; K.liq[i] = 0.0; K.rds[i] = 0; }
+    K.ice[NLEVSNO - 1] = h2osno;
+    K.liq[NLEVSNO - 1] = 0.0;
+    K.rds[NLEVSNO - 1] = (int)round(SNW_RDS_MIN);
   } else {
-    flg_nosnl = 0;
     snl_lcl = snl;
 #pragma unroll
     for (int i = 0; i < NLEVSNO; ++i) {
-      liq[i] = C2(h2osoi_liq, i);
-      ice[i] = C2(h2osoi_ice, i);
-      rds[i] = (int)round(C2(snw_rds, i));
+      K.liq[i] = C2(h2osoi_liq, i);
+      K.ice[i] = C2(h2osoi_ice, i);
+      K.rds[i] = (int)round(C2(snw_rds, i));
     }
   }
-  const int top = NLEVSNO - snl_lcl;   // index of the top snow slot; bottom slot is NLEVSNO-1
+  K.top = NLEVSNO - snl_lcl;   // index of the top snow slot; bottom slot is NLEVSNO-1
 #pragma unroll
   for (int i = 0; i < NLEVSNO; ++i)
-    if (i >= top && ((rds[i] < RDS_MIN_TBL) || (rds[i] > RDS_MAX_TBL))) err |= ERR_SNICAR_RADIUS;
-  if (err & ERR_SNICAR_RADIUS) return;   // the reference throws here; a table gather would be out of range
+    if (i >= K.top && ((K.rds[i] < RDS_MIN_TBL) || (K.rds[i] > RDS_MAX_TBL))) err |= ERR_SNICAR_RADIUS;
+}
 
-  const double mu_not = dmax(coszen, 0.01);
+// aerosol mass concentrations of snow slot i as SNICAR orders them (OC ignored, :144-145)
+ELMK_HD void snicar_cnc(const Cols& S, const int c, const int i, double (&cnc)[NAER])
+{
+  cnc[0] = C2(cnc_bcphi, i);
+  cnc[1] = C2(cnc_bcpho, i);
+  cnc[2] = 0.0;
+  cnc[3] = 0.0;
+  cnc[4] = C2(cnc_dst1, i);
+  cnc[5] = C2(cnc_dst2, i);
+  cnc[6] = C2(cnc_dst3, i);
+  cnc[7] = C2(cnc_dst4, i);
+}
+
+// ONE spectral band b of one incident-flux type (flg = 1 direct beam, 2 diffuse): weighted Mie parameters, delta
+// transform, Delta-Eddington adding-doubling (snow_radiative_transfer_solver :213-666 for one value of its band
+// loop).  Outputs: the band's albedo and absorbed fluxes of the five snow slots + the ground.  The ten (flg, b)
+// combinations of a column are independent of each other: the one-thread-per-column path runs them one after the
+// other (snicar_solve below), the SNICAR kernel of the CUDA library gives each its own lane.
+// CNC: callable (i, cnc[8]) that fills the aerosol concentrations of slot i (zeros for b >= 3, :146-152).
+template <class CNC>
+ELMK_HD void snicar_band(const Tables& T, const SnicarColumn& K, const int flg, const int b, const double mu_not,
+                         const double (&albsoi)[NUMRAD], const CNC& cnc_of, double& albedo_out,
+                         double (&flx_abs_b)[NLEVSNO + 1], uint32_t& err)
+{
+  using namespace alb;
+  const int top = K.top;
   const double flx_slrd = (flg == 1) ? 1.0 / (mu_not * PI) : 0.0;
   const double flx_slri = (flg == 1) ? 0.0 : 1.0;
   const int d = (flg == 1) ? 0 : 1;    // drc / dfs optics
-
   // Gaussian quadrature for the diffuse re-integration (:349-352)
   const double gauspt[8] = {0.9894009, 0.9445750, 0.8656312, 0.7554044, 0.6178762, 0.4580168, 0.2816036, 0.0950125};
   const double gauswt[8] = {0.0271525, 0.0622535, 0.0951585, 0.1246290, 0.1495960, 0.1691565, 0.1826034, 0.1894506};
   constexpr double puny = 1.0e-11;
-  constexpr double exp_min = 0x1.7cd79b5647c9bp-15;   // i_exp(-10), the reference's constant-folded value (:357)
+  constexpr double exp_min = 0x1.7cd79b5647c9bp-15;   // exp(-10), the reference's constant-folded value (:357)
   constexpr double trmin = 0.001;
-
-  double albout_lcl[NBND_SNW];
-  double flx_abs_lcl[NLEVSNO + 1][NBND_SNW];
-#pragma unroll
-  for (int i = 0; i <= NLEVSNO; ++i)
-#pragma unroll
-    for (int b = 0; b < NBND_SNW; ++b) flx_abs_lcl[i][b] = 0.0;
-
   // BC optics indices: fixed 100 nm effective radii (:127-128,236-237) -> round(100/50) - 1 = 1
   constexpr int idx_nclrds = 1;
+  const bool with_aer = (b < 3);   // aerosol concentrations are zeroed for bands 3 and 4 (:146-152)
 
-#pragma unroll 1
-  for (int b = 0; b < NBND_SNW; ++b) {
-    const bool with_aer = (b < 3);   // aerosol concentrations are zeroed for bands 3 and 4 (:146-152)
+  // ---- weighted Mie parameters and delta transform per layer (:213-305) ----
+  double ts_[NLEVSNO], ws_[NLEVSNO], gs_[NLEVSNO];
+ELMK_SNICAR_LOOP
+  for (int i = 0; i < NLEVSNO; ++i) {
+    ts_[i] = 0.0; ws_[i] = 0.0; gs_[i] = 0.0;
+    if (i >= top) {
+      const int ridx = K.rds[i] - RDS_MIN_TBL;
+      const double ss_snw = T.snw[d][0][b * MIE_N + ridx];
+      const double asm_snw = T.snw[d][1][b * MIE_N + ridx];
+      const double ext_snw = T.snw[d][2][b * MIE_N + ridx];
+      int idx_icerds;
+      if (K.rds[i] < 125) idx_icerds = K.rds[i] / 50 - 1;
+      else if (K.rds[i] < 175) idx_icerds = 1;
+      else idx_icerds = (K.rds[i] / 250) + 2 - 1;
+      idx_icerds = imin(imax(idx_icerds, 0), 7);
+      const double enh = T.bcenh[idx_icerds][idx_nclrds][b];
 
-    // ---- weighted Mie parameters and delta transform per layer (:213-305) ----
-    double ts_[NLEVSNO], ws_[NLEVSNO], gs_[NLEVSNO];
-#pragma unroll
-    for (int i = 0; i < NLEVSNO; ++i) {
-      ts_[i] = 0.0; ws_[i] = 0.0; gs_[i] = 0.0;
-      if (i >= top) {
-        const int ridx = rds[i] - RDS_MIN_TBL;
-        const double ss_snw = T.snw[d][0][b * MIE_N + ridx];
-        const double asm_snw = T.snw[d][1][b * MIE_N + ridx];
-        const double ext_snw = T.snw[d][2][b * MIE_N + ridx];
-        int idx_icerds;
-        if (rds[i] < 125) idx_icerds = rds[i] / 50 - 1;
-        else if (rds[i] < 175) idx_icerds = 1;
-        else idx_icerds = (rds[i] / 250) + 2 - 1;
-        idx_icerds = imin(imax(idx_icerds, 0), 7);
-        const double enh = T.bcenh[idx_icerds][idx_nclrds][b];
-
-        const double L_snw = ice[i] + liq[i];
-        const double tau_snw = L_snw * ext_snw;
-        double tau_sum = 0.0, omega_sum = 0.0, g_sum = 0.0;
-#pragma unroll
-        for (int j = 0; j < NAER; ++j) {
-          double ss, as, ex;
-          if (j == 0) { ss = T.bc[0][0][idx_nclrds][b]; as = T.bc[0][1][idx_nclrds][b]; ex = T.bc[0][2][idx_nclrds][b] * enh; }
-          else if (j == 1) { ss = T.bc[1][0][idx_nclrds][b]; as = T.bc[1][1][idx_nclrds][b]; ex = T.bc[1][2][idx_nclrds][b]; }
-          else { ss = T.aer_band[j - 2][0][b]; as = T.aer_band[j - 2][1][b]; ex = T.aer_band[j - 2][2][b]; }
-          const double L_aer = L_snw * (with_aer ? cnc[i][j] : 0.0);
-          const double tau_aer = L_aer * ex;
-          tau_sum += tau_aer;
-          omega_sum += (tau_aer * ss);
-          g_sum += (tau_aer * ss * as);
-        }
-        const double tau = tau_sum + tau_snw;
-        const double omega = (1.0 / tau) * (omega_sum + (ss_snw * tau_snw));
-        const double g = (1.0 / (tau * omega)) * (g_sum + (asm_snw * ss_snw * tau_snw));
-        gs_[i] = g / (1.0 + g);
-        ws_[i] = ((1.0 - sq(g)) * omega) / (1.0 - (omega * sq(g)));
-        ts_[i] = (1.0 - (omega * sq(g))) * tau;
+      const double L_snw = K.ice[i] + K.liq[i];
+      const double tau_snw = L_snw * ext_snw;
+      double tau_sum = 0.0, omega_sum = 0.0, g_sum = 0.0;
+      double cnc[NAER];
+      if (with_aer) {
+        cnc_of(i, cnc);
+      } else {
+ELMK_SNICAR_LOOP
+        for (int j = 0; j < NAER; ++j) cnc[j] = 0.0;
       }
-    }
-
-    // ---- Delta-Eddington adding-doubling (:384-666) ----
-    double trndir[NLEVSNO + 1], trntdr[NLEVSNO + 1], trndif[NLEVSNO + 1], rupdir[NLEVSNO + 1], rupdif[NLEVSNO + 1],
-        rdndif[NLEVSNO + 1];
-    double rdir[NLEVSNO], rdif_a[NLEVSNO], rdif_b[NLEVSNO], tdir[NLEVSNO], tdif_a[NLEVSNO], tdif_b[NLEVSNO],
-        trnlay[NLEVSNO];
-#pragma unroll
-    for (int i = 0; i <= NLEVSNO; ++i) {
-      trndir[i] = 0.0; trntdr[i] = 0.0; trndif[i] = 0.0; rupdir[i] = 0.0; rupdif[i] = 0.0; rdndif[i] = 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i <= NLEVSNO; ++i)
-      if (i == top) { trndir[i] = 1.0; trntdr[i] = 1.0; trndif[i] = 1.0; rdndif[i] = 0.0; }
-
-#pragma unroll
-    for (int i = 0; i < NLEVSNO; ++i) {
-      rdir[i] = 0.0; rdif_a[i] = 0.0; rdif_b[i] = 0.0; tdir[i] = 0.0; tdif_a[i] = 0.0; tdif_b[i] = 0.0; trnlay[i] = 0.0;
-      if (i >= top) {
-        if (trntdr[i] > trmin) {
-          const double ts = ts_[i], ws = ws_[i], gs = gs_[i];
-          const LayerDirect ld = snicar_layer_direct_inl(ts, ws, gs, mu_not, exp_min);
-          const double lm = ld.lm;
-          rdif_a[i] = ld.rdif_a;
-          tdif_a[i] = ld.tdif_a;
-          trnlay[i] = ld.trnlay;
-          rdir[i] = ld.rdir;
-          tdir[i] = ld.tdir;
-          const double R1 = rdif_a[i];
-          const double T1 = tdif_a[i];
-          double swt = 0.0, smr = 0.0, smt = 0.0;
-#pragma unroll 1
-          for (int ng = 0; ng < 8; ng += 2) {
-            const double mu0 = gauspt[ng], gwt0 = gauswt[ng], mu1 = gauspt[ng + 1], gwt1 = gauswt[ng + 1];
-            const GaussPair g = snicar_gauss_pair_inl(ts, ws, gs, lm, R1, T1, mu0, mu1, exp_min);
-            swt = swt + mu0 * gwt0;
-            smr = smr + mu0 * g.rdr0 * gwt0;
-            smt = smt + mu0 * g.tdr0 * gwt0;
-            swt = swt + mu1 * gwt1;
-            smr = smr + mu1 * g.rdr1 * gwt1;
-            smt = smt + mu1 * g.tdr1 * gwt1;
-          }
-          rdif_a[i] = smr / swt;
-          tdif_a[i] = smt / swt;
-          rdif_b[i] = rdif_a[i];
-          tdif_b[i] = tdif_a[i];
-        }
-        trndir[i + 1] = trndir[i] * trnlay[i];
-        const double refkm1 = 1.0 / (1.0 - rdndif[i] * rdif_a[i]);
-        const double tdrrdir = trndir[i] * rdir[i];
-        const double tdndif = trntdr[i] - trndir[i];
-        trntdr[i + 1] = trndir[i] * tdir[i] + (tdndif + tdrrdir * rdndif[i]) * refkm1 * tdif_a[i];
-        rdndif[i + 1] = rdif_b[i] + (tdif_b[i] * rdndif[i] * refkm1 * tdif_a[i]);
-        trndif[i + 1] = trndif[i] * refkm1 * tdif_a[i];
+ELMK_SNICAR_LOOP
+      for (int j = 0; j < NAER; ++j) {
+        double ss, as, ex;
+        if (j == 0) { ss = T.bc[0][0][idx_nclrds][b]; as = T.bc[0][1][idx_nclrds][b]; ex = T.bc[0][2][idx_nclrds][b] * enh; }
+        else if (j == 1) { ss = T.bc[1][0][idx_nclrds][b]; as = T.bc[1][1][idx_nclrds][b]; ex = T.bc[1][2][idx_nclrds][b]; }
+        else { ss = T.aer_band[j - 2][0][b]; as = T.aer_band[j - 2][1][b]; ex = T.aer_band[j - 2][2][b]; }
+        const double L_aer = L_snw * cnc[j];
+        const double tau_aer = L_aer * ex;
+        tau_sum += tau_aer;
+        omega_sum += (tau_aer * ss);
+        g_sum += (tau_aer * ss * as);
       }
+      const double tau = tau_sum + tau_snw;
+      const double omega = (1.0 / tau) * (omega_sum + (ss_snw * tau_snw));
+      const double g = (1.0 / (tau * omega)) * (g_sum + (asm_snw * ss_snw * tau_snw));
+      gs_[i] = g / (1.0 + g);
+      ws_[i] = ((1.0 - sq(g)) * omega) / (1.0 - (omega * sq(g)));
+      ts_[i] = (1.0 - (omega * sq(g))) * tau;
     }
-
-    // underlying ground: VIS albedo for band 0, NIR otherwise (:526-531)
-    rupdir[NLEVSNO] = (b == 0) ? albsoi[0] : albsoi[1];
-    rupdif[NLEVSNO] = rupdir[NLEVSNO];
-#pragma unroll
-    for (int i = NLEVSNO - 1; i >= 0; --i) {
-      if (i >= top) {
-        const double refkp1 = 1.0 / (1.0 - rdif_b[i] * rupdif[i + 1]);
-        rupdir[i] = rdir[i] + (trnlay[i] * rupdir[i + 1] + (tdir[i] - trnlay[i]) * rupdif[i + 1]) * refkp1 * tdif_b[i];
-        rupdif[i] = rdif_a[i] + tdif_a[i] * rupdif[i + 1] * refkp1 * tdif_b[i];
-      }
-    }
-
-    // net (down - up) flux at every interface; absorbed flux per layer
-    double dftmp[NLEVSNO + 1];
-    double albedo = 0.0, F_sfc_pls = 0.0;
-#pragma unroll
-    for (int i = 0; i <= NLEVSNO; ++i) {
-      dftmp[i] = 0.0;
-      if (i >= top) {
-        const double refk = 1.0 / (1.0 - rdndif[i] * rupdif[i]);
-        double dfdir = trndir[i] + (trntdr[i] - trndir[i]) * (1.0 - rupdif[i]) * refk -
-                       trndir[i] * rupdir[i] * (1.0 - rdndif[i]) * refk;
-        if (dfdir < puny) dfdir = 0.0;
-        double dfdif = trndif[i] * (1.0 - rupdif[i]) * refk;
-        if (dfdif < puny) dfdif = 0.0;
-        dftmp[i] = (flg == 1) ? dfdir : dfdif;
-        if (i == top) {
-          if (flg == 1) {
-            albedo = rupdir[i];
-            F_sfc_pls = (trndir[i] * rupdir[i] + (trntdr[i] - trndir[i]) * rupdif[i]) * refk;
-          } else {
-            albedo = rupdif[i];
-            F_sfc_pls = trndif[i] * rupdif[i] * refk;
-          }
-        }
-      }
-    }
-    double F_abs_sum = 0.0;
-#pragma unroll
-    for (int i = 0; i < NLEVSNO; ++i) {
-      if (i >= top) {
-        const double F_abs = dftmp[i] - dftmp[i + 1];
-        flx_abs_lcl[i][b] = F_abs;
-        if (F_abs < -0.00001) err |= ERR_SNICAR_NEGABS;
-        F_abs_sum = F_abs_sum + F_abs;
-      }
-    }
-    const double F_btm_net = dftmp[NLEVSNO];
-    flx_abs_lcl[NLEVSNO][b] = F_btm_net;
-    // (flg_nosnl == 1 re-stores the same two values, :628-639)
-#pragma unroll
-    for (int i = 0; i <= NLEVSNO; ++i)
-      if (i >= top && flx_abs_lcl[i][b] < 0.0) flx_abs_lcl[i][b] = 0.0;
-    const double energy_sum = (mu_not * PI * flx_slrd) + flx_slri - (F_abs_sum + F_btm_net + F_sfc_pls);
-    if (fabs(energy_sum) > 0.00001) err |= ERR_SNICAR_ENERGY;
-    albout_lcl[b] = albedo;
-    if (albedo > 1.0) err |= ERR_SNICAR_ALBEDO;
   }
-  (void)flg_nosnl;
 
-  // ---- band weighting to VIS / NIR (snow_albedo_radiation_factor :706-760) ----
+  // ---- Delta-Eddington adding-doubling (:384-666) ----
+  double trndir[NLEVSNO + 1], trntdr[NLEVSNO + 1], trndif[NLEVSNO + 1], rupdir[NLEVSNO + 1], rupdif[NLEVSNO + 1],
+      rdndif[NLEVSNO + 1];
+  double rdir[NLEVSNO], rdif_a[NLEVSNO], rdif_b[NLEVSNO], tdir[NLEVSNO], tdif_a[NLEVSNO], tdif_b[NLEVSNO],
+      trnlay[NLEVSNO];
+ELMK_SNICAR_LOOP
+  for (int i = 0; i <= NLEVSNO; ++i) {
+    trndir[i] = 0.0; trntdr[i] = 0.0; trndif[i] = 0.0; rupdir[i] = 0.0; rupdif[i] = 0.0; rdndif[i] = 0.0;
+  }
+ELMK_SNICAR_LOOP
+  for (int i = 0; i <= NLEVSNO; ++i)
+    if (i == top) { trndir[i] = 1.0; trntdr[i] = 1.0; trndif[i] = 1.0; rdndif[i] = 0.0; }
+
+ELMK_SNICAR_LOOP
+  for (int i = 0; i < NLEVSNO; ++i) {
+    rdir[i] = 0.0; rdif_a[i] = 0.0; rdif_b[i] = 0.0; tdir[i] = 0.0; tdif_a[i] = 0.0; tdif_b[i] = 0.0; trnlay[i] = 0.0;
+    if (i >= top) {
+      if (trntdr[i] > trmin) {
+        const double ts = ts_[i], ws = ws_[i], gs = gs_[i];
+        const LayerDirect ld = snicar_layer_direct_inl(ts, ws, gs, mu_not, exp_min);
+        const double lm = ld.lm;
+        rdif_a[i] = ld.rdif_a;
+        tdif_a[i] = ld.tdif_a;
+        trnlay[i] = ld.trnlay;
+        rdir[i] = ld.rdir;
+        tdir[i] = ld.tdir;
+        const double R1 = rdif_a[i];
+        const double T1 = tdif_a[i];
+        double swt = 0.0, smr = 0.0, smt = 0.0;
+#pragma unroll 1
+        for (int ng = 0; ng < 8; ng += 2) {
+          const double mu0 = gauspt[ng], gwt0 = gauswt[ng], mu1 = gauspt[ng + 1], gwt1 = gauswt[ng + 1];
+          const GaussPair g = snicar_gauss_pair_inl(ts, ws, gs, lm, R1, T1, mu0, mu1, exp_min);
+          swt = swt + mu0 * gwt0;
+          smr = smr + mu0 * g.rdr0 * gwt0;
+          smt = smt + mu0 * g.tdr0 * gwt0;
+          swt = swt + mu1 * gwt1;
+          smr = smr + mu1 * g.rdr1 * gwt1;
+          smt = smt + mu1 * g.tdr1 * gwt1;
+        }
+        rdif_a[i] = smr / swt;
+        tdif_a[i] = smt / swt;
+        rdif_b[i] = rdif_a[i];
+        tdif_b[i] = tdif_a[i];
+      }
+      trndir[i + 1] = trndir[i] * trnlay[i];
+      const double refkm1 = 1.0 / (1.0 - rdndif[i] * rdif_a[i]);
+      const double tdrrdir = trndir[i] * rdir[i];
+      const double tdndif = trntdr[i] - trndir[i];
+      trntdr[i + 1] = trndir[i] * tdir[i] + (tdndif + tdrrdir * rdndif[i]) * refkm1 * tdif_a[i];
+      rdndif[i + 1] = rdif_b[i] + (tdif_b[i] * rdndif[i] * refkm1 * tdif_a[i]);
+      trndif[i + 1] = trndif[i] * refkm1 * tdif_a[i];
+    }
+  }
+
+  // underlying ground: VIS albedo for band 0, NIR otherwise (:526-531)
+  rupdir[NLEVSNO] = (b == 0) ? albsoi[0] : albsoi[1];
+  rupdif[NLEVSNO] = rupdir[NLEVSNO];
+ELMK_SNICAR_LOOP
+  for (int i = NLEVSNO - 1; i >= 0; --i) {
+    if (i >= top) {
+      const double refkp1 = 1.0 / (1.0 - rdif_b[i] * rupdif[i + 1]);
+      rupdir[i] = rdir[i] + (trnlay[i] * rupdir[i + 1] + (tdir[i] - trnlay[i]) * rupdif[i + 1]) * refkp1 * tdif_b[i];
+      rupdif[i] = rdif_a[i] + tdif_a[i] * rupdif[i + 1] * refkp1 * tdif_b[i];
+    }
+  }
+
+  // net (down - up) flux at every interface; absorbed flux per layer
+  double dftmp[NLEVSNO + 1];
+  double albedo = 0.0, F_sfc_pls = 0.0;
+ELMK_SNICAR_LOOP
+  for (int i = 0; i <= NLEVSNO; ++i) {
+    dftmp[i] = 0.0;
+    if (i >= top) {
+      const double refk = 1.0 / (1.0 - rdndif[i] * rupdif[i]);
+      double dfdir = trndir[i] + (trntdr[i] - trndir[i]) * (1.0 - rupdif[i]) * refk -
+                     trndir[i] * rupdir[i] * (1.0 - rdndif[i]) * refk;
+      if (dfdir < puny) dfdir = 0.0;
+      double dfdif = trndif[i] * (1.0 - rupdif[i]) * refk;
+      if (dfdif < puny) dfdif = 0.0;
+      dftmp[i] = (flg == 1) ? dfdir : dfdif;
+      if (i == top) {
+        if (flg == 1) {
+          albedo = rupdir[i];
+          F_sfc_pls = (trndir[i] * rupdir[i] + (trntdr[i] - trndir[i]) * rupdif[i]) * refk;
+        } else {
+          albedo = rupdif[i];
+          F_sfc_pls = trndif[i] * rupdif[i] * refk;
+        }
+      }
+    }
+  }
+  double F_abs_sum = 0.0;
+ELMK_SNICAR_LOOP
+  for (int i = 0; i <= NLEVSNO; ++i) flx_abs_b[i] = 0.0;
+ELMK_SNICAR_LOOP
+  for (int i = 0; i < NLEVSNO; ++i) {
+    if (i >= top) {
+      const double F_abs = dftmp[i] - dftmp[i + 1];
+      flx_abs_b[i] = F_abs;
+      if (F_abs < -0.00001) err |= ERR_SNICAR_NEGABS;
+      F_abs_sum = F_abs_sum + F_abs;
+    }
+  }
+  const double F_btm_net = dftmp[NLEVSNO];
+  flx_abs_b[NLEVSNO] = F_btm_net;
+  // (flg_nosnl == 1 re-stores the same two values, :628-639)
+ELMK_SNICAR_LOOP
+  for (int i = 0; i <= NLEVSNO; ++i)
+    if (i >= top && flx_abs_b[i] < 0.0) flx_abs_b[i] = 0.0;
+  const double energy_sum = (mu_not * PI * flx_slrd) + flx_slri - (F_abs_sum + F_btm_net + F_sfc_pls);
+  if (fabs(energy_sum) > 0.00001) err |= ERR_SNICAR_ENERGY;
+  albedo_out = albedo;
+  if (albedo > 1.0) err |= ERR_SNICAR_ALBEDO;
+}
+
+// Band weighting of the five band results to VIS / NIR (snow_albedo_radiation_factor :706-760).
+// albout[b], flx_abs_lcl[i][b]: the band results; alb_out[2], flx_abs[6][2]: VIS / NIR (flx_abs zero on entry).
+ELMK_HD void snicar_combine(const int flg, const double mu_not, const int top, const int rds_top,
+                            const double (&albout_lcl)[NBND_SNW], const double (&flx_abs_lcl)[NLEVSNO + 1][NBND_SNW],
+                            double (&alb_out)[NUMRAD], double (&flx_abs)[NLEVSNO + 1][NUMRAD])
+{
   double wgt[NBND_SNW];
   wgt[0] = 1.0;
   if (flg == 1) {
@@ -351,9 +370,6 @@ ELMK_HD_NOINLINE void snicar_solve(const Cols& S, const Tables& T, const int c, 
   if ((mu_not < 0.2588) && (flg == 1)) {
     const double sza_c1 = 0.085730 + -0.630883 * mu_not + 1.303723 * sq(mu_not);
     const double sza_c0 = 1.467291 + -3.338043 * mu_not + 6.807489 * sq(mu_not);
-    int rds_top = 0;
-#pragma unroll
-    for (int i = 0; i < NLEVSNO; ++i) if (i == top) rds_top = rds[i];
     const double sza_factor = sza_c1 * (m_log10(rds_top * 1.0) - 6.0) + sza_c0;
     const double adjust = alb_out[1] * (sza_factor - 1.0) * wgt_sum;
     alb_out[1] *= sza_factor;
@@ -362,11 +378,53 @@ ELMK_HD_NOINLINE void snicar_solve(const Cols& S, const Tables& T, const int c, 
   }
 }
 
+// SNICAR for one incident-flux type, all five bands by one thread.  Outputs: alb_out[2] (VIS, NIR) and flx_abs[6][2]
+// (five snow slots + ground, VIS/NIR), both already zero on entry.
+ELMK_HD_NOINLINE void snicar_solve(const Cols& S, const Tables& T, const int c, const int flg, const double coszen,
+                          const double h2osno, const int snl, const double (&albsoi)[NUMRAD], double (&alb_out)[NUMRAD],
+                          double (&flx_abs)[NLEVSNO + 1][NUMRAD], uint32_t& err)
+{
+  using namespace alb;
+  if (!((coszen > 0.0) && (h2osno > MIN_SNW))) {
+    // snow_albedo_radiation_factor :762-768
+    if ((coszen > 0.0) && (h2osno < MIN_SNW) && (h2osno > 0.0)) {
+      alb_out[0] = albsoi[0];
+      alb_out[1] = albsoi[1];
+    } else {
+      alb_out[0] = 0.0;
+      alb_out[1] = 0.0;
+    }
+    return;
+  }
+  SnicarColumn K;
+  snicar_column(S, c, h2osno, snl, K, err);
+  if (err & ERR_SNICAR_RADIUS) return;   // the reference throws here; a table gather would be out of range
+  const double mu_not = dmax(coszen, 0.01);
+  double albout_lcl[NBND_SNW];
+  double flx_abs_lcl[NLEVSNO + 1][NBND_SNW];
+  const auto cnc_of = [&](const int i, double (&cnc)[NAER]) { snicar_cnc(S, c, i, cnc); };
+#pragma unroll 1
+  for (int b = 0; b < NBND_SNW; ++b) {
+    double fb[NLEVSNO + 1];
+    snicar_band(T, K, flg, b, mu_not, albsoi, cnc_of, albout_lcl[b], fb, err);
+#pragma unroll
+    for (int i = 0; i <= NLEVSNO; ++i) flx_abs_lcl[i][b] = fb[i];
+  }
+  int rds_top = 0;
+#pragma unroll
+  for (int i = 0; i < NLEVSNO; ++i) if (i == K.top) rds_top = K.rds[i];
+  snicar_combine(flg, mu_not, K.top, rds_top, albout_lcl, flx_abs_lcl, alb_out, flx_abs);
+}
+
 // two-stream canopy solution for one waveband; returns through references (two_stream_solver :391-498)
 struct TwoStreamCommon {
   double cosz, chil, gdir, twostext, avmu, temp0, temp2, wl, ws;
 };
 
+// SNICAR_DONE: the SNICAR kernel of the CUDA library has already run for this step and left albsnd / albsni and the
+// four flx_abs* fields of the sunlit snow columns in the state (elmk_lib.cu, k_snicar); they are read back instead of
+// being recomputed.
+template <bool SNICAR_DONE = false>
 ELMK_HD void column_albedo(const Cols& S, const Tables& T, const int c)
 {
   using namespace alb;
@@ -409,21 +467,12 @@ ELMK_HD void column_albedo(const Cols& S, const Tables& T, const int c)
   for (int i = 0; i <= NLEVSNO; ++i) {
     flx_absd_snw[i][0] = 0.0; flx_absd_snw[i][1] = 0.0; flx_absi_snw[i][0] = 0.0; flx_absi_snw[i][1] = 0.0;
   }
-  if ((coszen > 0.0) && (h2osno > MIN_SNW)) {
-    double cnc[NLEVSNO][NAER];
-#pragma unroll
-    for (int i = 0; i < NLEVSNO; ++i) {
-      cnc[i][0] = C2(cnc_bcphi, i);
-      cnc[i][1] = C2(cnc_bcpho, i);
-      cnc[i][2] = 0.0;   // OC ignored (:144-145)
-      cnc[i][3] = 0.0;
-      cnc[i][4] = C2(cnc_dst1, i);
-      cnc[i][5] = C2(cnc_dst2, i);
-      cnc[i][6] = C2(cnc_dst3, i);
-      cnc[i][7] = C2(cnc_dst4, i);
-    }
-    snicar_solve(S, T, c, 1, coszen, h2osno, snl, albsoi, cnc, albsnd, flx_absd_snw, err);
-    snicar_solve(S, T, c, 2, coszen, h2osno, snl, albsoi, cnc, albsni, flx_absi_snw, err);
+  const bool snicar_ran = SNICAR_DONE && (coszen > 0.0) && (h2osno > MIN_SNW);
+  if (snicar_ran) {
+    albsnd[0] = C2(albsnd, 0); albsnd[1] = C2(albsnd, 1); albsni[0] = C2(albsni, 0); albsni[1] = C2(albsni, 1);
+  } else if ((coszen > 0.0) && (h2osno > MIN_SNW)) {
+    snicar_solve(S, T, c, 1, coszen, h2osno, snl, albsoi, albsnd, flx_absd_snw, err);
+    snicar_solve(S, T, c, 2, coszen, h2osno, snl, albsoi, albsni, flx_absi_snw, err);
   } else if ((coszen > 0.0) && (h2osno < MIN_SNW) && (h2osno > 0.0)) {
     albsnd[0] = albsoi[0]; albsnd[1] = albsoi[1]; albsni[0] = albsoi[0]; albsni[1] = albsoi[1];
   }
@@ -599,11 +648,13 @@ ELMK_HD void column_albedo(const Cols& S, const Tables& T, const int c)
     C2(albd, ib) = albd[ib]; C2(albi, ib) = albi[ib]; C2(fabd, ib) = fabd[ib]; C2(fabi, ib) = fabi[ib];
     C2(fabi_sun, ib) = fabi_sun[ib]; C2(fabi_sha, ib) = fabi_sha[ib];
     C2(ftdd, ib) = ftdd[ib]; C2(ftid, ib) = ftid[ib]; C2(ftii, ib) = ftii[ib];
-    C2(albsnd, ib) = albsnd[ib]; C2(albsni, ib) = albsni[ib];
+    if (!snicar_ran) { C2(albsnd, ib) = albsnd[ib]; C2(albsni, ib) = albsni[ib]; }
   }
+  if (!snicar_ran) {   // (else the SNICAR kernel has stored them)
 #pragma unroll
-  for (int i = 0; i <= NLEVSNO; ++i) {
-    C2(flx_absdv, i) = absdv[i]; C2(flx_absdn, i) = absdn[i]; C2(flx_absiv, i) = absiv[i]; C2(flx_absin, i) = absin[i];
+    for (int i = 0; i <= NLEVSNO; ++i) {
+      C2(flx_absdv, i) = absdv[i]; C2(flx_absdn, i) = absdn[i]; C2(flx_absiv, i) = absiv[i]; C2(flx_absin, i) = absin[i];
+    }
   }
   C1(vcmaxcintsun) = vcsun;
   C1(vcmaxcintsha) = vcsha;

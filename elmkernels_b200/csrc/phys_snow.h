@@ -19,6 +19,12 @@
 #pragma once
 #include "elmk_state.h"
 
+// ELMK_SNOW_ROLLED (experiment): loops over the five snow slots stay loops
+#if defined(__CUDA_ARCH__) && defined(ELMK_SNOW_ROLLED)
+#define ELMK_SNOW_LOOP _Pragma("unroll 1")
+#else
+#define ELMK_SNOW_LOOP _Pragma("unroll")
+#endif
 namespace elmk {
 
 namespace snw {
@@ -87,7 +93,7 @@ ELMK_HD void snow_water(snw::Pack& P, const int capsnow, const double dtime, con
   }
 
   double vol_ice[NS], vol_liq[NS], eff_por[NS];
-#pragma unroll
+ELMK_SNOW_LOOP
   for (int i = 0; i < NS; ++i) {
     vol_ice[i] = 0.0; vol_liq[i] = 0.0; eff_por[i] = 0.0;
     if (i >= top) {
@@ -103,7 +109,7 @@ ELMK_HD void snow_water(snw::Pack& P, const int capsnow, const double dtime, con
   double qin_aer[NMSS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int i = top; i < NS; ++i) {
     P.liq[i] = P.liq[i] + qin;
-#pragma unroll
+ELMK_SNOW_LOOP
     for (int a = 0; a < NMSS; ++a) P.mss[a][i] = P.mss[a][i] + qin_aer[a];
     if (i < NS - 1) {
       if (eff_por[i] < wimp || eff_por[i + 1] < wimp) {
@@ -126,7 +132,7 @@ ELMK_HD void snow_water(snw::Pack& P, const int capsnow, const double dtime, con
     qin = qout;
     double mss_liqice = P.liq[i] + P.ice[i];
     if (mss_liqice < 1.0e-30) mss_liqice = 1.0e-30;
-#pragma unroll
+ELMK_SNOW_LOOP
     for (int a = 0; a < NMSS; ++a) {
       double q = qout * scvng[a] * (P.mss[a][i] / mss_liqice);
       if (q > P.mss[a][i]) q = P.mss[a][i];
@@ -213,7 +219,7 @@ ELMK_HD void combine_layers(snw::Pack& P, const double dtime, double& h2osno, do
       }
       if (i != NS - 1) {
         P.dz[i + 1] += P.dz[i];
-#pragma unroll
+ELMK_SNOW_LOOP
         for (int a = 0; a < NMSS; ++a) P.mss[a][i + 1] += P.mss[a][i];
       }
       const int top = NS - snl;
@@ -222,7 +228,7 @@ ELMK_HD void combine_layers(snw::Pack& P, const double dtime, double& h2osno, do
           P.t[ii] = P.t[ii - 1];
           P.liq[ii] = P.liq[ii - 1];
           P.ice[ii] = P.ice[ii - 1];
-#pragma unroll
+ELMK_SNOW_LOOP
           for (int a = 0; a < NMSS; ++a) P.mss[a][ii] = P.mss[a][ii - 1];
           P.rds[ii] = P.rds[ii - 1];
           P.dz[ii] = P.dz[ii - 1];
@@ -247,9 +253,9 @@ ELMK_HD void combine_layers(snw::Pack& P, const double dtime, double& h2osno, do
   if (snow_depth > 0.0 && ((fse * snow_depth < 0.01) || (h2osno / (fse * snow_depth) < 50.0))) {
     snl = 0;
     h2osno = zwice;
-#pragma unroll
+ELMK_SNOW_LOOP
     for (int i = 0; i < NS; ++i)
-#pragma unroll
+ELMK_SNOW_LOOP
       for (int a = 0; a < NMSS; ++a) P.mss[a][i] = 0.0;
     if (h2osno <= 0.0) snow_depth = 0.0;
     P.liq[NS - 1] = 0.0;
@@ -287,7 +293,7 @@ ELMK_HD void combine_layers(snw::Pack& P, const double dtime, double& h2osno, do
           j = i;
           l = neibor;
         }
-#pragma unroll
+ELMK_SNOW_LOOP
         for (int a = 0; a < NMSS; ++a) P.mss[a][j] += P.mss[a][l];
         P.rds[j] = (P.rds[j] * (P.liq[j] + P.ice[j]) + P.rds[l] * (P.liq[l] + P.ice[l])) /
                    (P.liq[j] + P.ice[j] + P.liq[l] + P.ice[l]);
@@ -301,7 +307,7 @@ ELMK_HD void combine_layers(snw::Pack& P, const double dtime, double& h2osno, do
             P.t[k] = P.t[k - 1];
             P.ice[k] = P.ice[k - 1];
             P.liq[k] = P.liq[k - 1];
-#pragma unroll
+ELMK_SNOW_LOOP
             for (int a = 0; a < NMSS; ++a) P.mss[a][k] = P.mss[a][k - 1];
             P.rds[k] = P.rds[k - 1];
             P.dz[k] = P.dz[k - 1];
@@ -333,15 +339,15 @@ ELMK_HD void divide_excess(const int k, const double keep, double (&dzsno)[snw::
   double zwice = propor * swice[k];
   double zwliq = propor * swliq[k];
   double zm[NMSS];
-#pragma unroll
+ELMK_SNOW_LOOP
   for (int a = 0; a < NMSS; ++a) zm[a] = propor * m[a][k];
   propor = keep / dzsno[k];
   swice[k] *= propor;
   swliq[k] *= propor;
-#pragma unroll
+ELMK_SNOW_LOOP
   for (int a = 0; a < NMSS; ++a) m[a][k] *= propor;
   dzsno[k] = keep;
-#pragma unroll
+ELMK_SNOW_LOOP
   for (int a = 0; a < NMSS; ++a) m[a][k + 1] += zm[a];
   rds[k + 1] = (rds[k + 1] * (swliq[k + 1] + swice[k + 1]) + rds[k] * (zwliq + zwice)) /
                (swliq[k + 1] + swice[k + 1] + zwliq + zwice);
@@ -370,7 +376,7 @@ ELMK_HD void divide_split(const int k, const int tchk, double (&dzsno)[snw::NS],
   } else {
     tsno[k] += dtdz * dzsno[k] / 2.0;
   }
-#pragma unroll
+ELMK_SNOW_LOOP
   for (int a = 0; a < NMSS; ++a) {
     m[a][k] /= 2.0;
     m[a][k + 1] = m[a][k];
@@ -385,10 +391,10 @@ ELMK_HD void divide_layers(snw::Pack& P, const double frac_sno, uint32_t& err)
   const int snl = P.snl;
   int msno = snl;
   int top = NS - snl;
-#pragma unroll
+ELMK_SNOW_LOOP
   for (int i = 0; i < NS; ++i) {
     dzsno[i] = 0.0; swice[i] = 0.0; swliq[i] = 0.0; tsno[i] = 0.0; rds[i] = 0.0;
-#pragma unroll
+ELMK_SNOW_LOOP
     for (int a = 0; a < NMSS; ++a) m[a][i] = 0.0;
   }
   for (int i = 0; i < snl; ++i) {
@@ -396,7 +402,7 @@ ELMK_HD void divide_layers(snw::Pack& P, const double frac_sno, uint32_t& err)
     swice[i] = P.ice[i + top];
     swliq[i] = P.liq[i + top];
     tsno[i] = P.t[i + top];
-#pragma unroll
+ELMK_SNOW_LOOP
     for (int a = 0; a < NMSS; ++a) m[a][i] = P.mss[a][i + top];
     rds[i] = P.rds[i + top];
   }
@@ -411,7 +417,7 @@ ELMK_HD void divide_layers(snw::Pack& P, const double frac_sno, uint32_t& err)
       swice[1] = swice[0];
       swliq[1] = swliq[0];
       tsno[1] = tsno[0];
-#pragma unroll
+ELMK_SNOW_LOOP
       for (int a = 0; a < NMSS; ++a) {
         m[a][0] /= 2.0;
         m[a][1] = m[a][0];
@@ -459,7 +465,7 @@ ELMK_HD void divide_layers(snw::Pack& P, const double frac_sno, uint32_t& err)
     P.ice[i] = swice[i - top];
     P.liq[i] = swliq[i - top];
     P.t[i] = tsno[i - top];
-#pragma unroll
+ELMK_SNOW_LOOP
     for (int a = 0; a < NMSS; ++a) P.mss[a][i] = m[a][i - top];
     P.rds[i] = rds[i - top];
   }
@@ -552,7 +558,7 @@ ELMK_HD void column_snow_hydrology(const Cols& S, const Tables& T, const double 
   uint32_t err = 0;
   Pack P;
   P.snl = C1(snl);
-#pragma unroll
+ELMK_SNOW_LOOP
   for (int i = 0; i <= NS; ++i) {
     P.liq[i] = C2(h2osoi_liq, i);
     P.ice[i] = C2(h2osoi_ice, i);
@@ -560,7 +566,7 @@ ELMK_HD void column_snow_hydrology(const Cols& S, const Tables& T, const double 
     P.dz[i] = C2(dz, i);
     P.zi[i] = C2(zisoi, i);
   }
-#pragma unroll
+ELMK_SNOW_LOOP
   for (int i = 0; i < NS; ++i) {
     P.z[i] = C2(zsoi, i);
     P.rds[i] = C2(snw_rds, i);
@@ -609,13 +615,13 @@ ELMK_HD void column_snow_hydrology(const Cols& S, const Tables& T, const double 
   }
   if (C1(veg_active)) {
     const double tran = C1(qflx_tran_veg);
-#pragma unroll
+ELMK_SNOW_LOOP
     for (int i = 0; i < NLEVSOI; ++i) C2(qflx_rootsoi, i) = C2(rootr, i) * tran;
   }
   {
     int imelt[NS];
     double swe_old[NS];
-#pragma unroll
+ELMK_SNOW_LOOP
     for (int i = 0; i < NS; ++i) {
       imelt[i] = C2(imelt, i);
       swe_old[i] = C2(swe_old, i);
@@ -638,14 +644,14 @@ ELMK_HD void column_snow_hydrology(const Cols& S, const Tables& T, const double 
     // (masses and concentrations are final here - snow_aging does not touch them - and go straight to memory:
     //  thirty fewer doubles to carry through the last stage)
     const int snotop = NS - P.snl;
-#pragma unroll
+ELMK_SNOW_LOOP
     for (int sl = 0; sl < NS; ++sl) {
       const double snowmass = (sl < snotop) ? 1.e-12 : P.ice[sl] + P.liq[sl];
       const double scl = (sl == snotop && capsnow) ? (snowmass / (snowmass + q_snwcp_ice * dtime))
                                                    : ((sl < snotop) ? 0.0 : 1.0);
       const double inv = 1.0 / snowmass;
       double m[NMSS];
-#pragma unroll
+ELMK_SNOW_LOOP
       for (int a = 0; a < NMSS; ++a) m[a] = P.mss[a][sl] * scl;
       C2(mss_bcphi, sl) = m[0]; C2(cnc_bcphi, sl) = m[0] * inv;
       C2(mss_bcpho, sl) = m[1]; C2(cnc_bcpho, sl) = m[1] * inv;
@@ -659,19 +665,19 @@ ELMK_HD void column_snow_hydrology(const Cols& S, const Tables& T, const double 
   // -- launch 5: snow_aging --
   {
     double snofrz_lyr[NS];
-#pragma unroll
+ELMK_SNOW_LOOP
     for (int i = 0; i < NS; ++i) snofrz_lyr[i] = C2(qflx_snofrz_lyr, i);
     snow_aging(P, T, capsnow, frac_sno, dtime, q_snwcp_ice, C1(qflx_snow_grnd), h2osno, snofrz_lyr, err);
   }
 
   // ---- write back ----
   C1(snl) = P.snl;
-#pragma unroll
+ELMK_SNOW_LOOP
   for (int i = 0; i <= NS; ++i) {
     C2(h2osoi_liq, i) = P.liq[i];
     C2(h2osoi_ice, i) = P.ice[i];
   }
-#pragma unroll
+ELMK_SNOW_LOOP
   for (int i = 0; i < NS; ++i) {
     C2(t_soisno, i) = P.t[i];
     C2(dz, i) = P.dz[i];

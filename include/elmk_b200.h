@@ -237,6 +237,14 @@ int elmk_init_timestep(elmk_handle h, int reset_forc_hgt);
 /* ---- one pass of the selected kernel groups over all columns, asynchronous on the
  *      handle's stream: replaces the 11 wrapper calls of ELMInterface::advance ---- */
 int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_t group_mask);
+
+/* Launch plan of elmk_step.  ELMK_PLAN_FUSED (default): the production plan - fused launches, the SNICAR kernel with
+ * one lane per (column, flux type, band), the re-packed CanopyFluxes iteration.  ELMK_PLAN_SPLIT: one launch per kernel
+ * group with one thread per column, the reference's wrapper granularity (23 parallel_for -> 11 launches); the two plans
+ * give identical bits (tests/test_gpu_parity.py).  Takes effect from the next elmk_step. */
+#define ELMK_PLAN_FUSED 0
+#define ELMK_PLAN_SPLIT 1
+int elmk_set_plan(elmk_handle h, int plan);
 int elmk_sync(elmk_handle h);
 
 /* number of kernel launches issued by this handle since creation (for bench accounting) */
@@ -247,7 +255,8 @@ int64_t elmk_launch_count(elmk_handle h);
  *      Kokkos::parallel_for (e.g. canopy_fluxes_kokkos.cc:264) for the Kokkos profiling tools.
  *      elmk_timing_read synchronises, accumulates the recorded intervals and returns, for up to `max`
  *      distinct launch names, the name, the total milliseconds and the number of launches; the return
- *      value is the number of names (or a negative error).  elmk_timing_enable(h, 0|1) also resets. ---- */
+ *      value is the number of names (or a negative error).  elmk_timing_enable(h, 0|1|2) also resets; 2 times the
+ *      sub-launches of the composite launches as well (group mask 0: "albedo:snicar", "canopy_fluxes:iterate" ...). ---- */
 int elmk_timing_enable(elmk_handle h, int on);
 int elmk_timing_read(elmk_handle h, int max, const char** names, double* total_ms, int64_t* launches,
                      uint32_t* group_masks);

@@ -124,5 +124,22 @@ int main(int argc, char** argv) {
   });
   run2("x = 2, y in [-12, 12]", N, [](double& x, double& y) { x = 2.0; y = uni(-12, 12); });
   run2("overflow / underflow edge", N / 4, [](double& x, double& y) { x = uni(0.5, 40); y = uni(-400, 400); });
+  // pow with a constant base and its logarithm half folded (soil conductivities 0.57^y, 2.29^y; 2^y of photosynthesis)
+  {
+    const double bases[3] = {0.57, 2.29, 2.0};
+    const double folded[3][2] = {{ELMK_POWLOG_0_57}, {ELMK_POWLOG_2_29}, {ELMK_POWLOG_2_0}};
+    for (int k = 0; k < 3; ++k) {
+      double lhi, llo;
+      pow_log(as_u64(bases[k]), lhi, llo);
+      const bool same_consts = same(lhi, folded[k][0]) && same(llo, folded[k][1]);
+      long bad = 0;
+      for (long i = 0; i < N; ++i) {
+        const volatile double y = (i & 1) ? uni(-8, 8) : uni(0, 1);
+        if (!same(g_pow_cbase(bases[k], folded[k][0], folded[k][1], y), pow(bases[k], y))) ++bad;
+      }
+      printf("%-6s base %-4g folded log %-10s n=%ld mismatches=%ld\n", "powc", bases[k], same_consts ? "ok" : "STALE", N, bad + !same_consts);
+      failures += (bad != 0) || !same_consts;
+    }
+  }
   return failures ? 1 : 0;
 }

@@ -98,38 +98,18 @@ def test_full_chain_free_running(cuda_lib, checker, params):
     assert np.allclose(ra[:8], rb[:8], rtol=1e-12, atol=1e-12 * np.max(np.abs(ra[:8])))
 
 
-def test_split_and_fused_plans_agree(cuda_lib, params, monkeypatch):
-    """The fused launch plan and one-launch-per-group give identical bits."""
-    cfg = ensemble.EnsembleConfig(ncols=2048, seed=3, h2osfc_fraction=0.1, soil_temp_spread=5.0)
-    monkeypatch.setenv("ELMK_PLAN", "split")
-    pair = parity.Pair(cuda_lib, cuda_lib, params, cfg)   # a: split plan
-    monkeypatch.delenv("ELMK_PLAN")
-    pair.b.close()
-    pair.b = cuda_lib.columns(cfg.ncols)                   # b: default (fused) plan
-    pair.b.set_tables(params)
-    pair.b.upload_state(pair.state0)
-    for _ in range(6):
-        pair.begin_step()
-        pair.run()
-    assert not pair.compare(0.0)
-    assert pair.b.launch_count < pair.a.launch_count
-
-
-def test_wide_sorting_window_gives_identical_bits(cuda_lib, params, monkeypatch):
-    """Large handles sort 4096-column windows in the radiative-transfer launch; the order in which a block visits its
-    columns must not change any result."""
-    cfg = ensemble.EnsembleConfig(ncols=9000, seed=17, soil_temp_spread=5.0)
-    monkeypatch.setenv("ELMK_RAD_WINDOW", "wide")
-    pair = parity.Pair(cuda_lib, cuda_lib, params, cfg)    # a: wide window
-    monkeypatch.setenv("ELMK_RAD_WINDOW", "narrow")
-    pair.b.close()
-    pair.b = cuda_lib.columns(cfg.ncols)                   # b: 1024-column windows
-    pair.b.set_tables(params)
-    pair.b.upload_state(pair.state0)
-    for _ in range(4):
-        pair.begin_step()
-        pair.run()
-    assert not pair.compare(0.0)
+def test_split_and_fused_plans_agree(cuda_lib, params):
+    """The fused launch plan (SNICAR with one lane per band, re-packed CanopyFluxes, fused launches) and one launch per
+    kernel group with one thread per column give identical bits."""
+    for cfg in (ensemble.EnsembleConfig(ncols=2048, seed=3, h2osfc_fraction=0.1, soil_temp_spread=5.0),
+                ensemble.EnsembleConfig(ncols=3000, seed=17, snow_fraction=1.0, soil_temp_spread=5.0)):
+        pair = parity.Pair(cuda_lib, cuda_lib, params, cfg, night_fraction=0.1)
+        pair.a.set_plan("split")
+        for _ in range(6):
+            pair.begin_step()
+            pair.run()
+        assert not pair.compare()
+        assert pair.b.launch_count < pair.a.launch_count
 
 
 def test_golden_vectors(cuda_lib, params):
