@@ -1,20 +1,34 @@
 #!/usr/bin/env python3
 """Benchmark of the ELM column timestep on B200 (contract: one JSON line on stdout from rank 0).
 
-Workload (BASELINE.json config 5, the configuration the metric "column-steps/sec, full ELM step" is quoted
-on): the full kernel chain of kokkos_driver's timestep - init_timestep bookkeeping + groups a1..a11 - over
-2,097,152 synthetic land columns per GPU (16M columns on 8 GPUs: weak scaling, contiguous column ranges
-per GPU, no collective on the step), state persistent in HBM across steps.
+Default workload = BASELINE.json config 5, the configuration the metric "column-steps/sec, full ELM step" is quoted
+on: the full chain of kokkos_driver's timestep over 2,097,152 synthetic land columns per GPU (16M columns on 8 GPUs:
+weak scaling, contiguous column ranges per GPU, no collective on the step), state persistent in HBM across steps.
+One step = what ELMInterface::advance does for one dt (driver/kokkos/elm_kokkos_interface.cc:269-322), everything
+on the device:
+    elmk_solar_step   coszen of every column (its own latitude / longitude), day lengths
+    elmk_phenology    LAI / SAI / canopy heights from resident monthly values
+    elmk_atm_forcing  the eight forcing functors from resident raw series (forcing refreshed per step on device)
+    elmk_init_timestep, elmk_step(all groups a1..a11)
 
-  value   column-steps/s with the forcing already resident in HBM (device-timed, max over ranks)
-  e2e     the same through the C ABI with HOST buffers: every step uploads that step's atmospheric forcing
-          and phenology (17 fields) from pinned host memory and reads back the eight per-column balance
-          diagnostics + the error word
-  roofline  the dominant kernel of the step: algorithmic bytes per launch (tools/group_bytes.py, element
-          level) / its mean CUDA-event duration, against the measured HBM copy bandwidth
-  cpu_baseline  the reference's own code (oracle/_ref, OpenMP on all host cores) on a bounded sample
+--config 2 | 3 | 4 run the sub-chains of BASELINE.json configs 2-4 through the same entry point (group mask):
+    2  frac_wet + albedo/SNICAR + surface radiation       1,048,576 columns per GPU, 25 % night, 1112 B / column-step
+    3  canopy hydrology + canopy temperature + bare-ground 4,194,304 columns per GPU, half bare, ponds on a fifth, 1249 B
+    4  CanopyFluxes                                        4,194,304 vegetated columns per GPU, 40 % night, all PFTs, 2020 B;
+                                                           the line carries the histogram of stability-iteration passes
 
-`--impl reference` times that CPU path alone, as the reference arm.
+  value     column-steps/s, device-timed (CUDA events on the handle's stream, max over ranks), inputs resident in HBM
+  e2e       the same through the C ABI with HOST buffers inside the timed region: config 5 uploads one new record of
+            each of the seven raw forcing series per step from pinned host memory (elmk_atm_series_row) and reads the
+            eight per-column balance diagnostics + the error word back every step (overlapped exchange); configs 2-4
+            upload the 17 forcing / phenology fields and read back a result field + the error word
+  roofline  the dominant launch: algorithmic bytes per launch / its mean CUDA-event duration, against the measured HBM
+            copy bandwidth; `step` is the same for the whole step with the frozen byte counts of BASELINE.md section 4
+  verify    65,536 columns of this rank's ensemble stepped by oracle/_ref (the reference's own code) beside the GPU,
+            outside the timed region: every field compared bit for bit
+  cpu_baseline  oracle/_ref with OpenMP on all host cores on a bounded sample of the same workload
+
+`--impl reference` times that CPU path alone, as the reference arm (same --config).
 """
 from __future__ import annotations
 
@@ -32,33 +46,44 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-ALGORITHMIC_BYTES_PER_COLUMN_STEP = 6325   # SURVEY.md section 8(d) / BASELINE.md section 4, element level, frozen
-DECLARED_BYTES_PER_COLUMN_STEP = 7201      # declared-extent upper bound IN + 2*PROG + OUT (7117 of SURVEY.md + imelt carried across steps + errmask)
 HBM_FALLBACK_GBS = 6650.0
-METRIC = "column-steps/sec, full ELM step"
 CHUNK = 1 << 18                            # columns generated / uploaded at a time
+DT = 1800.0
+FORC_DT_DAYS = 3.0 / 24.0                  # three-hourly forcing records
+RING = 8                                   # time levels of the resident forcing window (e2e refreshes one per step)
+DOY0 = 195                                 # the run starts on 14 July
 
 FORCING_FIELDS = ("coszen forc_tbot forc_thbot forc_pbot forc_qbot forc_lwrad forc_u forc_v forc_rain forc_snow "
                   "forc_solad forc_solai elai esai frac_veg_nosno_alb").split()
-RESULT_FIELDS = "dtend_column_h2o errh2o errh2osno dwb errsol errlon errseb netrad errmask".split()
+DIAG_FIELDS = "dtend_column_h2o errh2o errh2osno dwb errsol errlon errseb netrad errmask".split()
 
 
-def kernel_counters():
-    """ncu counters of one step of this workload (profiles/r1_kernel_counters.json, written by tools/ncu_counters.py
-    from a capture of `bench.py --ncols 524288 --steps 1`): DRAM bytes and FP64 instructions per column and launch
-    group.  Static evidence committed with the repo - nothing is profiled while the benchmark runs."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_counters.json")))
-    except Exception:
-        return None
+def configs():
+    from elmkernels_b200 import abi
+    return {
+        5: dict(name="full ELM column timestep (solar geometry + phenology + forcing functors + init_timestep + groups "
+                     "a1..a11, BASELINE.json config 5)", metric="column-steps/sec, full ELM step", mask=abi.G_ALL,
+                ncols=1 << 21, bytes=6325, ens=dict(soil_temp_spread=6.0), night=None, out=DIAG_FIELDS),
+        2: dict(name="SurfaceAlbedo + SurfaceRadiation two-stream (groups a1 + a2 + a4, BASELINE.json config 2)",
+                metric="column-steps/sec, albedo + surface radiation", mask=abi.G_FRAC_WET | abi.G_ALBEDO | abi.G_SURFACE_RADIATION,
+                ncols=1 << 20, bytes=1112, ens=dict(), night=0.25, out=["fsa", "fsr", "errmask"]),
+        3: dict(name="CanopyHydrology + CanopyTemperature + BareGroundFluxes (groups a3 + a5 + a6, BASELINE.json config 3)",
+                metric="column-steps/sec, hydrology + temperature + bare-ground fluxes",
+                mask=abi.G_CANOPY_HYDROLOGY | abi.G_CANOPY_TEMPERATURE | abi.G_BAREGROUND_FLUXES, ncols=1 << 22, bytes=1249,
+                ens=dict(bare_fraction=0.5, h2osfc_fraction=0.2), night=None, out=["t_grnd", "eflx_sh_grnd", "errmask"]),
+        4: dict(name="CanopyFluxes stability + photosynthesis iteration, mixed PFTs (group a7, BASELINE.json config 4)",
+                metric="column-steps/sec, CanopyFluxes", mask=abi.G_CANOPY_FLUXES, ncols=1 << 22, bytes=2020,
+                ens=dict(bare_fraction=0.0), night=0.4, out=["t_veg", "eflx_sh_veg", "errmask"]),
+    }
 
 
-def fp64_peak():
-    """Measured FP64 pipe peak of this pool's B200 (tools/fp64_peak.cu -> profiles/r1_fp64_peak.json)."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_peak.json")))
-    except Exception:
-        return None
+def static_json(*names):
+    for n in names:
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", n))), n
+        except Exception:
+            pass
+    return None, None
 
 
 def measured_peak():
@@ -100,18 +125,159 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_chunk(params, fields, ncols, seed):
+# ---- the synthetic workload: a deterministic function of (rank, chunk), the same on the GPU and on the CPU checker ----
+def chunk_seed(rank, chunk):
+    return 20240000 + 5 + 7919 * (rank * 64 + chunk)
+
+
+def make_chunk(P, fields, ncols, seed, cfg):
     from elmkernels_b200 import ensemble
-    cfg = ensemble.EnsembleConfig(ncols=ncols, seed=seed, soil_temp_spread=6.0)
-    st = ensemble.make_state(cfg, params, fields)
-    forcing = ensemble.Forcing(ncols, seed=seed + 1)
-    return st, forcing
+    st = ensemble.make_state(ensemble.EnsembleConfig(ncols=ncols, seed=seed, **cfg["ens"]), P, fields)
+    return st, ensemble.Forcing(ncols, seed=seed + 1, night_fraction=cfg["night"])
 
 
-def use_all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms are meant to use every host core."""
-    n = os.cpu_count() or 1
+def chunk_series(ncols, seed, ntimes):
+    """Raw forcing series (ntimes, ncols) and monthly phenology (3, ncols) + coordinates of one chunk."""
+    r = np.random.default_rng(seed + 2)
+    hours = np.arange(ntimes)[:, None] * 3.0
+    tb = 270.0 + r.uniform(-12, 12, ncols)[None, :] + 5.0 * np.sin(2 * np.pi * (hours - 9.0) / 24.0)
+    atm = {
+        "TBOT": tb,
+        "PBOT": np.broadcast_to(r.uniform(95000.0, 103000.0, ncols)[None, :], (ntimes, ncols)).copy(),
+        "QBOT": r.uniform(40.0, 95.0, (ntimes, ncols)),                      # relative humidity, percent
+        "FLDS": r.uniform(180.0, 380.0, (ntimes, ncols)),
+        "FSDS": r.uniform(200.0, 800.0, (ntimes, ncols)),                    # scaled by the cosine of the zenith angle on the device
+        "PREC": np.where(r.uniform(size=(ntimes, ncols)) < 0.3, r.uniform(0.0, 4e-4, (ntimes, ncols)), 0.0),
+        "WIND": r.uniform(0.5, 7.0, (ntimes, ncols)),
+    }
+    lai = np.where(r.uniform(size=ncols) < 0.2, 0.0, r.uniform(0.3, 4.0, ncols))[None, :] * np.array([0.8, 1.0, 1.2])[:, None]
+    phen = {"MLAI": lai, "MSAI": 0.25 * lai + 0.1 * (lai > 0),
+            "MHTOP": np.broadcast_to(r.uniform(0.2, 2.2, ncols), (3, ncols)).copy(),
+            "MHBOT": np.broadcast_to(r.uniform(0.01, 0.15, ncols), (3, ncols)).copy()}
+    lat, lon = np.deg2rad(r.uniform(-65.0, 72.0, ncols)), np.deg2rad(r.uniform(-180.0, 180.0, ncols))
+    return atm, phen, lat, lon
+
+
+class Workload:
+    """One handle (GPU or CPU checker) carrying columns [0, n) of this rank's ensemble, stepped through the C ABI."""
+
+    def __init__(self, lib, P, cfg, key, n, rank, device=0, pinned=None, gen_n=None):
+        """gen_n: column count of the handle whose first n columns this one mirrors (the generator draws whole chunks:
+        a checker that carries a subsample has to draw the same chunk and keep its head)."""
+        from elmkernels_b200 import forcing
+        self.F, self.cfg, self.key, self.n = forcing, cfg, key, n
+        self.cols = lib.columns(n, device=device)
+        self.cols.set_tables(P)
+        self.step_no = 0
+        full = key == 5
+        ntimes = RING
+        atm = {k: np.empty((ntimes, n)) for k in self.cols.ATM_VARS} if full else None
+        phen = {k: np.empty((3, n)) for k in self.cols.PHEN_VARS} if full else None
+        lat, lon = (np.empty(n), np.empty(n)) if full else (None, None)
+        self.forc_host = pinned    # {field: pinned array [n(,nlev)]} filled here when given (configs 2-4 e2e)
+        gen_n = gen_n or n
+        for c0 in range(0, n, CHUNK):
+            m = min(CHUNK, n - c0)
+            mg = min(CHUNK, gen_n - c0)      # columns the generator draws for this chunk
+            seed = chunk_seed(rank, c0 // CHUNK)
+            st, fg = make_chunk(P, lib.fields, mg, seed, cfg)
+            f = fg.at(12 + (c0 // CHUNK) % 24, st)
+            if m < mg:
+                st = {k: np.ascontiguousarray(v[:m]) for k, v in st.items()}
+                f = {k: np.ascontiguousarray(v[:m]) for k, v in f.items()}
+            self.cols.upload_state(st, col0=c0)
+            self.cols.upload_state(f, col0=c0)
+            if pinned is not None:
+                for k in FORCING_FIELDS:
+                    pinned[k][c0:c0 + m] = f[k]
+            if full:
+                a, p, la, lo = chunk_series(mg, seed, ntimes)
+                for k in atm:
+                    atm[k][:, c0:c0 + m] = a[k][:, :m]
+                for k in phen:
+                    phen[k][:, c0:c0 + m] = p[k][:, :m]
+                lat[c0:c0 + m], lon[c0:c0 + m] = la[:m], lo[:m]
+            del st, f
+        if full:
+            for k, v in atm.items():
+                self.cols.atm_series(k, v)
+            for k, v in phen.items():
+                self.cols.phen_series(k, v)
+            self.cols.set_coordinates(lat, lon)
+        self.saved = None
+        if key == 4:
+            # CanopyFluxes starts every step from the same leaf temperature and canopy water (else the second step finds
+            # the first one's converged answer and the iteration is over at once): its four read-write scalars are
+            # restored before every step, inside the timed region
+            self.rw = ("t_veg", "h2ocan", "displa", "z0mv")
+        if key in (2, 3, 4):
+            self.spin_up()
+
+    def spin_up(self):
+        """Two steps of the whole chain so that the sub-chain sees realistic inputs; for configs 3
+        and 4 the groups that precede theirs in the chain run once more on the forcing of the timed steps."""
+        from elmkernels_b200 import abi
+        for _ in range(2):
+            self.cols.init_timestep(True)
+            self.cols.step()
+        self.cols.init_timestep(True)
+        before = {2: 0, 3: abi.G_FRAC_WET | abi.G_ALBEDO,
+                  4: abi.G_FRAC_WET | abi.G_ALBEDO | abi.G_CANOPY_HYDROLOGY | abi.G_SURFACE_RADIATION |
+                  abi.G_CANOPY_TEMPERATURE | abi.G_BAREGROUND_FLUXES}[self.key]
+        if before:
+            self.cols.step(groups=before)
+        if self.key == 4:
+            self.saved = {k: self.cols.download(k) for k in self.rw}
+            self.restore = None
+            if self.cols.lib.backend.startswith("cuda"):
+                # device-resident copies, restored with device-to-device copies on the handle's stream
+                import torch
+                dev = torch.device("cuda", torch.cuda.current_device())
+                stream = torch.cuda.ExternalStream(self.cols.stream, device=dev)
+
+                class Raw:   # a field of the handle as a CUDA array
+                    def __init__(self, ptr, n):
+                        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+                views = {k: torch.as_tensor(Raw(self.cols.device_ptr(k)[0], self.n), device=dev) for k in self.rw}
+                keep = {k: v.clone() for k, v in views.items()}
+
+                def restore():
+                    with torch.cuda.stream(stream):
+                        for k in self.rw:
+                            views[k].copy_(keep[k], non_blocking=True)
+                self.restore = restore
+
+    def step(self):
+        c = self.cols
+        if self.key == 5:
+            sec = self.step_no * DT
+            dayl, max_dayl = c.solar_step(DT, DOY0 + sec / 86400.0 + 1.0, DOY0 + 1 + int(sec // 86400))
+            m1 = self.F.first_month_idx(7, 14, sec % 86400.0) - 5     # the series hold June, July, August
+            pw1, pw2 = self.F.monthly_data_weights(7, 14, sec % 86400.0)
+            c.phenology(m1, pw1, pw2)
+            t_idx, w1, w2 = self.F.forcing_time_weights((sec + DT / 2.0) / 86400.0, FORC_DT_DAYS)
+            c.atm_forcing(t_idx % (RING - 1), w1, w2, True)           # the resident window is a ring of records
+            c.init_timestep(False)
+            c.step(dtime=DT, dayl=dayl, max_dayl=max_dayl)
+        else:
+            if self.key == 4:
+                if self.restore:
+                    self.restore()
+                else:
+                    c.upload_state(self.saved)
+            if self.key == 3:
+                c.init_timestep(True)
+            c.step(dtime=DT, groups=self.cfg["mask"])
+        self.step_no += 1
+
+
+def use_all_host_threads(share=1):
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms are meant to use every host core
+    (bound threads, one per core)."""
+    n = max(1, (os.cpu_count() or 1) // share)
     os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     try:
         import ctypes
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
@@ -120,79 +286,63 @@ def use_all_host_threads():
     return n
 
 
-def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path (oracle/_ref), all host threads."""
-    if rank != 0:
-        return
-    use_all_host_threads()
-    from elmkernels_b200 import abi, params as prm
-    path = os.path.join(ROOT, "oracle", "_ref", "libelmref.so")
-    kind = "reference"
+def checker_library():
+    from elmkernels_b200 import abi
+    os.environ.setdefault("ELMREF_SCRUB_STACK", "1")   # deterministic column order in the oracle (oracle/shim/Kokkos_Core.hpp)
+    path, kind = os.path.join(ROOT, "oracle", "_ref", "libelmref.so"), "reference"
     if not os.path.exists(path):
         path, kind = os.path.join(ROOT, "oracle", "port", "_build", "libelmport.so"), "port"
-    lib = abi.Library(path)
+    if not os.path.exists(path):
+        return None, None
+    return abi.Library(path), kind
+
+
+def time_cpu(P, cfg, key, ncols, steps, warmup):
+    """The reference's own code on a bounded sample: `warmup` untimed steps, then `steps` steps timed one by one;
+    the value is columns / median step time."""
+    cores = use_all_host_threads()
+    lib, kind = checker_library()
+    if lib is None:
+        return None
+    w = Workload(lib, P, cfg, key, ncols, rank=0)
+    for _ in range(warmup):
+        w.step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        w.step()
+        times.append(time.perf_counter() - t0)
+    w.cols.close()
+    med = float(np.median(times))
+    return {"value": ncols / med, "unit": "column-steps/s", "cores": cores, "kind": kind,
+            "sample": f"{ncols} columns of the same synthetic workload, {warmup} warm-up + {steps} timed steps "
+                      f"(median step time), OpenMP bound to all {cores} host cores ({lib.backend})",
+            "ms_per_step": 1e3 * med, "total_s": float(np.sum(times))}
+
+
+def run_reference(args, cfg, rank):
+    if rank != 0:
+        return
+    from elmkernels_b200 import params as prm
     P = prm.load_params()
-    n = args.cpu_cols
-    st, forcing = make_chunk(P, lib.fields, n, 20240000 + 5)
-    cols = lib.columns(n)
-    cols.set_tables(P)
-    cols.upload_state(st)
-    f = forcing.at(12, st)
-    cols.upload_state(f)
-    for _ in range(args.warmup):
-        cols.init_timestep(True)
-        cols.step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cols.init_timestep(True)
-        cols.step()
-    dt = time.perf_counter() - t0
-    cores = os.cpu_count() or 1
-    value = n * args.steps / dt
-    sample = f"{n} columns x {args.steps} steps (of the {args.ncols}-column/GPU workload), {args.warmup} warm-up steps"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "column-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+    b = time_cpu(P, cfg, args.config, args.cpu_cols, args.steps, max(args.warmup, 2))
+    if b is None:
+        print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref nor oracle/port is built"}), flush=True)
+        return
+    line = {"impl": "reference", "metric": cfg["metric"], "value": b["value"], "unit": "column-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 2), "ms_per_step": b["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "full ELM column timestep (init_timestep + groups a1..a11), synthetic mixed-PFT "
-                                   "ensemble with snl 0..5", "columns_per_gpu": args.ncols, "dtime_s": 1800,
-                       "backend": lib.backend},
-            "cpu_baseline": {"value": value, "unit": "column-steps/s", "cores": cores, "kind": kind, "sample": sample},
-            "e2e": {"value": value, "unit": "column-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": {"workload": cfg["name"], "columns_per_gpu": args.ncols, "dtime_s": DT},
+            "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": b["value"], "unit": "column-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(P, ncols, steps=3, warmup=1):
-    from elmkernels_b200 import abi
-    path = os.path.join(ROOT, "oracle", "_ref", "libelmref.so")
-    kind = "reference"
-    if not os.path.exists(path):
-        path, kind = os.path.join(ROOT, "oracle", "port", "_build", "libelmport.so"), "port"
-    if not os.path.exists(path):
-        return None
-    use_all_host_threads()
-    lib = abi.Library(path)
-    st, forcing = make_chunk(P, lib.fields, ncols, 20240000 + 5)
-    cols = lib.columns(ncols)
-    cols.set_tables(P)
-    cols.upload_state(st)
-    cols.upload_state(forcing.at(12, st))
-    for _ in range(warmup):
-        cols.init_timestep(True)
-        cols.step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cols.init_timestep(True)
-        cols.step()
-    dt = time.perf_counter() - t0
-    cols.close()
-    return {"value": ncols * steps / dt, "unit": "column-steps/s", "cores": os.cpu_count() or 1, "kind": kind,
-            "sample": f"{ncols} columns x {steps} steps of the same synthetic ensemble, {warmup} warm-up, "
-                      f"OpenMP over all host cores ({lib.backend})"}
-
-
 def launch_bytes(group_bytes, mask):
     """Algorithmic HBM bytes per column of one launch covering the groups in `mask` (chain order)."""
+    if mask == (1 << 6):
+        return 2020   # CanopyFluxes alone: the frozen figure of BASELINE.md section 4
     produced, rd, wr = {}, 0, {}
     for g, name in enumerate(group_bytes["order"]):
         if not (mask >> g) & 1:
@@ -209,29 +359,63 @@ def launch_bytes(group_bytes, mask):
     return rd + sum(wr.values())
 
 
+def verify(lib, P, cfg, key, rank, gpu: Workload, nv, steps):
+    """Columns [0, nv) of this rank on the CPU checker beside the GPU handle, `steps` steps from the same state: every
+    field bit for bit.  Runs before the timed region (the GPU state simply is `steps` steps older afterwards)."""
+    chk, kind = checker_library()
+    if chk is None:
+        return {"skipped": "no checker library"}
+    use_all_host_threads()
+    ref = Workload(chk, P, cfg, key, nv, rank, gen_n=gpu.n)
+    ref.step_no = gpu.step_no
+    bad, elements = {}, 0
+    for _ in range(steps):
+        ref.step()
+        gpu.step()
+    for k in lib.field_names:
+        a, b = ref.cols.download(k), gpu.cols.download(k, col0=0, n=nv)
+        elements += a.size
+        if a.dtype.kind == "f":
+            m = (a.view(np.uint64) != b.view(np.uint64)) & ~(np.isnan(a) & np.isnan(b))
+        else:
+            m = a != b
+        if m.any():
+            bad[k] = int(m.sum())
+    ea, eb = ref.cols.errors(), gpu.cols.errors()
+    ref.cols.close()
+    return {"columns": nv, "steps": steps, "fields": len(lib.field_names), "elements_compared": elements,
+            "mismatching_elements": int(sum(bad.values())), "mismatching_fields": bad, "bit_identical": not bad,
+            "checker": chk.backend, "kind": kind, "error_words_equal": ea[0] == eb[0]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ncols", type=int, default=1 << 21, help="columns per GPU")
+    ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5], help="BASELINE.json config (default 5: the full step)")
+    ap.add_argument("--ncols", type=int, default=0, help="columns per GPU (default: the size SURVEY.md 8(d) gives the config)")
     ap.add_argument("--cpu-cols", type=int, default=1 << 17, help="columns of the CPU-baseline sample")
+    ap.add_argument("--verify-cols", type=int, default=1 << 16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    cfg = configs()[args.config]
+    args.ncols = args.ncols or cfg["ncols"]
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg, rank)
         return
 
     import torch
     import torch.distributed as dist
     import elmkernels_b200
-    from elmkernels_b200 import abi, params as prm
+    from elmkernels_b200 import params as prm
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -240,36 +424,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = elmkernels_b200.load()
     P = prm.load_params()
-    n = args.ncols
-    cols = lib.columns(n, device=local)
-    cols.set_tables(P)
+    n, key = args.ncols, args.config
 
-    # ---- synthetic ensemble: unique columns, generated and uploaded chunk by chunk ----
-    forc_host = {}
-    for k in FORCING_FIELDS:
-        _, dt, nl = lib.fields[k]
-        t = torch.empty((n,) if nl == 1 else (n, nl), dtype={0: torch.float64, 1: torch.int32, 2: torch.uint8}[dt],
-                        pin_memory=True)
-        forc_host[k] = t.numpy()
-    for c0 in range(0, n, CHUNK):
-        m = min(CHUNK, n - c0)
-        st, forcing = make_chunk(P, lib.fields, m, 20240000 + 5 + 7919 * (rank * 64 + c0 // CHUNK))
-        cols.upload_state(st, col0=c0)
-        f = forcing.at(12 + (c0 // CHUNK) % 24, st)
-        for k in FORCING_FIELDS:
-            forc_host[k][c0:c0 + m] = f[k]
-        del st, f
-    up_plan = cols.plan(FORCING_FIELDS, [forc_host[k] for k in FORCING_FIELDS])
-    res_host = {}
-    for k in RESULT_FIELDS:
-        _, dt, nl = lib.fields[k]
-        res_host[k] = torch.empty((n,), dtype={0: torch.float64, 1: torch.int32}[dt], pin_memory=True).numpy()
-    down_plan = cols.plan(RESULT_FIELDS, [res_host[k] for k in RESULT_FIELDS])
-    h2d = sum(a.nbytes for a in forc_host.values())
-    d2h = sum(a.nbytes for a in res_host.values())
-    cols.upload_many(up_plan)
+    def pinned(name, rows=None):
+        _, dt, nl = lib.fields[name]
+        shape = (n,) if nl == 1 else (n, nl)
+        return torch.empty(shape, dtype={0: torch.float64, 1: torch.int32, 2: torch.uint8}[dt], pin_memory=True).numpy()
+
+    forc_host = {k: pinned(k) for k in FORCING_FIELDS} if key != 5 else None
+    W = Workload(lib, P, cfg, key, n, rank, device=local, pinned=forc_host)
+    cols = W.cols
     cols.sync()
-
     stream = torch.cuda.ExternalStream(cols.stream, device=torch.device("cuda", local))
 
     def barrier():
@@ -277,19 +442,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step():
-        cols.init_timestep(True)
-        cols.step()
+    # ---- parity beside the measurement: a subsample of this rank's columns on the reference's own code ----
+    check = None
+    if not args.no_verify:
+        check = verify(lib, P, cfg, key, rank, W, min(args.verify_cols, n), steps=2)
 
     # ---- warm-up ----
     for _ in range(args.warmup):
-        one_step()
+        W.step()
     cols.sync()
     any_err, first = cols.errors()
     if any_err:
         raise SystemExit(f"column error bits {any_err:#x} (first column {first}) during warm-up")
 
-    # ---- timed region: K steps, forcing resident in HBM ----
+    # ---- timed region: K steps, inputs resident in HBM ----
     sampler = ClockSampler(local)
     sampler.start()
     cols.timing(2 if os.environ.get("ELMK_TIMING_DETAIL") else True)
@@ -298,38 +464,57 @@ def main():
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
-        one_step()
+        W.step()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = cols.launch_count - l0
     kern = cols.timing_read()
     cols.timing(False)
+    hist = cols.canflux_pass_histogram() if key in (4, 5) else None
 
-    # ---- end to end: host forcing in, per-column diagnostics out, every step ----
-    # Through the overlapped exchange of the C ABI (elmk_exchange_*): every step's forcing is copied from pinned
-    # host memory and every step's diagnostics are copied back to pinned host memory inside the timed region; the
-    # copies of step k+1's inputs and of step k's results run on two copy streams while step k+1 computes.  The
-    # host reads step k's result (the error word) before it issues step k+2.
-    xch = cols.exchange(FORCING_FIELDS, RESULT_FIELDS)
-    fin = [forc_host[k] for k in FORCING_FIELDS]
-    fout = [[res_host[k] for k in RESULT_FIELDS],
-            [torch.empty_like(torch.from_numpy(res_host[k]), pin_memory=True).numpy() for k in RESULT_FIELDS]]
+    # ---- end to end: host buffers in, per-column results out, every step, through the C ABI ----
+    out_fields = cfg["out"]
+    res = [[pinned(k) for k in out_fields] for _ in range(2)]
+    d2h = sum(a.nbytes for a in res[0])
+    if key == 5:
+        # one new record of every raw series per step: pinned rows -> the ring slot that the forcing functors read
+        # two records later (elmk_atm_series_row copies on its own stream while the step computes)
+        rows = [{v: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for v in cols.ATM_VARS} for _ in range(2)]
+        rr = np.random.default_rng(17 + rank)
+        for slot in rows:
+            for v, a in slot.items():
+                a[:] = {"TBOT": 272.0, "PBOT": 99000.0, "QBOT": 60.0, "FLDS": 300.0, "FSDS": 500.0, "PREC": 0.0, "WIND": 3.0}[v]
+                a += rr.uniform(-0.5, 0.5, n) * (1.0 if v != "PREC" else 0.0)
+        h2d = sum(a.nbytes for a in rows[0].values())
+        xch = cols.exchange([], out_fields)
+    else:
+        h2d = sum(a.nbytes for a in forc_host.values())
+        xch = cols.exchange(FORCING_FIELDS, out_fields)
+        fin = [forc_host[k] for k in FORCING_FIELDS]
     host_checks = []
 
     def e2e_steps(k_steps):
-        xch.post(fin)
+        if key != 5:
+            xch.post(fin)
         for k in range(k_steps):
-            xch.commit()
-            if k + 1 < k_steps:
-                xch.post(fin)
-            one_step()
-            xch.fetch(fout[k & 1])
+            if key == 5:
+                t_next = (W.F.forcing_time_index((W.step_no * DT + DT / 2.0) / 86400.0, FORC_DT_DAYS) + 3) % (RING - 1)
+                for v in cols.ATM_VARS:
+                    cols.atm_series_row(v, t_next, rows[k & 1][v])
+            else:
+                xch.commit()
+                if k + 1 < k_steps:
+                    xch.post_wait()                             # the previous post has left the host buffers:
+                    fin[1][:8] += 1.0e-9 * ((k & 1) * 2 - 1)  # the host may write the next step's forcing into them
+                    xch.post(fin)
+            W.step()
+            xch.fetch(res[k & 1])
             if k >= 1:
-                xch.wait()                                   # step k-1's diagnostics are on the host
-                host_checks.append(int(fout[(k - 1) & 1][-1].max()))
+                xch.wait()                                   # step k-1's results are on the host
+                host_checks.append(int(res[(k - 1) & 1][-1].max()))
         xch.wait()
-        host_checks.append(int(fout[(k_steps - 1) & 1][-1].max()))
+        host_checks.append(int(res[(k_steps - 1) & 1][-1].max()))
 
     e2e_steps(2)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -348,19 +533,22 @@ def main():
     any_err, first = cols.errors()
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
+    ok = torch.tensor([1.0 if (check is None or check.get("bit_identical", True)) else 0.0], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # optional global balance diagnostic: sum/min/max of the eight a11 fields over all GPUs (NCCL),
-        # outside the timed region - the step itself has no collective
-        from elmkernels_b200.sharding import reduce_diagnostics
-        global_diag = reduce_diagnostics(cols.diag_reduce(), device=f"cuda:{local}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if key == 5:
+            # optional global balance diagnostic: sum/min/max of the eight a11 fields over all GPUs (NCCL),
+            # outside the timed region - the step itself has no collective
+            from elmkernels_b200.sharding import reduce_diagnostics
+            reduce_diagnostics(cols.diag_reduce(), device=f"cuda:{local}")
     ms, ms_e2e = float(t[0]), float(t[1])
 
     if rank == 0:
         peak, peak_src = measured_peak()
         gb = json.load(open(os.path.join(ROOT, "elmkernels_b200", "data", "group_bytes.json")))
-        other = {k[0]: k[2] / k[3] for k in kern if not k[1]}   # init_timestep (and, with ELMK_TIMING_DETAIL, sub-launches)
-        kern = [k for k in kern if k[1]]   # launches of elmk_step (init_timestep has mask 0)
+        other = {k[0]: k[2] / k[3] for k in kern if not k[1]}   # launches outside elmk_step (and sub-launches with ELMK_TIMING_DETAIL)
+        kern = [k for k in kern if k[1]]
         total_kernel_ms = sum(k[2] for k in kern) or 1.0
         top = max(kern, key=lambda k: k[2])
         per_launch_ms = top[2] / top[3]
@@ -368,38 +556,38 @@ def main():
         achieved = bytes_per_col * n / (per_launch_ms * 1e-3) / 1e9
         value = n * world * args.steps / (ms * 1e-3)
         e2e = n * world * args.steps / (ms_e2e * 1e-3)
-        counters, fpk = kernel_counters(), fp64_peak()
-        cg = (counters or {}).get("groups", {})
+        counters, csrc = static_json("r2_kernel_counters.json", "r1_kernel_counters.json")
+        fpk, _ = static_json("r1_fp64_peak.json")
+        cg = (counters or {}).get("groups", {}) if key == 5 else {}
         traffic = cg[top[0]]["dram_bytes_per_column"] * n if top[0] in cg else None
         fp64 = None
         if top[0] in cg and fpk:
             # FP64 pipe: thread-level DADD+DMUL+DFMA instructions per launch / live duration, against the measured
-            # instruction rate of the pipe (a DFMA counts as one instruction; the physics is built without FMA
-            # contraction, so its flop rate is bounded by the DMUL/DADD figure)
+            # instruction rate of the pipe (a DFMA counts as one instruction)
             inst = cg[top[0]]["fp64_inst_per_column"] * n
             peak_inst = fpk["dfma_tflops"] / 2.0
             fp64 = {"achieved": inst / (per_launch_ms * 1e-3) / 1e12, "peak": peak_inst, "unit": "T FP64 inst/s",
                     "frac": inst / (per_launch_ms * 1e-3) / 1e12 / peak_inst,
-                    "flop_per_column": cg[top[0]]["flop_per_column"], "inst_per_column": cg[top[0]]["fp64_inst_per_column"],
+                    "inst_per_column": cg[top[0]]["fp64_inst_per_column"],
                     "peak_source": "measured DFMA microbenchmark (profiles/r1_fp64_peak.json)",
-                    "counts_source": "ncu, profiles/r1_kernel_counters.json (%d columns)" % counters["ncols"]}
+                    "counts_source": "ncu, profiles/%s (%d columns)" % (csrc, counters["ncols"])}
+        step_gbs = cfg["bytes"] * n * args.steps / (ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": "column-steps/s", "n_gpus": world, "steps": args.steps,
+            "metric": cfg["metric"], "value": value, "unit": "column-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "full ELM column timestep (init_timestep + groups a1..a11, BASELINE.json config 5), "
-                                   "synthetic mixed-PFT ensemble with snl 0..5, state persistent in HBM",
-                       "columns_per_gpu": n, "columns_total": n * world, "dtime_s": 1800,
+            "config": {"workload": cfg["name"] + ", synthetic mixed-PFT ensemble with snl 0..5, state persistent in HBM, "
+                                   "inputs of every step produced on the device" if key == 5 else cfg["name"] + ", synthetic ensemble",
+                       "baseline_config": key, "columns_per_gpu": n, "columns_total": n * world, "dtime_s": DT,
                        "parallelism": f"columns sharded over {world} GPU(s), no collective on the step",
                        "l2": "inputs larger than L2: %.1f GB of column state per GPU vs 126 MB" % (n * 5765 / 1e9)},
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "fp64": fp64,
-                         "note": "the dominant launch is bounded by FP64 latency / issue, not by HBM: see fp64 and DESIGN.md section 4",
+                         "note": "launches of this path are bounded by FP64 dependent-issue latency and instruction fetch, "
+                                 "not by HBM: DESIGN.md section 4",
                          "bytes_per_column": bytes_per_col, "ms_per_launch": per_launch_ms,
                          "share_of_step": top[2] / total_kernel_ms,
-                         "step": {"bytes_per_column": ALGORITHMIC_BYTES_PER_COLUMN_STEP,
-                                  "achieved": ALGORITHMIC_BYTES_PER_COLUMN_STEP * n * args.steps / (ms * 1e-3) / 1e9,
-                                  "frac": ALGORITHMIC_BYTES_PER_COLUMN_STEP * n * args.steps / (ms * 1e-3) / 1e9 / peak},
+                         "step": {"bytes_per_column": cfg["bytes"], "achieved": step_gbs, "frac": step_gbs / peak},
                          "kernels": {k[0]: {"ms_per_launch": k[2] / k[3], "share": k[2] / total_kernel_ms,
                                             "bytes_per_column": launch_bytes(gb, k[1]),
                                             "GBps": launch_bytes(gb, k[1]) * n / (k[2] / k[3] * 1e-3) / 1e9,
@@ -407,11 +595,21 @@ def main():
                                             "fp64_inst_per_column": cg.get(k[0], {}).get("fp64_inst_per_column")}
                                      for k in kern}},
             "e2e": {"value": e2e, "unit": "column-steps/s", "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps},
-            "other_launches_ms": other, "gpu_launches": launches, "clocks": clocks, "errors": {"any": any_err, "first_column": first},
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
+                    "what": ("one new record of the seven raw forcing series in, eight balance diagnostics + error word out"
+                             if key == 5 else "17 forcing / phenology fields in, %s out" % " + ".join(out_fields))},
+            "other_launches_ms": other, "gpu_launches": launches, "clocks": clocks,
+            "errors": {"any": any_err, "first_column": first},
+            "verify": dict(check, all_ranks_bit_identical=bool(float(ok[0]) > 0.5)) if check else None,
         }
+        if hist is not None:
+            nz = np.nonzero(hist)[0]
+            line["canflux_passes"] = {"histogram": {int(k): int(hist[k]) for k in nz},
+                                      "mean": float((hist * np.arange(42)).sum() / max(hist.sum(), 1)),
+                                      "columns": int(hist.sum())}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(P, args.cpu_cols)
+            b = time_cpu(P, cfg, key, args.cpu_cols, steps=5, warmup=2)
+            line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")} if b else None
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -94,6 +94,8 @@ class Library:
                                              C.c_int64, C.c_int]),
             "elmk_init_timestep": (C.c_int, [H, C.c_int]),
             "elmk_step": (C.c_int, [H, C.c_double, C.c_double, C.c_double, C.c_uint32]),
+            "elmk_set_coordinates": (C.c_int, [H, _PD, _PD, C.c_int64]),
+            "elmk_solar_step": (C.c_int, [H, C.c_double, C.c_double, C.c_int, _PD, _PD]),
             "elmk_sync": (C.c_int, [H]),
             "elmk_set_plan": (C.c_int, [H, C.c_int]),
             "elmk_launch_count": (C.c_int64, [H]),
@@ -114,6 +116,8 @@ class Library:
             "elmk_init_columns": (C.c_int, [H, _PD, _PD, _PD, C.c_double, _PD]),
             "elmk_atm_series": (C.c_int, [H, C.c_int, _PD, C.c_int]),
             "elmk_atm_forcing": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_int]),
+            "elmk_atm_series_row": (C.c_int, [H, C.c_int, C.c_int, _PD]),
+            "elmk_canflux_pass_histogram": (C.c_int, [H, C.POINTER(C.c_int64)]),
             "elmk_phen_series": (C.c_int, [H, C.c_int, _PD, C.c_int]),
             "elmk_phenology": (C.c_int, [H, C.c_int, C.c_double, C.c_double]),
             "elmk_timing_enable": (C.c_int, [H, C.c_int]),
@@ -341,6 +345,19 @@ class Columns:
         """Raw forcing series of one variable, shape (ntimes, ncols) as AtmDataManager::data."""
         self._series(self.lib.dll.elmk_atm_series, f"elmk_atm_series({var})", self.ATM_VARS.index(var), arr)
 
+    def atm_series_row(self, var: str, t: int, row: np.ndarray):
+        """Replace time level t of a resident series (asynchronous for pinned `row`, which must stay alive)."""
+        assert row.dtype == np.float64 and row.shape == (self.ncols,) and row.flags["C_CONTIGUOUS"]
+        self._check(self.lib.dll.elmk_atm_series_row(self._h, self.ATM_VARS.index(var), int(t), row.ctypes.data_as(_PD)),
+                    "elmk_atm_series_row")
+
+    def canflux_pass_histogram(self) -> np.ndarray:
+        """hist[k] = vegetated columns whose stability iteration took k passes in the last step (CUDA library only)."""
+        hist = np.zeros(42, dtype=np.int64)
+        self._check(self.lib.dll.elmk_canflux_pass_histogram(self._h, hist.ctypes.data_as(C.POINTER(C.c_int64))),
+                    "elmk_canflux_pass_histogram")
+        return hist
+
     def atm_forcing(self, t_idx: int, wt1: float, wt2: float, qbot_is_rh: bool = True):
         self._check(self.lib.dll.elmk_atm_forcing(self._h, int(t_idx), float(wt1), float(wt2), int(qbot_is_rh)),
                     "elmk_atm_forcing")
@@ -352,6 +369,20 @@ class Columns:
         self._check(self.lib.dll.elmk_phenology(self._h, int(start_idx), float(wt1), float(wt2)), "elmk_phenology")
 
     # -- stepping --
+    def set_coordinates(self, lat_r, lon_r):
+        """Latitude / longitude [rad]: scalars (one site for every column, as in the reference) or one per column."""
+        lat = np.ascontiguousarray(np.atleast_1d(lat_r), dtype=np.float64)
+        lon = np.ascontiguousarray(np.atleast_1d(lon_r), dtype=np.float64)
+        assert lat.shape == lon.shape and lat.size in (1, self.ncols)
+        self._check(self.lib.dll.elmk_set_coordinates(self._h, lat.ctypes.data_as(_PD), lon.ctypes.data_as(_PD), lat.size),
+                    "elmk_set_coordinates")
+
+    def solar_step(self, dtime: float, decday: float, doy1: int):
+        """coszen of every column for the step starting at decimal day `decday`; returns (dayl, max_dayl)."""
+        d, m = C.c_double(), C.c_double()
+        self._check(self.lib.dll.elmk_solar_step(self._h, dtime, decday, int(doy1), C.byref(d), C.byref(m)), "elmk_solar_step")
+        return d.value, m.value
+
     def init_timestep(self, reset_forc_hgt: bool = True):
         self._check(self.lib.dll.elmk_init_timestep(self._h, int(reset_forc_hgt)), "elmk_init_timestep")
 

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -279,6 +280,12 @@ constexpr int kCanfluxDoubles = 0
 
 // 384-thread lock-step blocks: fastest of 128...768 threads with and without lock-step on B200
 constexpr int kIterBlock = 384;
+// row of the scratch that holds the pass count of a column (itlef) after the launch
+constexpr int kCanfluxItlefRow = 0
+#define X(n) +1
+    ELMK_CANFLUX_CONST(X) ELMK_CANFLUX_CARRIED(X)
+#undef X
+    + 3;   // nrad, veg, soybean, itlef
 struct CanfluxQueue {
   double* scratch;   // [kCanfluxDoubles][np]
   int* list;         // [np]: day columns from the front, night columns from the back
@@ -421,6 +428,27 @@ __global__ void __launch_bounds__(kBlock) k_atm_forcing(const Cols S, const AtmS
   const int c = blockIdx.x * kBlock + threadIdx.x;
   if (c >= S.ncols) return;
   column_atm_forcing(S, A, t, wt1, wt2, qbot_is_rh != 0, c);
+}
+// histogram of the stability-iteration pass counts of the vegetated columns (elmk_canflux_pass_histogram)
+__global__ void __launch_bounds__(256) k_pass_histogram(const Cols S, const double* __restrict__ itlef, unsigned long long* hist)
+{
+  __shared__ unsigned int h[42];
+  if (threadIdx.x < 42) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < S.ncols; c += gridDim.x * blockDim.x)
+    if (S.frac_veg_nosno[c] != 0) {
+      int it = (int)itlef[c];
+      it = it < 0 ? 0 : it > 41 ? 41 : it;
+      atomicAdd(&h[it], 1u);
+    }
+  __syncthreads();
+  if (threadIdx.x < 42 && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(kBlock) k_coszen(const Cols S, const SolarStep G)
+{
+  const int c = blockIdx.x * kBlock + threadIdx.x;
+  if (c >= S.ncols) return;
+  column_coszen(S, G, c);
 }
 __global__ void __launch_bounds__(kBlock) k_phenology(const Cols S, const PhenSeries P, const int m, const double wt1,
                                                       const double wt2)
@@ -650,6 +678,12 @@ struct Ctx {
   int atm_ntimes[ATM_NVARS] = {};
   double* phen[PHEN_NVARS] = {};   // monthly phenology values [nmonths][np] (elmk_phen_series)
   int phen_nmonths[PHEN_NVARS] = {};
+  cudaStream_t s_series = nullptr;  // copy stream of elmk_atm_series_row
+  cudaEvent_t ev_series = nullptr, ev_forcing = nullptr;
+  bool series_pending = false;
+  double* coords = nullptr;        // sin(lat), cos(lat), tan(lat), lon: [4][ncoords] (elmk_set_coordinates)
+  int64_t ncoords = 0;
+  double lat0 = 0.0;
   CanfluxQueue cq = {nullptr, nullptr, nullptr, 0};   // CanopyFluxes re-packing scratch (allocated on first use)
   int iterate_blocks = 0;
   bool repack = true;
@@ -1003,6 +1037,10 @@ int elmk_destroy(elmk_handle h) {
   cudaFree(c->d_diag);
   for (double* p : c->atm) cudaFree(p);
   for (double* p : c->phen) cudaFree(p);
+  if (c->s_series) { cudaStreamSynchronize(c->s_series); cudaStreamDestroy(c->s_series); }
+  if (c->ev_series) cudaEventDestroy(c->ev_series);
+  if (c->ev_forcing) cudaEventDestroy(c->ev_forcing);
+  cudaFree(c->coords);
   cudaFree(c->snicar_scratch);
   cudaFree(c->cq.scratch);
   cudaFree(c->cq.list);
@@ -1326,11 +1364,113 @@ int elmk_init_columns(elmk_handle h, const double* pct_sand, const double* pct_c
   return rc;
 }
 
+int elmk_set_coordinates(elmk_handle h, const double* lat_r, const double* lon_r, int64_t n) {
+  Ctx* c = ctx(h);
+  if (!c || !lat_r || !lon_r || !(n == 1 || n == c->ncols)) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  std::vector<double> host((size_t)4 * n);
+  for (int64_t i = 0; i < n; ++i) {
+    host[i] = std::sin(lat_r[i]);
+    host[n + i] = std::cos(lat_r[i]);
+    host[2 * n + i] = std::tan(solar::ensure_tan_defined(lat_r[i]));
+    host[3 * n + i] = lon_r[i];
+  }
+  if (c->coords) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(c->coords));
+    c->coords = nullptr;
+  }
+  CU(cudaMalloc(&c->coords, sizeof(double) * host.size()));
+  CU(cudaMemcpyAsync(c->coords, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->ncoords = n;
+  c->lat0 = lat_r[0];
+  return ELMK_OK;
+}
+
+int elmk_solar_step(elmk_handle h, double dtime, double decday, int doy1, double* dayl, double* max_dayl) {
+  Ctx* c = ctx(h);
+  if (!c) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (!c->coords) {
+    c->last_error = "elmk_solar_step before elmk_set_coordinates";
+    return ELMK_EINVAL;
+  }
+  // the per-step scalars of average_cosz (incident_shortwave.cc:108-116), on the host like the reference's
+  const double declin = solar::declination((int)decday);
+  SolarStep G;
+  G.sin_lat = c->coords; G.cos_lat = c->coords + c->ncoords; G.tan_lat = c->coords + 2 * c->ncoords;
+  G.lon = c->coords + 3 * c->ncoords;
+  G.per_column = c->ncoords > 1;
+  G.dtrad = dtime * solar::TWO_PI / 86400.0;
+  G.frac2pi = (decday - std::floor(decday)) * solar::TWO_PI;
+  G.sin_decl = std::sin(declin);
+  G.cos_decl = std::cos(declin);
+  G.tan_decl = std::tan(solar::ensure_tan_defined(declin));
+  const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
+  {
+    TimedScope ts(c, "coszen", 0u);
+    k_coszen<<<grid, kBlock, 0, c->stream>>>(c->cols, G);
+  }
+  c->launches += 1;
+  CU(cudaGetLastError());
+  if (dayl) *dayl = solar::daylength(c->lat0, solar::declination(doy1));
+  if (max_dayl) *max_dayl = solar::max_daylength(c->lat0);
+  return ELMK_OK;
+}
+
 int elmk_atm_series(elmk_handle h, int var, const double* host, int ntimes) {
   Ctx* c = ctx(h);
   if (!c || var < 0 || var >= ATM_NVARS) return ELMK_EINVAL;
   if (int rc = bind(c)) return rc;
   return set_series(c, &c->atm[var], &c->atm_ntimes[var], host, ntimes);
+}
+
+int elmk_atm_series_row(elmk_handle h, int var, int t, const double* host) {
+  Ctx* c = ctx(h);
+  if (!c || var < 0 || var >= ATM_NVARS || !host) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (!c->atm[var] || t < 0 || t >= c->atm_ntimes[var]) {
+    c->last_error = "elmk_atm_series_row: no such series / time level";
+    return ELMK_EINVAL;
+  }
+  if (!c->s_series) {
+    CU(cudaStreamCreateWithFlags(&c->s_series, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_series, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_forcing, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->ev_forcing, c->stream));
+  }
+  // the row may still be read by the forcing kernel issued last: the copy waits for it, then runs beside the step
+  CU(cudaStreamWaitEvent(c->s_series, c->ev_forcing, 0));
+  CU(cudaMemcpyAsync(c->atm[var] + (size_t)t * c->np, host, sizeof(double) * c->ncols, cudaMemcpyHostToDevice, c->s_series));
+  CU(cudaEventRecord(c->ev_series, c->s_series));
+  c->series_pending = true;
+  return ELMK_OK;
+}
+
+int elmk_canflux_pass_histogram(elmk_handle h, int64_t hist[42]) {
+  Ctx* c = ctx(h);
+  if (!c || !hist) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (!c->cq.scratch) {
+    c->last_error = "elmk_canflux_pass_histogram: the re-packed CanopyFluxes launch has not run on this handle";
+    return ELMK_EINVAL;
+  }
+  unsigned long long* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(unsigned long long) * 42));
+  cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long) * 42, c->stream);
+  if (e == cudaSuccess) {
+    k_pass_histogram<<<148 * 8, 256, 0, c->stream>>>(c->cols, c->cq.scratch + (size_t)kCanfluxItlefRow * c->np, d);
+    c->launches += 1;
+    e = cudaGetLastError();
+  }
+  unsigned long long host[42];
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host, d, sizeof(host), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(c, e, "elmk_canflux_pass_histogram");
+  for (int i = 0; i < 42; ++i) hist[i] = (int64_t)host[i];
+  return ELMK_OK;
 }
 
 int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_is_rh) {
@@ -1348,9 +1488,14 @@ int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_
   }
   const unsigned grid = (unsigned)((c->ncols + kBlock - 1) / kBlock);
   {
+    if (c->series_pending) {   // rows posted by elmk_atm_series_row have to be on the device first
+      CU(cudaStreamWaitEvent(c->stream, c->ev_series, 0));
+      c->series_pending = false;
+    }
     TimedScope ts(c, "atm_forcing", 0u);
     k_atm_forcing<<<grid, kBlock, 0, c->stream>>>(c->cols, A, t_idx, wt1, wt2, qbot_is_rh);
   }
+  if (c->s_series) CU(cudaEventRecord(c->ev_forcing, c->stream));
   c->launches += 1;
   CU(cudaGetLastError());
   return ELMK_OK;

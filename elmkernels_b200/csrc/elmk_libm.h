@@ -491,6 +491,34 @@ ELMK_LM_HD double g_cos(const double x)
   return cos(x);
 }
 
+// sin, same file (__sin): used by the per-column solar geometry (phys_forcing.h)
+ELMK_LM_HD double g_sin(const double x)
+{
+  using namespace sc;
+  const uint32_t k = (uint32_t)(as_u64(x) >> 32) & 0x7fffffffu;
+  if (k < 0x3e500000u) return x;
+  if (k < 0x3feb6000u) return do_sin(x, 0.0);
+  if (k < 0x400368fdu) {
+    const double t = hp0 - fabs(x);
+    const double r = do_cos(t, hp1);
+    return as_f64((as_u64(r) & 0x7fffffffffffffffull) | (as_u64(x) & 0x8000000000000000ull));
+  }
+  if (k < 0x419921fbu) {
+    const double t = fma(x, hpinv, toint);
+    const double xn = t - toint;
+    const uint32_t n = (uint32_t)as_u64(t) & 3u;
+    double y = fma(-xn, mp1, x);
+    y = fma(-xn, mp2, y);
+    const double b = fma(-xn, pp3, y);
+    const double db = fma(-xn, pp3, y - b);
+    const double a = fma(-xn, pp4, b);
+    const double da = db + fma(-xn, pp4, b - a);
+    const double r = (n & 1u) ? do_cos(a, da) : do_sin(a, da);
+    return (n & 2u) ? -r : r;
+  }
+  return sin(x);
+}
+
 // ---- tanh (s_tanh.c, not fused) over expm1 (s_expm1.c, the __expm1_fma variant) -----------------------------------
 ELMK_LM_HD double hi_add(const double y, const int k)   // add k to the binary exponent of y
 {

@@ -19,6 +19,91 @@ namespace elmk {
 constexpr int ATM_TBOT = 0, ATM_PBOT = 1, ATM_QBOT = 2, ATM_FLDS = 3, ATM_FSDS = 4, ATM_PREC = 5, ATM_WIND = 6, ATM_NVARS = 7;
 constexpr int PHEN_MLAI = 0, PHEN_MSAI = 1, PHEN_MHTOP = 2, PHEN_MHBOT = 3, PHEN_NVARS = 4;
 
+// ---- solar geometry of kokkos_init_timestep (init_timestep_kokkos.cc:27-35) ----
+// incident_shortwave::average_cosz (src/physics/incident_shortwave.cc:108-116) per column, and ELM::daylength /
+// max_daylength (src/physics/day_length.cc:16-39).  The reference evaluates them once for its single site
+// (S.lat_r, S.lon_r) on the host and assigns the cosine to every column; here every column may have its own
+// coordinates.  The trigonometric functions of the latitude do not change with time: the host evaluates them once
+// (elmk_set_coordinates), the per-step declination terms are kernel arguments, and the device is left with the
+// half-day arc cosine and four sines per column, from the restatements of libm's routines (elmk_libm.h).
+struct SolarStep {
+  const double* sin_lat;   // [n] sin(lat), cos(lat), tan(ensure_tan_defined(lat)), longitude [rad]
+  const double* cos_lat;
+  const double* tan_lat;
+  const double* lon;
+  int per_column;          // 0: element 0 applies to every column (one site)
+  double dtrad, frac2pi, sin_decl, cos_decl, tan_decl;
+};
+namespace solar {
+constexpr double TWO_PI = PI * 2.0, PI_OVER_TWO = PI / 2.0;
+ELMK_HD double ensure_tan_defined(const double v) { return (v == PI_OVER_TWO) ? v - 1.0e-05 : (v == -PI_OVER_TWO) ? v + 1.0e-05 : v; }
+// declination_angle_sin (:17): host only (its sine is evaluated once per step)
+inline double declination(const int doy) { return 23.45 * PI / 180.0 * sin(TWO_PI * (284.0 + doy) / 365.0); }
+// ELM::daylength (day_length.cc:16-34).  QUIRK: the clamp `min(offset_pole, max(1.0 * offset_pole, lat))` always
+// yields offset_pole, so the latitude does not enter (the lower bound was meant to be -offset_pole); reproduced.
+inline double daylength(const double lat, const double decl)
+{
+  (void)lat;
+  constexpr double secs_per_radian = 13750.9871;
+  constexpr double lat_epsilon = 10.0 * 2.220446049250313e-16;
+  constexpr double offset_pole = PI / 2.0 - lat_epsilon;
+  const double my_lat = offset_pole;
+  double temp = -(sin(my_lat) * sin(decl)) / (cos(my_lat) * cos(decl));
+  temp = dmin(1.0, dmax(-1.0, temp));
+  return 2.0 * secs_per_radian * acos(temp);
+}
+inline double max_daylength(const double lat) { return (lat < 0.0) ? daylength(lat, -0.409571) : daylength(lat, 0.409571); }
+} // namespace solar
+
+#if defined(__CUDA_ARCH__)
+ELMK_HD_NOINLINE double m_sin(double x) { return lm::g_sin(x); }
+#else
+ELMK_HD_NOINLINE double m_sin(double x) { return sin(x); }
+#endif
+
+ELMK_HD void column_coszen(const Cols& S, const SolarStep& G, const int c)
+{
+  using namespace solar;
+  const int k = G.per_column ? c : 0;
+  const double dtrad = G.dtrad;
+  // dt_start_rad (:39-44), dt_end_rad (:47-50)
+  double t_start = G.frac2pi + G.lon[k] - PI;
+  t_start = (t_start >= PI) ? t_start - TWO_PI : (t_start < -PI) ? t_start + TWO_PI : t_start;
+  const double t_end = t_start + dtrad;
+  // coshalfday (:54-58)
+  const double ch = -G.tan_lat[k] * G.tan_decl;
+  const double cos_h = (ch <= -1.0) ? PI : (ch >= 1.0) ? 0.0 : m_acos(ch);
+  // avg_hourangle (:63-96)
+  double ha0, ha1, ha2, ha3;
+  if (t_end >= PI && t_start <= PI && PI - cos_h <= dtrad) {
+    ha0 = dmin(dmax(t_start, -cos_h), cos_h);
+    ha1 = cos_h;
+    ha2 = TWO_PI - cos_h;
+    ha3 = dmin(dmax(t_end, TWO_PI - cos_h), TWO_PI + cos_h);
+  } else if (t_end >= -PI && t_start <= -PI && PI - cos_h <= dtrad) {
+    ha0 = dmin(dmax(t_start, -TWO_PI - cos_h), -TWO_PI + cos_h);
+    ha1 = -TWO_PI + cos_h;
+    ha2 = -cos_h;
+    ha3 = dmin(dmax(t_end, -cos_h), cos_h);
+  } else {
+    if (t_start > PI) ha0 = dmin(dmax(t_start - TWO_PI, -cos_h), cos_h);
+    else if (t_start < -PI) ha0 = dmin(dmax(t_start + TWO_PI, -cos_h), cos_h);
+    else ha0 = dmin(dmax(t_start, -cos_h), cos_h);
+    if (t_end > PI) ha1 = dmin(dmax(t_end - TWO_PI, -cos_h), cos_h);
+    else if (t_end < -PI) ha1 = dmin(dmax(t_end + TWO_PI, -cos_h), cos_h);
+    else ha1 = dmin(dmax(t_end, -cos_h), cos_h);
+    ha2 = 0.0;
+    ha3 = 0.0;
+  }
+  // integrate_cosz (:100-113)
+  const double aa = G.sin_lat[k] * G.sin_decl;
+  const double bb = G.cos_lat[k] * G.cos_decl;
+  double cosz = 0.0;
+  if (ha1 > ha0 || ha3 > ha2)
+    cosz = (aa * (ha1 - ha0) + bb * (m_sin(ha1) - m_sin(ha0))) / dtrad + (aa * (ha3 - ha2) + bb * (m_sin(ha3) - m_sin(ha2))) / dtrad;
+  C1(coszen) = cosz;
+}
+
 struct AtmSeries {
   const double* v[ATM_NVARS];
   long long stride;   // elements between consecutive times

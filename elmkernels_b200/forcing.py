@@ -8,13 +8,18 @@ reference's data managers do on the host before they launch their per-column fun
 The per-column work itself runs on the device (elmk_atm_forcing, elmk_phenology)."""
 from __future__ import annotations
 
+import math
 from typing import Tuple
 
 NDAYPM = (31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31)   # no leap years, as the reference
 
 
 def forcing_time_index(days_since_data_start: float, forc_dt_days: float) -> int:
-    """Index of the forcing record that starts the interval containing the (step-centred) model time."""
+    """Index of the forcing record that starts the interval containing the (step-centred) model time
+    (forc_t_idx_check_bounds, atm_data_impl.hh:147-169): truncation, except within 1e-8 days of a record boundary,
+    where the reference rounds to the nearest record (forc_t_idx_aligned :122-137)."""
+    if abs(math.remainder(days_since_data_start, forc_dt_days)) < 1.0e-8:
+        return int(round(days_since_data_start / forc_dt_days))
     return int(days_since_data_start / forc_dt_days)
 
 
@@ -22,8 +27,9 @@ def forcing_time_weights(days_since_data_start: float, forc_dt_days: float) -> T
     """(t_idx, wt1, wt2): linear interpolation weights of records t_idx and t_idx + 1."""
     t_idx = forcing_time_index(days_since_data_start, forc_dt_days)
     elapsed = (days_since_data_start - t_idx * forc_dt_days) / forc_dt_days
-    if not (0.0 <= elapsed <= 1.0):
+    if not (-1.0e-8 <= elapsed <= 1.0):
         raise ValueError("model time outside the forcing interval")
+    elapsed = max(elapsed, 0.0)   # a model time a hair before the record it was aligned to sits on that record
     return t_idx, 1.0 - elapsed, elapsed
 
 

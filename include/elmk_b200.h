@@ -197,6 +197,17 @@ int elmk_exchange_post_wait(elmk_exchange x);
 int elmk_init_columns(elmk_handle h, const double* pct_sand, const double* pct_clay, const double* organic,
                       double organic_max, const double* snow_depth);
 
+/* ---- solar geometry: the first lines of kokkos_init_timestep (init_timestep_kokkos.cc:27-35).
+ *      elmk_set_coordinates: latitude and longitude [rad] of the columns; n == 1 is the reference's single site
+ *        (S.lat_r, S.lon_r apply to every column), n == ncols gives every column its own.  The time-invariant
+ *        sin / cos / tan of the latitudes are evaluated here, once, on the host.
+ *      elmk_solar_step: incident_shortwave::average_cosz(lat, lon, dtime, decday) of every column into the coszen
+ *        field (device), with decday = Utils::decimal_doy(current) + 1; *dayl = ELM::daylength(lat,
+ *        declination_angle_sin(doy1)) with doy1 = current.doy + 1 and *max_dayl = ELM::max_daylength(lat), both for
+ *        the first coordinate, to be handed to elmk_step. ---- */
+int elmk_set_coordinates(elmk_handle h, const double* lat_r, const double* lon_r, int64_t n);
+int elmk_solar_step(elmk_handle h, double dtime, double decday, int doy1, double* dayl, double* max_dayl);
+
 /* ---- producers of the per-step inputs, on the device (the step before the chain in kokkos_init_timestep,
  *      init_timestep_kokkos.cc:39-47).
  *      elmk_atm_series: one raw forcing series, host[t * ncols + col] - the layout of AtmDataManager::data
@@ -226,6 +237,12 @@ int elmk_init_columns(elmk_handle h, const double* pct_sand, const double* pct_c
 #define ELMK_PHEN_NVARS 4
 int elmk_atm_series(elmk_handle h, int var, const double* host, int ntimes);
 int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_is_rh);
+/* one time level of a resident series replaced from the host (the reference's read_atm_data refreshes its window of
+ * records while the run proceeds, atm_forcing_kokkos.cc:15-27): asynchronous on a copy stream of the handle, ordered
+ * after the forcing kernel that may still read the row and before the next elmk_atm_forcing; pinned host memory
+ * overlaps with the step.  host holds ncols values and must stay untouched until the next elmk_atm_forcing has been
+ * followed by elmk_sync (or any blocking call). */
+int elmk_atm_series_row(elmk_handle h, int var, int t, const double* host);
 int elmk_phen_series(elmk_handle h, int var, const double* host, int nmonths);
 int elmk_phenology(elmk_handle h, int start_idx, double wt1, double wt2);
 
@@ -274,6 +291,12 @@ const char* elmk_error_text(uint32_t bit); /* the reference's message for one er
  *      Counterpart of ELMKokkos::min_max_sum (src/utils/kokkos_utils.hh:13-58); the cross-rank
  *      reduction of the 24 doubles is done by the caller (NCCL all-reduce in the Python host). ---- */
 int elmk_diag_reduce(elmk_handle h, double out[24]);
+
+/* ---- pass counts of the CanopyFluxes stability iteration (canopy_fluxes_impl.hh:215-451, itlef) of the last elmk_step
+ *      that ran group a7 in the fused plan: hist[k] = number of vegetated columns that took k passes (k = 3..41).
+ *      The reference keeps the count in a wrapper-local View; here it is read from the iteration scratch.
+ *      ELMK_EUNSUPPORTED on the CPU checkers. ---- */
+int elmk_canflux_pass_histogram(elmk_handle h, int64_t hist[42]);
 
 /* ---- the library's transcendental functions, evaluated where the library computes (the product: on the device):
  *      out[i] = fn(x[i]) or fn(x[i], y[i]).  exp, log, log10, pow, atan, cos, tanh, erf and acos return the bits of

@@ -83,3 +83,4 @@ int elmk_math_eval(elmk_handle h, int fn, int64_t n, const double* x, const doub
   return ELMK_OK;
 }
 int elmk_set_plan(elmk_handle h, int plan) { return (h && (plan == ELMK_PLAN_FUSED || plan == ELMK_PLAN_SPLIT)) ? ELMK_OK : ELMK_EINVAL; }
+int elmk_canflux_pass_histogram(elmk_handle, int64_t*) { return ELMK_EUNSUPPORTED; }

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,6 +54,9 @@ struct PortCtx {
   std::vector<void*> base;
   std::vector<double> snw[2][3], snowage[3];
   std::vector<double> atm[ATM_NVARS], phen[PHEN_NVARS];   // [ntimes][ncols]
+  std::vector<double> coords;   // sin(lat), cos(lat), tan(lat), lon: [4][ncoords]
+  int64_t ncoords = 0;
+  double lat0 = 0.0;
   bool tables_set = false;
   int64_t launches = 0;
   std::string last_error;
@@ -218,6 +222,12 @@ int elmk_atm_series(elmk_handle h, int var, const double* host, int ntimes) {
   c.atm[var].assign(host, host + (size_t)ntimes * c.ncols);
   return ELMK_OK;
 }
+int elmk_atm_series_row(elmk_handle h, int var, int t, const double* host) {
+  PortCtx& c = *ctx(h);
+  if (var < 0 || var >= ATM_NVARS || !host || t < 0 || (size_t)(t + 1) * c.ncols > c.atm[var].size()) return ELMK_EINVAL;
+  std::copy(host, host + c.ncols, c.atm[var].begin() + (size_t)t * c.ncols);
+  return ELMK_OK;
+}
 int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_is_rh) {
   PortCtx& c = *ctx(h);
   AtmSeries A;
@@ -227,6 +237,37 @@ int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_
     A.v[v] = c.atm[v].data();
   }
   for_columns(c, [&](int i) { column_atm_forcing(c.cols, A, t_idx, wt1, wt2, qbot_is_rh != 0, i); });
+  return ELMK_OK;
+}
+int elmk_set_coordinates(elmk_handle h, const double* lat_r, const double* lon_r, int64_t n) {
+  PortCtx& c = *ctx(h);
+  if (!lat_r || !lon_r || !(n == 1 || n == c.ncols)) return ELMK_EINVAL;
+  c.coords.resize((size_t)4 * n);
+  for (int64_t i = 0; i < n; ++i) {
+    c.coords[i] = std::sin(lat_r[i]);
+    c.coords[n + i] = std::cos(lat_r[i]);
+    c.coords[2 * n + i] = std::tan(solar::ensure_tan_defined(lat_r[i]));
+    c.coords[3 * n + i] = lon_r[i];
+  }
+  c.ncoords = n;
+  c.lat0 = lat_r[0];
+  return ELMK_OK;
+}
+int elmk_solar_step(elmk_handle h, double dtime, double decday, int doy1, double* dayl, double* max_dayl) {
+  PortCtx& c = *ctx(h);
+  if (c.coords.empty()) return ELMK_EINVAL;
+  const double declin = solar::declination((int)decday);
+  SolarStep G;
+  G.sin_lat = c.coords.data(); G.cos_lat = G.sin_lat + c.ncoords; G.tan_lat = G.sin_lat + 2 * c.ncoords; G.lon = G.sin_lat + 3 * c.ncoords;
+  G.per_column = c.ncoords > 1;
+  G.dtrad = dtime * solar::TWO_PI / 86400.0;
+  G.frac2pi = (decday - std::floor(decday)) * solar::TWO_PI;
+  G.sin_decl = std::sin(declin);
+  G.cos_decl = std::cos(declin);
+  G.tan_decl = std::tan(solar::ensure_tan_defined(declin));
+  for_columns(c, [&](int i) { column_coszen(c.cols, G, i); });
+  if (dayl) *dayl = solar::daylength(c.lat0, solar::declination(doy1));
+  if (max_dayl) *max_dayl = solar::max_daylength(c.lat0);
   return ELMK_OK;
 }
 int elmk_phen_series(elmk_handle h, int var, const double* host, int nmonths) {

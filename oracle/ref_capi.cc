@@ -29,6 +29,8 @@
 #include "data_types.hh"
 #include "elm_constants.h"
 #include "helper_functions.hh"
+#include "day_length.h"
+#include "incident_shortwave.h"
 
 #include "albedo_kokkos.hh"
 #include "bareground_fluxes_kokkos.hh"
@@ -72,6 +74,7 @@ struct RefCtx {
   ViewI1 errmask;
   // raw forcing series and monthly phenology values, as the reference's data managers hold them: (ntimes, ncells)
   ViewD2 atm[ELMK_ATM_NVARS], phen[ELMK_PHEN_NVARS];
+  std::vector<double> lat, lon;   // elmk_set_coordinates
   bool tables_set = false;
   int64_t launches = 0;
   std::string last_error;
@@ -375,6 +378,33 @@ int elmk_atm_series(elmk_handle h, int var, const double* host, int ntimes) {
   RefCtx& c = *ctx(h);
   if (var < 0 || var >= ELMK_ATM_NVARS) return ELMK_EINVAL;
   return ref_set_series(c, c.atm[var], "atm_series", host, ntimes);
+}
+// the first lines of kokkos_init_timestep (init_timestep_kokkos.cc:27-35) with the reference's own functions, evaluated
+// for every column's coordinates instead of the single site
+int elmk_set_coordinates(elmk_handle h, const double* lat_r, const double* lon_r, int64_t n) {
+  RefCtx& c = *ctx(h);
+  if (!lat_r || !lon_r || !(n == 1 || n == c.ncols)) return ELMK_EINVAL;
+  c.lat.assign(lat_r, lat_r + n);
+  c.lon.assign(lon_r, lon_r + n);
+  return ELMK_OK;
+}
+int elmk_solar_step(elmk_handle h, double dtime, double decday, int doy1, double* dayl, double* max_dayl) {
+  RefCtx& c = *ctx(h);
+  if (c.lat.empty()) return ELMK_EINVAL;
+  ELMStateType& S = *c.S;
+  const bool per = c.lat.size() > 1;
+  for (int64_t i = 0; i < c.ncols; ++i)
+    S.coszen(i) = ELM::incident_shortwave::average_cosz(c.lat[per ? i : 0], c.lon[per ? i : 0], dtime, decday);
+  if (dayl) *dayl = ELM::daylength(c.lat[0], ELM::incident_shortwave::declination_angle_sin(doy1));
+  if (max_dayl) *max_dayl = ELM::max_daylength(c.lat[0]);
+  c.launches += 1;
+  return ELMK_OK;
+}
+int elmk_atm_series_row(elmk_handle h, int var, int t, const double* host) {
+  RefCtx& c = *ctx(h);
+  if (var < 0 || var >= ELMK_ATM_NVARS || !host || t < 0 || static_cast<size_t>(t) >= c.atm[var].extent(0)) return ELMK_EINVAL;
+  for (int64_t i = 0; i < c.ncols; ++i) c.atm[var](t, i) = host[i];
+  return ELMK_OK;
 }
 int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_is_rh) {
   RefCtx& c = *ctx(h);

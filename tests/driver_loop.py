@@ -1,7 +1,7 @@
 """The reference driver's whole loop through the C ABI, device-side producers included:
 
     setup:     soil grid + texture + initial snow depth  ->  elmk_init_columns           (initialize_kokkos_elm)
-    each step: coszen (host, one value per step as the reference)                         (kokkos_init_timestep :25-33)
+    each step: elmk_solar_step: coszen of every column (own latitude / longitude), day lengths (kokkos_init_timestep :27-35)
                elmk_phenology, elmk_atm_forcing                                           (update_phenology, get_forcing)
                elmk_init_timestep, elmk_step(all groups)                                  (init_step_kernel, advance)
 
@@ -59,19 +59,21 @@ def run(lib, params, n, nsteps, collect=None):
         cols.atm_series(k, v)
     for k, v in monthly(n).items():
         cols.phen_series(k, v)
+    # every column at its own place on the globe (the reference driver has one site)
+    cols.set_coordinates(np.deg2rad(r.uniform(-70.0, 75.0, n)), np.deg2rad(r.uniform(-180.0, 180.0, n)))
     out = []
     for step in range(nsteps):
         sec = step * DT
         centred_days = (sec + DT / 2.0) / 86400.0
-        hour = (sec / 3600.0) % 24.0
-        cols.fill("coszen", max(0.0, float(np.sin(2 * np.pi * (hour - 6.0) / 24.0))))
+        doy = 195                                                   # 14 July
+        dayl, max_dayl = cols.solar_step(DT, doy + sec / 86400.0 + 1.0, doy + 1)
         m1 = forcing.first_month_idx(7, 14, sec % 86400.0) - 5     # series holds June, July, August
         pw1, pw2 = forcing.monthly_data_weights(7, 14, sec % 86400.0)
         cols.phenology(m1, pw1, pw2)
         t_idx, w1, w2 = forcing.forcing_time_weights(centred_days, FORC_DT_DAYS)
         cols.atm_forcing(t_idx, w1, w2, True)
         cols.init_timestep(False)                                   # forcing heights were just set by atm_forcing
-        cols.step(dtime=DT)
+        cols.step(dtime=DT, dayl=dayl, max_dayl=max_dayl)
         if collect and step in collect:
             out.append(cols.download_state())
     err = cols.errors()

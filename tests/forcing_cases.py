@@ -61,3 +61,28 @@ def run(lib, params, n, rh=True):
         out.append({k: cols.download(k) for k in OUT_ATM + OUT_PHEN})
     cols.close()
     return out
+
+
+def solar(lib, params, n=4000, seed=5):
+    """elmk_solar_step for columns spread over the globe (poles and the date line included) at several times of the
+    year and of the day: [(coszen[n], dayl, max_dayl)]."""
+    r = np.random.default_rng(seed)
+    lat = np.deg2rad(r.uniform(-90.0, 90.0, n))
+    lon = np.deg2rad(r.uniform(-180.0, 180.0, n))
+    lat[:6] = np.array([np.pi / 2, -np.pi / 2, 0.0, np.deg2rad(66.6), np.deg2rad(-66.6), 1.5])
+    lon[:6] = np.array([0.0, np.pi, -np.pi, 0.0, 3.0, -3.0])
+    cols = lib.columns(n)
+    cols.set_tables(params)
+    cols.set_coordinates(lat, lon)
+    out = []
+    for doy in (0, 79, 171, 264, 354):
+        for frac in (0.0, 0.21, 0.5, 0.77, 0.98):
+            for dt in (1800.0, 3600.0, 10800.0):
+                dayl, mx = cols.solar_step(dt, doy + frac + 1.0, doy + 1)
+                out.append((cols.download("coszen"), dayl, mx))
+    # one site for all columns (the reference's own use)
+    cols.set_coordinates(0.6, -1.9)
+    dayl, mx = cols.solar_step(1800.0, 100.3, 100)
+    out.append((cols.download("coszen"), dayl, mx))
+    cols.close()
+    return out

@@ -107,6 +107,11 @@ int main(int argc, char** argv) {
   run1("erf", "uniform [-7, 7]", N, gerf, rerf, [] { return uni(-7, 7); });
   run1("erf", "uniform [-1.3, 1.3]", N, gerf, rerf, [] { return uni(-1.3, 1.3); });
   run1("erf", "log-uniform 2^-60..2^4 +-", N, gerf, rerf, [] { return logu(-60, 4, true); });
+  auto rsin = [](double x) { return sin(x); };
+  auto gsin = [](double x) { return g_sin(x); };
+  run1("sin", "uniform [-7, 7]", N, gsin, rsin, [] { return uni(-7, 7); });
+  run1("sin", "uniform [-1000, 1000]", N, gsin, rsin, [] { return uni(-1000, 1000); });
+  run1("sin", "log-uniform 2^-40..2^26 +-", N, gsin, rsin, [] { return logu(-40, 26, true); });
   auto racos = [](double x) { return acos(x); };
   auto gacos = [](double x) { return g_acos(x); };
   run1("acos", "uniform [-1, 1]", N, gacos, racos, [] { return uni(-1, 1); });

@@ -17,3 +17,13 @@ def test_cuda_forcing_and_phenology_match_the_reference(cuda_lib, checker, param
         for k in sa:
             bad = parity.mismatch(sa[k], sb[k])
             assert not bad.any(), f"{k}: {int(bad.sum())} elements differ, e.g. {sa[k][bad][:3]} vs {sb[k][bad][:3]}"
+
+
+def test_cuda_solar_geometry_matches_the_reference(cuda_lib, checker, params):
+    """coszen of every column (device: arc cosine + four sines per column from the libm restatements) and the two day
+    lengths, against the reference's functions, bit for bit."""
+    a, b = F.solar(checker, params, n=20000), F.solar(cuda_lib, params, n=20000)
+    for (ca, da, ma), (cb, db, mb) in zip(a, b):
+        bad = parity.mismatch(ca, cb)
+        assert not bad.any(), f"coszen: {int(bad.sum())} columns differ, e.g. {ca[bad][:3]} vs {cb[bad][:3]}"
+        assert da == db and ma == mb
