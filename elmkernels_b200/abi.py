@@ -60,6 +60,16 @@ class Tables(C.Structure):
                 ("snicar_snow", _PD * 6), ("snicar_bc", _PD * 6), ("bcenh", _PD), ("snowage", _PD * 3)]
 
 
+def table_arrays(params):
+    """The arrays behind the pointer members of struct elmk_tables, in member order (pft[40], albsat, albdry,
+    snicar_band[18], snicar_snow[6], snicar_bc[6], bcenh, snowage[3])."""
+    out = [params["pft_" + n] for n in PFT_ORDER] + [params["albsat"], params["albdry"]]
+    out += [params["snicar_" + n] for n in SNICAR_BAND] + [params["snicar_" + n] for n in SNICAR_SNOW]
+    out += [params["snicar_" + n] for n in SNICAR_BC] + [params["snicar_bcenh"]]
+    out += [params["snowage_" + n] for n in ("tau", "kappa", "drdt0")]
+    return out
+
+
 class ElmkError(RuntimeError):
     pass
 
@@ -96,6 +106,7 @@ class Library:
             "elmk_step": (C.c_int, [H, C.c_double, C.c_double, C.c_double, C.c_uint32]),
             "elmk_set_coordinates": (C.c_int, [H, _PD, _PD, C.c_int64]),
             "elmk_solar_step": (C.c_int, [H, C.c_double, C.c_double, C.c_int, _PD, _PD]),
+            "elmk_fn_call": (C.c_int, [C.c_int, C.c_int, _PD, C.c_int64]),
             "elmk_sync": (C.c_int, [H]),
             "elmk_set_plan": (C.c_int, [H, C.c_int]),
             "elmk_launch_count": (C.c_int64, [H]),

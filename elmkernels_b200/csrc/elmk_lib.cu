@@ -98,6 +98,43 @@ __device__ __forceinline__ void run_groups(const Cols& S, const Tables& T, const
 #undef ELMK_GROUP
 }
 
+// ---- bulk prefetch of a block's input rows into L2 (TMA engine: cp.async.bulk.prefetch.L2, SASS UBLKPF) ----------
+// With the column-innermost layout every (field, level) row of a block's 128 columns is one contiguous, 16-byte
+// aligned segment of 1 KB (doubles).  The unsorted launches are bound by memory latency (ncu: long_scoreboard
+// 10-16 stalled slots per issue at ~2 TB/s): their loads sit between calls and data-dependent branches, so a warp
+// has one or two of them in flight.  The first warps of a block therefore ask the TMA engine for all rows the
+// block is going to read, before the column work starts; the demand loads then find their sectors in L2.
+__device__ __forceinline__ void prefetch_row(const void* p, const unsigned bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+template <class T>
+__device__ __forceinline__ void prefetch_field(const Cols& S, const T* base, const int lev0, const int nlev, int& row, const int col0)
+{
+  // one row per thread, rows numbered across all fields of the list
+  for (int l = 0; l < nlev; ++l, ++row)
+    if (row % kBlock == (int)threadIdx.x) prefetch_row(base + (long long)(lev0 + l) * S.np + col0, (unsigned)(kBlock * sizeof(T)));
+}
+template <uint32_t MASK> __device__ __forceinline__ void prefetch_inputs(const Cols& S)
+{
+#ifdef ELMK_BULK_PREFETCH
+  const int col0 = blockIdx.x * kBlock;
+  int row = 0;
+#define PF(field, lev0, nlev) prefetch_field(S, S.field, lev0, nlev, row, col0);
+  if (MASK & ELMK_G_SOIL_TEMPERATURE) {
+    PF(t_soisno, 0, 20) PF(zsoi, 0, 20) PF(h2osoi_liq, 0, 20) PF(h2osoi_ice, 0, 20) PF(dz, 0, 20) PF(zisoi, 0, 21)
+    PF(watsat, 0, 15) PF(tkdry, 0, 15) PF(tkmg, 0, 15) PF(csol, 5, 15) PF(sucsat, 0, 15) PF(bsw, 0, 15) PF(sabg_lyr, 0, 6)
+    PF(frac_sno, 0, 1) PF(frac_sno_eff, 0, 1) PF(frac_h2osfc, 0, 1) PF(h2osfc, 0, 1) PF(h2osno, 0, 1) PF(t_h2osfc, 0, 1)
+    PF(dlrad, 0, 1) PF(emg, 0, 1) PF(forc_lwrad, 0, 1) PF(htvp, 0, 1) PF(sabg_soil, 0, 1) PF(sabg_snow, 0, 1)
+    PF(eflx_sh_soil, 0, 1) PF(qflx_ev_soil, 0, 1) PF(eflx_sh_h2osfc, 0, 1) PF(qflx_ev_h2osfc, 0, 1) PF(eflx_sh_snow, 0, 1)
+    PF(qflx_ev_snow, 0, 1) PF(cgrnd, 0, 1) PF(t_grnd, 0, 1) PF(int_snow, 0, 1) PF(snow_depth, 0, 1)
+  }
+#undef PF
+#else
+  (void)S;
+#endif
+}
+
 template <uint32_t MASK>
 __global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
 {
@@ -109,6 +146,7 @@ __global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* _
 template <uint32_t MASK, int MINBLOCKS>
 __global__ void __launch_bounds__(kBlock, MINBLOCKS) k_groups_occ(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
 {
+  prefetch_inputs<MASK>(S);
   const int c = blockIdx.x * kBlock + threadIdx.x;
   if (!kWholeBlocks<MASK> && c >= S.ncols) return;
   run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c, c < S.ncols);
@@ -456,6 +494,41 @@ __global__ void __launch_bounds__(kBlock) k_phenology(const Cols S, const PhenSe
   const int c = blockIdx.x * kBlock + threadIdx.x;
   if (c >= S.ncols) return;
   column_phenology(S, P, m, wt1, wt2, c);
+}
+
+// elmk_fn_call: one library-level physics function on the flat argument array of ONE column (include/elm/*.h)
+struct FlatRow {
+  double* p;
+  __device__ double& operator[](const int i) const { return p[i]; }
+};
+constexpr int kFnSlots[ELMK_FN_COUNT] = {13, 14, 7, 150, 26};
+__global__ void k_fn_call(const int fn, double* __restrict__ a)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  switch (fn) {
+    case ELMK_FN_INTERCEPTION:
+      hyd::interception((int)a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]);
+      break;
+    case ELMK_FN_GROUND_FLUX:
+      hyd::ground_flux((int)a[0], (int)a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13]);
+      break;
+    case ELMK_FN_FRACTION_WET:
+      hyd::fraction_wet((int)a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+      break;
+    case ELMK_FN_SNOW_INIT: {
+      // dtime capsnow oldfflag forc_t t_grnd snow_grnd snow_melt n_melt | snow_depth h2osno int_snow | swe_old[5] liq[20]
+      // ice[20] t[20] frac_iceold[5] | snl | dz[20] z[20] zi[21] snw_rds[5] | frac_sno_eff frac_sno
+      int snl = (int)a[81];
+      hyd::snow_init(a[0], (int)a[1], (int)a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], FlatRow{a + 11}, FlatRow{a + 16},
+                     FlatRow{a + 36}, FlatRow{a + 56}, FlatRow{a + 76}, snl, FlatRow{a + 82}, FlatRow{a + 102}, FlatRow{a + 122},
+                     FlatRow{a + 143}, a[148], a[149]);
+      a[81] = (double)snl;
+    } break;
+    case ELMK_FN_FRACTION_H2OSFC:
+      hyd::fraction_h2osfc(a[0], a[1], a[2], FlatRow{a + 3}, a[23], a[24], a[25]);
+      break;
+    default: break;
+  }
 }
 
 // elmk_math_eval: the library's transcendentals at caller-given arguments (parity diagnostic)
@@ -1285,6 +1358,21 @@ int elmk_exchange_post_wait(elmk_exchange xh) {
   CU(cudaEventSynchronize(x->in_ready[slot]));
   x->post_waits += 1;
   return ELMK_OK;
+}
+
+int elmk_fn_call(int device, int fn, double* args, int64_t nargs) {
+  if (fn < 0 || fn >= ELMK_FN_COUNT || !args || nargs != kFnSlots[fn]) return ELMK_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return ELMK_ECUDA;
+  double* d = nullptr;
+  if (cudaMalloc(&d, sizeof(double) * nargs) != cudaSuccess) return ELMK_ECUDA;
+  cudaError_t e = cudaMemcpy(d, args, sizeof(double) * nargs, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_fn_call<<<1, 32>>>(fn, d);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(args, d, sizeof(double) * nargs, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? ELMK_OK : ELMK_ECUDA;
 }
 
 int elmk_math_eval(elmk_handle h, int fn, int64_t n, const double* x, const double* y, double* out) {

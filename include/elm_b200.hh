@@ -268,14 +268,47 @@ private:
 
 // ---- drop-in wrappers: same names and arguments as driver/kokkos/<group>_kokkos.hh -------------------
 namespace detail {
+struct Mirror {
+  const void* state;
+  int64_t ncols;
+  int ltype, ctype, vtype, oldfflag;
+  bool urbpoi, lakpoi;
+  double dewmx;
+  std::unique_ptr<Device> dev;
+};
+inline std::vector<Mirror>& mirrors() {
+  static std::vector<Mirror> cache;
+  return cache;
+}
+template <class State> bool same_scalars(const Mirror& m, const State& S) {
+  return m.ltype == S.Land.ltype && m.ctype == S.Land.ctype && m.vtype == S.Land.vtype && m.urbpoi == (bool)S.Land.urbpoi &&
+         m.lakpoi == (bool)S.Land.lakpoi && m.oldfflag == S.oldfflag && m.dewmx == S.dewmx;
+}
+// One device mirror per state object, created on first use.  The entry is keyed on the object's address AND its
+// column count (a state destroyed and another allocated at the same address does not inherit the mirror), the tables
+// are sent again whenever the scalars of the land unit change, and ELM::b200::release(S) / release_all() free the
+// device memory; refresh_tables(S) re-sends the PFT / SNICAR tables after the caller changed them in place.
 template <class State> Device& device_for(State& S) {
-  // one device mirror per state object, created on first use and kept for the life of the process
-  static std::vector<std::pair<const void*, std::unique_ptr<Device>>> cache;
-  for (auto& e : cache)
-    if (e.first == static_cast<const void*>(&S)) return *e.second;
-  cache.emplace_back(static_cast<const void*>(&S), std::make_unique<Device>(S.num_columns));
-  cache.back().second->set_tables(S);
-  return *cache.back().second;
+  auto& cache = mirrors();
+  for (size_t k = 0; k < cache.size(); ++k) {
+    Mirror& m = cache[k];
+    if (m.state != static_cast<const void*>(&S)) continue;
+    if (m.ncols != (int64_t)S.num_columns) {   // stale: another object lived at this address
+      cache.erase(cache.begin() + k);
+      break;
+    }
+    if (!same_scalars(m, S)) {
+      m.dev->set_tables(S);
+      m.ltype = S.Land.ltype; m.ctype = S.Land.ctype; m.vtype = S.Land.vtype; m.urbpoi = S.Land.urbpoi; m.lakpoi = S.Land.lakpoi;
+      m.oldfflag = S.oldfflag; m.dewmx = S.dewmx;
+    }
+    return *m.dev;
+  }
+  Mirror m{static_cast<const void*>(&S), (int64_t)S.num_columns, S.Land.ltype, S.Land.ctype, S.Land.vtype, S.oldfflag,
+           (bool)S.Land.urbpoi, (bool)S.Land.lakpoi, S.dewmx, std::make_unique<Device>(S.num_columns)};
+  m.dev->set_tables(S);
+  cache.push_back(std::move(m));
+  return *cache.back().dev;
 }
 template <class State> void run_group(State& S, double dtime, uint32_t group) {
   Device& d = device_for(S);
@@ -285,6 +318,16 @@ template <class State> void run_group(State& S, double dtime, uint32_t group) {
   d.check_errors();
 }
 } // namespace detail
+
+// frees the device mirror of S (the drop-in wrappers create one on first use and keep it)
+template <class State> void release(State& S) {
+  auto& cache = detail::mirrors();
+  for (size_t k = 0; k < cache.size(); ++k)
+    if (cache[k].state == static_cast<const void*>(&S)) { cache.erase(cache.begin() + k); return; }
+}
+inline void release_all() { detail::mirrors().clear(); }
+// after the caller changed PFT / SNICAR / snow-age tables of S in place
+template <class State> void refresh_tables(State& S) { detail::device_for(S).set_tables(S); }
 
 template <class State> void kokkos_frac_wet(State& S) { detail::run_group(S, 0.0, ELMK_G_FRAC_WET); }
 template <class State> void kokkos_albedo_snicar(State& S) { detail::run_group(S, 0.0, ELMK_G_ALBEDO); }
@@ -297,6 +340,31 @@ template <class State> void kokkos_soil_temperature(State& S, const double& dtim
 template <class State, class Date> void kokkos_snow_hydrology(State& S, const double& dtime, const Date&) { detail::run_group(S, dtime, ELMK_G_SNOW_HYDROLOGY); }
 template <class State> void kokkos_surface_fluxes(State& S, const double& dtime) { detail::run_group(S, dtime, ELMK_G_SURFACE_FLUXES); }
 template <class State> void kokkos_evaluate_conservation(State& S, const double& dtime) { detail::run_group(S, dtime, ELMK_G_CONSERVATION); }
+// the per-column lambda of kokkos_init_timestep (init_timestep_kokkos.cc:53-72); its file reading (phenology, forcing)
+// stays with the driver
+template <class State> void kokkos_init_timestep_columns(State& S) {
+  Device& d = detail::device_for(S);
+  d.upload(S);
+  d.init_timestep(true);
+  d.download(S);
+}
 
 } // namespace b200
+
+// With ELM_B200_DROP_IN defined before this header is included, the eleven wrappers are ELM::kokkos_<group> themselves:
+// a driver written against the reference (driver/kokkos/elm_kokkos_interface.cc:289-318) switches backend by including
+// this header in place of the eleven driver/kokkos/<group>_kokkos.hh and linking libelmk_b200.so - no call site changes.
+#ifdef ELM_B200_DROP_IN
+using b200::kokkos_frac_wet;
+using b200::kokkos_albedo_snicar;
+using b200::kokkos_canopy_hydrology;
+using b200::kokkos_surface_radiation;
+using b200::kokkos_canopy_temperature;
+using b200::kokkos_bareground_fluxes;
+using b200::kokkos_canopy_fluxes;
+using b200::kokkos_soil_temperature;
+using b200::kokkos_snow_hydrology;
+using b200::kokkos_surface_fluxes;
+using b200::kokkos_evaluate_conservation;
+#endif
 } // namespace ELM

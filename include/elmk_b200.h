@@ -315,6 +315,20 @@ int elmk_canflux_pass_histogram(elmk_handle h, int64_t hist[42]);
 #define ELMK_MATH_COUNT 10
 int elmk_math_eval(elmk_handle h, int fn, int64_t n, const double* x, const double* y, double* out);
 
+/* ---- library-level physics functions (the reference's ELM::<namespace>::<function> free functions, e.g.
+ *      src/physics/canopy_hydrology.h) executed on the device for ONE column: args holds the function's arguments in
+ *      the reference's order without the LandType - scalars (ints and bools as doubles) one slot each, per-column rows
+ *      expanded in place with their full extent - and is updated in place with everything the function writes.
+ *      Synchronous, no handle (device = CUDA device ordinal).  The C++ headers of include/elm/ are the typed front end;
+ *      the device code is the one the fused kernels of elmk_step run.  ELMK_EUNSUPPORTED on the CPU checkers. ---- */
+#define ELMK_FN_INTERCEPTION 0      /* canopy_hydrology::interception     canopy_hydrology_impl.hh:8    13 slots */
+#define ELMK_FN_GROUND_FLUX 1       /* canopy_hydrology::ground_flux      :83    14 slots */
+#define ELMK_FN_FRACTION_WET 2      /* canopy_hydrology::fraction_wet     :123    7 slots */
+#define ELMK_FN_SNOW_INIT 3         /* canopy_hydrology::snow_init        :146  150 slots */
+#define ELMK_FN_FRACTION_H2OSFC 4   /* canopy_hydrology::fraction_h2osfc  :312   26 slots */
+#define ELMK_FN_COUNT 5
+int elmk_fn_call(int device, int fn, double* args, int64_t nargs);
+
 /* raw device pointer + level stride of a field (for zero-copy interop with torch tensors) */
 int elmk_device_ptr(elmk_handle h, int field, void** ptr, int64_t* level_stride);
 /* the handle's CUDA stream (a cudaStream_t), so that a caller can record its own events on it or make

@@ -84,3 +84,4 @@ int elmk_math_eval(elmk_handle h, int fn, int64_t n, const double* x, const doub
 }
 int elmk_set_plan(elmk_handle h, int plan) { return (h && (plan == ELMK_PLAN_FUSED || plan == ELMK_PLAN_SPLIT)) ? ELMK_OK : ELMK_EINVAL; }
 int elmk_canflux_pass_histogram(elmk_handle, int64_t*) { return ELMK_EUNSUPPORTED; }
+int elmk_fn_call(int, int, double*, int64_t) { return ELMK_EUNSUPPORTED; }   // the checkers ARE the function library

@@ -1,0 +1,95 @@
+"""The C++ host adaptor (include/elm_b200.hh) computing on the B200 through the reference's own ELMState type:
+tests/adaptor/_build/adaptor_steps (built in the container where the reference headers are, shipped with the snapshot)
+loads an ensemble into an ELMStateType, runs three resident steps (Device::upload_forcing + advance) and one more step
+as the eleven ELM::kokkos_<group>(S[, dt]) drop-in calls of ELMInterface::advance, and dumps every member of the state
+object.  The same sequence through the Python binding on the checker (oracle/_ref) must give the same bits."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from elmkernels_b200 import abi, ensemble
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "adaptor", "_build", "adaptor_steps")
+FORCING = ("coszen forc_tbot forc_thbot forc_pbot forc_qbot forc_lwrad forc_u forc_v forc_rain forc_snow forc_solad "
+           "forc_solai elai esai frac_veg_nosno_alb").split()
+
+
+def members():
+    txt = open(os.path.join(ROOT, "include", "elmk_members.h")).read()
+    out = []
+    for block in ("ELMK_STATE_MEMBERS", "ELMK_AEROSOL_MEMBERS"):
+        body = txt[txt.index(f"#define {block}(X)"):]
+        body = body[:body.index("\n\n")]
+        out += [(m.group(1), int(m.group(2))) for m in re.finditer(r"X\((\w+), [^,]+, (\d+)\)", body)]
+    return out
+
+
+def tables_blob(P, dayl, max_dayl):
+    parts = [np.array([1, 1, 12, 0, 0, 1, 0.1, dayl, max_dayl], dtype=np.float64)]
+    t = abi.table_arrays(P)   # the arrays of struct elmk_tables in member order
+    for a in t:
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        parts += [np.array([a.size], dtype=np.float64), a]
+    return np.concatenate(parts)
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="tests/adaptor/_build/adaptor_steps not built (needs the reference headers)")
+def test_adaptor_advances_the_reference_state_on_the_gpu(checker, cuda_lib, params, tmp_path):
+    n, nsteps = 1500, 3
+    dayl, max_dayl = 50000.0, 86400.0
+    cfg = ensemble.EnsembleConfig(ncols=n, seed=31, h2osfc_fraction=0.1, soil_temp_spread=5.0)
+    st = ensemble.make_state(cfg, params, cuda_lib.fields)
+    F = ensemble.Forcing(n, seed=8)
+    tables_blob(params, dayl, max_dayl).tofile(tmp_path / "tables.bin")
+    with open(tmp_path / "state.bin", "wb") as f:
+        for k in cuda_lib.field_names:
+            f.write(np.ascontiguousarray(st[k]).tobytes())
+    # the checker's run gives the forcing of every step (burial of LAI depends on the evolving snow state)
+    ref = checker.columns(n)
+    ref.set_tables(params)
+    ref.upload_state(st)
+    for k in range(nsteps + 1):
+        f = F.at(k, {q: ref.download(q) for q in ("vtype", "snow_depth", "frac_sno", "htop", "hbot", "tlai", "tsai")})
+        np.concatenate([np.ascontiguousarray(f[q], dtype=np.float64).ravel() for q in FORCING]).tofile(tmp_path / f"forcing_{k}.bin")
+        ref.upload_state(f)
+        ref.init_timestep(True)
+        if k < nsteps:
+            ref.step(dayl=dayl, max_dayl=max_dayl)
+        else:
+            for g in range(abi.G_ALL.bit_length()):
+                ref.step(dayl=dayl, max_dayl=max_dayl, groups=1 << g)
+    r = subprocess.run([EXE, str(tmp_path), str(n), str(nsteps)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = np.fromfile(tmp_path / "out.bin", dtype=np.float64)
+    pos, bad = 0, {}
+    for name, nlev in members():
+        want = ref.download(name).astype(np.float64).reshape(n, -1)
+        got = out[pos:pos + n * nlev].reshape(n, nlev)
+        pos += n * nlev
+        m = (want.view(np.uint64) != got.view(np.uint64)) & ~(np.isnan(want) & np.isnan(got))
+        if m.any():
+            bad[name] = int(m.sum())
+    assert pos == out.size
+    assert not bad, f"state members that differ from the checker after {nsteps} + 1 steps through the adaptor: {bad}"
+
+
+@pytest.mark.parametrize("name,checks", [("CanHydro", 1824)])
+def test_reference_unit_test_runs_on_the_gpu_through_the_function_api(name, checks):
+    """The reference's own test/test_<name>.cc, compiled unchanged against include/elm/ (the library-level ELM::<ns>::<fn>
+    API of this repository in place of the reference's src/physics) and linked against libelmk_b200.so: every physics
+    call of the test executes on the GPU (elmk_fn_call), and every comparison against the ELM Fortran dump that passes
+    with the reference's own implementation (oracle/run_ref_tests.py: all of them) must pass here."""
+    exe = os.path.join(ROOT, "tests", "adaptor", "_build", f"ref_test_{name}")
+    if not os.path.exists(exe):
+        pytest.skip("not built (needs the reference sources)")
+    r = subprocess.run([exe], capture_output=True, text=True, cwd=os.path.dirname(exe))
+    assert r.returncode == 0, r.stderr[-2000:]
+    passed = len(re.findall(r"passes: true", r.stdout))
+    failed = [l for l in r.stdout.splitlines() if "passes: false" in l]
+    assert not failed, failed[:10]
+    assert passed == checks, (passed, checks)
