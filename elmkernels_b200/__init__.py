@@ -2,7 +2,7 @@
 per-column land-surface timestep, behind the C ABI of include/elmk_b200.h.
 
 The product library is libelmk_b200.so in this directory.  There is no CPU fallback: `load()` raises
-if the CUDA library has not been built (python __graft_entry__.py / make -C elmkernels_b200/csrc).
+if the CUDA library has not been built (python __graft_entry__.py, or python elmkernels_b200/build.py).
 """
 import os
 

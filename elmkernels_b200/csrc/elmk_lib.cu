@@ -497,11 +497,8 @@ __global__ void __launch_bounds__(kBlock) k_phenology(const Cols S, const PhenSe
 }
 
 // elmk_fn_call: one library-level physics function on the flat argument array of ONE column (include/elm/*.h)
-struct FlatRow {
-  double* p;
-  __device__ double& operator[](const int i) const { return p[i]; }
-};
-constexpr int kFnSlots[ELMK_FN_COUNT] = {13, 14, 7, 150, 26};
+#define FlatRow(ptr) ColRow{(ptr), 1}
+constexpr int kFnSlots[ELMK_FN_COUNT] = {13, 14, 7, 150, 26, 11, 36, 39, 9, 18};
 __global__ void k_fn_call(const int fn, double* __restrict__ a)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -519,13 +516,39 @@ __global__ void k_fn_call(const int fn, double* __restrict__ a)
       // dtime capsnow oldfflag forc_t t_grnd snow_grnd snow_melt n_melt | snow_depth h2osno int_snow | swe_old[5] liq[20]
       // ice[20] t[20] frac_iceold[5] | snl | dz[20] z[20] zi[21] snw_rds[5] | frac_sno_eff frac_sno
       int snl = (int)a[81];
-      hyd::snow_init(a[0], (int)a[1], (int)a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], FlatRow{a + 11}, FlatRow{a + 16},
-                     FlatRow{a + 36}, FlatRow{a + 56}, FlatRow{a + 76}, snl, FlatRow{a + 82}, FlatRow{a + 102}, FlatRow{a + 122},
-                     FlatRow{a + 143}, a[148], a[149]);
+      hyd::snow_init(a[0], (int)a[1], (int)a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], FlatRow(a + 11), FlatRow(a + 16),
+                     FlatRow(a + 36), FlatRow(a + 56), FlatRow(a + 76), snl, FlatRow(a + 82), FlatRow(a + 102), FlatRow(a + 122),
+                     FlatRow(a + 143), a[148], a[149]);
       a[81] = (double)snl;
     } break;
     case ELMK_FN_FRACTION_H2OSFC:
-      hyd::fraction_h2osfc(a[0], a[1], a[2], FlatRow{a + 3}, a[23], a[24], a[25]);
+      hyd::fraction_h2osfc(a[0], a[1], a[2], FlatRow(a + 3), a[23], a[24], a[25]);
+      break;
+    case ELMK_FN_RAD_INITIALIZE_FLUX:
+      rad::initialize_flux(a[0], a[1], a[2], a[3], a[4], FlatRow(a + 5));
+      break;
+    case ELMK_FN_RAD_TOTAL_ABSORBED:
+      // snl | ftdd ftid ftii solad solai fabd fabi albsod albsoi albsnd albsni albgrd albgri [2 each] | sabv fsa sabg sabg_soil
+      // sabg_snow | trd[2] tri[2]
+      rad::total_absorbed_radiation((int)a[0], FlatRow(a + 1), FlatRow(a + 3), FlatRow(a + 5), FlatRow(a + 7), FlatRow(a + 9),
+                                    FlatRow(a + 11), FlatRow(a + 13), FlatRow(a + 15), FlatRow(a + 17), FlatRow(a + 19),
+                                    FlatRow(a + 21), FlatRow(a + 23), FlatRow(a + 25), a[27], a[28], a[29], a[30], a[31],
+                                    FlatRow(a + 32), FlatRow(a + 34));
+      break;
+    case ELMK_FN_RAD_LAYER_ABSORBED:
+      // snl sabg sabg_snow snow_depth | flx_absdv flx_absdn flx_absiv flx_absin [6 each] | trd[2] tri[2] | sabg_lyr[6] | ok
+      a[38] = rad::layer_absorbed_radiation((int)a[0], a[1], a[2], a[3], FlatRow(a + 4), FlatRow(a + 10), FlatRow(a + 16),
+                                            FlatRow(a + 22), FlatRow(a + 28), FlatRow(a + 30), FlatRow(a + 32)) ? 1.0 : 0.0;
+      break;
+    case ELMK_FN_RAD_REFLECTED:
+      rad::reflected_radiation(FlatRow(a + 0), FlatRow(a + 2), FlatRow(a + 4), FlatRow(a + 6), a[8]);
+      break;
+    case ELMK_FN_RAD_SUNSHADE:
+      // nrad elai | tlai_z fsun_z | solad[2] solai[2] | fabd_sun_z fabd_sha_z fabi_sun_z fabi_sha_z | parsun_z parsha_z laisun_z
+      // laisha_z | laisun laisha
+      rad::canopy_sunshade_fractions((int)a[0], a[1], FlatRow(a + 2), FlatRow(a + 3), FlatRow(a + 4), FlatRow(a + 6), FlatRow(a + 8),
+                                     FlatRow(a + 9), FlatRow(a + 10), FlatRow(a + 11), FlatRow(a + 12), FlatRow(a + 13),
+                                     FlatRow(a + 14), FlatRow(a + 15), a[16], a[17]);
       break;
     default: break;
   }
@@ -654,6 +677,29 @@ __global__ void __launch_bounds__(256) k_inner_to_outer(const T* __restrict__ sr
     const int cl = e / nlev, lev = e - cl * nlev;
     dst[c0 * nlev + e] = tile[cl * pitch + lev];
   }
+}
+
+// The padding columns [ncols, np) of the last block: the soil-temperature launch keeps their threads alive (its block
+// barriers need whole blocks), so they run the group body on whatever the padding holds.  A physically plausible
+// constant column there keeps every value they compute and store finite (all-zero state divides by zero layer
+// thicknesses); nothing reads the padding back, elmk_errors scans the valid columns only, and
+// tests/test_gpu_padding.py checks that it stays finite and free of error bits.
+__global__ void k_init_padding(const Cols S)
+{
+  const int c = S.ncols + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= S.np) return;
+  for (int i = 0; i < NLEVTOT; ++i) {
+    C2(dz, i) = (i < NLEVSNO) ? 0.0 : 0.5;
+    C2(zsoi, i) = (i < NLEVSNO) ? 0.0 : 0.5 * (i - NLEVSNO) + 0.25;
+    C2(t_soisno, i) = (i < NLEVSNO) ? 0.0 : 280.0;
+    C2(h2osoi_liq, i) = (i < NLEVSNO) ? 0.0 : 50.0;
+    C2(csol, i) = 2.0e6;
+  }
+  for (int i = 0; i <= NLEVTOT; ++i) C2(zisoi, i) = (i < NLEVSNO) ? 0.0 : 0.5 * (i - NLEVSNO);
+  for (int i = 0; i < NLEVGRND; ++i) {
+    C2(watsat, i) = 0.4; C2(tkdry, i) = 0.2; C2(tkmg, i) = 1.5; C2(bsw, i) = 5.0; C2(sucsat, i) = 100.0;
+  }
+  C1(t_grnd) = 280.0; C1(t_h2osfc) = 280.0; C1(emg) = 0.96; C1(htvp) = HVAP; C1(forc_lwrad) = 300.0;
 }
 
 template <typename T> __global__ void k_fill(T* __restrict__ p, const long long count, const T v)
@@ -1053,6 +1099,10 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
     return bail(fail(c, e, "cudaMalloc(diag)"));
   if ((e = cudaMallocHost(&c->h_pinned, sizeof(double) * 8 * kDiagSlices * 3)) != cudaSuccess)
     return bail(fail(c, e, "cudaMallocHost"));
+  if (c->np > c->ncols) {
+    k_init_padding<<<1, kColAlign, 0, c->stream>>>(c->cols);
+    if ((e = cudaGetLastError()) != cudaSuccess) return bail(fail(c, e, "k_init_padding"));
+  }
   if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail(fail(c, e, "cudaStreamSynchronize"));
 #ifdef ELMK_DEV_VARIANTS
   {

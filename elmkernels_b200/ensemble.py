@@ -14,8 +14,8 @@ the reference's init functions, restated vectorised over columns:
   phenology burial of LAI/SAI by snow                      src/physics/phenology_physics_impl.hh:36-61
   VIS/NIR split of incident shortwave                      src/physics/atm_physics_impl.hh:126-141
 
-tests/test_ensemble_cpu.py checks the one-time initialisation against the reference's own functions
-(through the oracle library).
+tests/test_init_cpu.py checks the one-time initialisation against the reference's own functions (through the
+oracle library).
 """
 from __future__ import annotations
 

@@ -109,6 +109,13 @@ def _find_partner(body: list[str], i: int, general):
         md = DEST.match(l)
         if md:
             written.add(md.group(1))
+        elif VECDEST.match(l):
+            # vector destination list ({%fd7, %fd8} of an ld.*.v2.f64 ...): every register inside the braces is written
+            written.update(FDREG.findall(VECDEST.match(l).group(1)))
+        elif FDREG.search(l):
+            # an instruction that names an f64 register in a form this pass does not parse: fail closed - the window
+            # ends here, nothing moves across it
+            return None
         named.update(REG.findall(l))
         seen += 1
         j += 1
@@ -144,6 +151,8 @@ def _recip_div(ind: str, d: str, a: str, rc: str, nc: str, k: int, b_for_call: s
 
 LDPARAM = re.compile(r"^\s*ld\.param\.f64\s+(%fd\d+),\s*\[([\w$]+)_param_\d+(?:\+\d+)?\];")
 DEST = re.compile(r"^\s*(?:@!?%p\d+\s+)?[a-z][\w.]*\s+(%fd\d+)\s*[,;]")
+VECDEST = re.compile(r"^\s*(?:@!?%p\d+\s+)?[a-z][\w.]*\s+\{([^}]*)\}\s*,")
+FDREG = re.compile(r"%fd\d+")
 
 
 def _rewrite_function(name: str, body: list[str], counter: list[int], stats: dict) -> list[str]:

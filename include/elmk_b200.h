@@ -326,7 +326,12 @@ int elmk_math_eval(elmk_handle h, int fn, int64_t n, const double* x, const doub
 #define ELMK_FN_FRACTION_WET 2      /* canopy_hydrology::fraction_wet     :123    7 slots */
 #define ELMK_FN_SNOW_INIT 3         /* canopy_hydrology::snow_init        :146  150 slots */
 #define ELMK_FN_FRACTION_H2OSFC 4   /* canopy_hydrology::fraction_h2osfc  :312   26 slots */
-#define ELMK_FN_COUNT 5
+#define ELMK_FN_RAD_INITIALIZE_FLUX 5 /* surface_radiation::initialize_flux           surface_radiation_impl.hh:9    11 slots */
+#define ELMK_FN_RAD_TOTAL_ABSORBED 6  /* surface_radiation::total_absorbed_radiation  :30   36 slots */
+#define ELMK_FN_RAD_LAYER_ABSORBED 7  /* surface_radiation::layer_absorbed_radiation  :77   39 slots (last: 0 where the reference asserts) */
+#define ELMK_FN_RAD_REFLECTED 8       /* surface_radiation::reflected_radiation       :179   9 slots */
+#define ELMK_FN_RAD_SUNSHADE 9        /* surface_radiation::canopy_sunshade_fractions :202  18 slots */
+#define ELMK_FN_COUNT 10
 int elmk_fn_call(int device, int fn, double* args, int64_t nargs);
 
 /* raw device pointer + level stride of a field (for zero-copy interop with torch tensors) */

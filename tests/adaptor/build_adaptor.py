@@ -33,7 +33,9 @@ def build(force=False):
 # (which takes the place of the reference's src/physics on the include path) and linked against the product library:
 # every ELM::<namespace>::<function> call of the test then runs on the GPU.  The ELM Fortran fixture files the tests
 # read at run time are copied next to the binaries (build output: git-ignored, travels with the snapshot).
-REF_TESTS = {"CanHydro": ["CanopyHydrology_IN.txt", "CanopyHydrology_OUT.txt"]}
+REF_TESTS = {"CanHydro": ["CanopyHydrology_IN.txt", "CanopyHydrology_OUT.txt"],
+             "SurfRad": ["SurfaceRadiation_IN.txt", "SurfaceRadiation_OUT.txt"],
+             "CanSunShade": ["CanopySunShadeFractions_IN.txt", "CanopySunShadeFractions_OUT.txt"]}
 
 
 def build_reference_tests(force=False):

@@ -64,6 +64,26 @@ def test_rewrite_forms():
     assert "div.rn.f64 \t%fd3, %fd1, %fd2;" in out[:out.index(".entry k_test")]
 
 
+def test_pairing_does_not_move_a_division_across_the_load_that_defines_its_operand():
+    """Vector destinations ({%fd7, %fd8} of an ld.v2.f64) count as written; an f64 instruction in a form the pass does
+    not parse ends the pairing window (fail closed)."""
+    div = lambda d, a, b: f"\tdiv.rn.f64 \t{d}, {a}, {b};"
+    anyform = lambda m: True
+    # the second division reads %fd7, defined by the v2 load between the two: it cannot move up
+    body = [div("%fd3", "%fd1", "%fd2"), "\tld.global.v2.f64 \t{%fd7, %fd8}, [%rd1];", div("%fd9", "%fd7", "%fd2")]
+    r = R._find_partner(body, 0, anyform)
+    assert r is None or r[1] == "down"
+    # ... and the first cannot move down when the load overwrites its own operand
+    body = [div("%fd3", "%fd7", "%fd2"), "\tld.global.v2.f64 \t{%fd7, %fd8}, [%rd1];", div("%fd9", "%fd7", "%fd2")]
+    assert R._find_partner(body, 0, anyform) is None
+    # without the load in between the two pair up
+    body = [div("%fd3", "%fd1", "%fd2"), "\tadd.rn.f64 \t%fd10, %fd1, %fd2;", div("%fd9", "%fd5", "%fd6")]
+    assert R._find_partner(body, 0, anyform) == (2, "up")
+    # an unparsed form that names f64 registers closes the window
+    body = [div("%fd3", "%fd1", "%fd2"), "\tst.global.v2.f64 \t[%rd1], {%fd5, %fd6};", div("%fd9", "%fd5", "%fd6")]
+    assert R._find_partner(body, 0, anyform) is None
+
+
 def test_missing_m_div_is_an_error():
     with pytest.raises(RuntimeError):
         R.rewrite(".version 8.8\n.target sm_100a\n.address_size 64\n")
