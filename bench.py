@@ -46,6 +46,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+ALGORITHMIC_BYTES_PER_COLUMN_STEP = 6325   # SURVEY.md section 8(d) / BASELINE.md section 4, element level, frozen (config 5)
+DECLARED_BYTES_PER_COLUMN_STEP = 7201      # declared-extent upper bound IN + 2*PROG + OUT (7117 of SURVEY.md + imelt carried across steps + errmask)
 HBM_FALLBACK_GBS = 6650.0
 CHUNK = 1 << 18                            # columns generated / uploaded at a time
 DT = 1800.0
@@ -63,7 +65,7 @@ def configs():
     return {
         5: dict(name="full ELM column timestep (solar geometry + phenology + forcing functors + init_timestep + groups "
                      "a1..a11, BASELINE.json config 5)", metric="column-steps/sec, full ELM step", mask=abi.G_ALL,
-                ncols=1 << 21, bytes=6325, ens=dict(soil_temp_spread=6.0), night=None, out=DIAG_FIELDS),
+                ncols=1 << 21, bytes=ALGORITHMIC_BYTES_PER_COLUMN_STEP, ens=dict(soil_temp_spread=6.0), night=None, out=DIAG_FIELDS),
         2: dict(name="SurfaceAlbedo + SurfaceRadiation two-stream (groups a1 + a2 + a4, BASELINE.json config 2)",
                 metric="column-steps/sec, albedo + surface radiation", mask=abi.G_FRAC_WET | abi.G_ALBEDO | abi.G_SURFACE_RADIATION,
                 ncols=1 << 20, bytes=1112, ens=dict(), night=0.25, out=["fsa", "fsr", "errmask"]),
