@@ -216,11 +216,19 @@ __global__ void __launch_bounds__(kSnicarBlock, MINBLOCKS) k_snicar(const Cols S
     const int nact = nactive;
     const int nitems = ((nact + 31) / 32) * kSnicarTasks;
     // ---- the band solves ----
+#ifdef ELMK_SNICAR_LOCKSTEP
+    // (experiment) the warps of the block start every item together: one warp's instruction fetch serves the others
+    for (int round = 0; round * (kSnicarBlock / 32) < nitems; ++round) {
+      __syncthreads();
+      const int item = round * (kSnicarBlock / 32) + (threadIdx.x >> 5);
+      if (item >= nitems) continue;
+#else
     while (true) {
       int item = 0;
       if (lane == 0) item = atomicAdd(&next_item, 1);
       item = __shfl_sync(0xffffffffu, item, 0);
       if (item >= nitems) break;
+#endif
       const int chunk = item / kSnicarTasks, task = item - chunk * kSnicarTasks;   // the tasks of a chunk run side by side
       const int flg = task / NBND_SNW + 1, b = task - (flg - 1) * NBND_SNW;
       const int idx = chunk * 32 + lane;
@@ -608,10 +616,10 @@ constexpr uint32_t M_RAD_REST = ELMK_G_FRAC_WET | G_ALBEDO_REST;
 constexpr uint32_t M_SFC = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | ELMK_G_CANOPY_TEMPERATURE |
                            ELMK_G_BAREGROUND_FLUXES;
 constexpr uint32_t M_END = ELMK_G_SNOW_HYDROLOGY | ELMK_G_SURFACE_FLUXES | ELMK_G_CONSERVATION;
-// (register caps = resident blocks per SM, chosen by A/B runs on B200 at 2M columns)
+// (register caps = resident blocks per SM, chosen by A/B runs on B200 at 2M columns: profiles/r2_experiments.md)
 const Launch kFused[] = {
-    {M_RAD, k_groups_occ<M_RAD_REST, 6>, "fracwet+albedo", kBlock, kBlock, kSnicarFirst},
-    ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 10),
+    {M_RAD, k_groups_occ<M_RAD_REST, 4>, "fracwet+albedo", kBlock, kBlock, kSnicarFirst},
+    ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 8),
     {ELMK_G_CANOPY_FLUXES, k_groups<ELMK_G_CANOPY_FLUXES>, "canopy_fluxes", kBlock, kBlock, kCanfluxRepacked},
     ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 8),
     ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 6),
@@ -806,7 +814,7 @@ struct Ctx {
   CanfluxQueue cq = {nullptr, nullptr, nullptr, 0};   // CanopyFluxes re-packing scratch (allocated on first use)
   int iterate_blocks = 0;
   bool repack = true;
-  void (*snicar_fn)(const Cols, const Tables*, double*, int) = k_snicar<3>;
+  void (*snicar_fn)(const Cols, const Tables*, double*, int) = k_snicar<4>;
   double* snicar_scratch = nullptr;   // kSnicarSlice doubles per resident block (allocated on first use)
   int snicar_blocks = 0;
   void (*iterate_fn)(const Cols, const CanfluxQueue) = k_canflux_iterate<kIterBlock, true>;
@@ -1109,7 +1117,7 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
     const char* rp = std::getenv("ELMK_CANFLUX_REPACK");
     if (rp && rp[0] == '0') c->repack = false;
     const char* sn = std::getenv("ELMK_SNICAR_OCC");
-    if (sn) c->snicar_fn = std::atoi(sn) == 4 ? k_snicar<4> : std::atoi(sn) == 2 ? k_snicar<2> : k_snicar<3>;
+    if (sn) c->snicar_fn = std::atoi(sn) == 3 ? k_snicar<3> : std::atoi(sn) == 2 ? k_snicar<2> : k_snicar<4>;
     const char* ib = std::getenv("ELMK_ITER");   // e.g. "256l" = 256-thread lock-step blocks, "128" = 128 threads free-running
     if (ib) {
       const int nb = std::atoi(ib);

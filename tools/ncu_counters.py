@@ -21,7 +21,9 @@ for r in rows[1:]:
     if m.startswith("dram__bytes") and u != "byte":
         v *= {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
     d[m] = v
-GROUP = [("k_init_timestep", "init_timestep"), ("k_groups_sorted<3", "fracwet+albedo"), ("k_groups_occ<60", "hydrology+radiation+temperature+bareground"),
+GROUP = [("k_init_timestep", "init_timestep"), ("k_coszen", "coszen"), ("k_phenology", "phenology"), ("k_atm_forcing", "atm_forcing"),
+         ("k_groups_sorted<3", "fracwet+albedo"), ("k_snicar", "fracwet+albedo"), ("k_groups_occ<1048577", "fracwet+albedo"),
+         ("k_groups_occ<60", "hydrology+radiation+temperature+bareground"),
          ("k_canflux", "canopy_fluxes"), ("k_groups_occ<128", "soil_temperature"), ("k_groups_occ<1792", "snow+surface_fluxes+conservation")]
 res = OrderedDict()
 for d in K.values():
