@@ -216,19 +216,11 @@ __global__ void __launch_bounds__(kSnicarBlock, MINBLOCKS) k_snicar(const Cols S
     const int nact = nactive;
     const int nitems = ((nact + 31) / 32) * kSnicarTasks;
     // ---- the band solves ----
-#ifdef ELMK_SNICAR_LOCKSTEP
-    // (experiment) the warps of the block start every item together: one warp's instruction fetch serves the others
-    for (int round = 0; round * (kSnicarBlock / 32) < nitems; ++round) {
-      __syncthreads();
-      const int item = round * (kSnicarBlock / 32) + (threadIdx.x >> 5);
-      if (item >= nitems) continue;
-#else
     while (true) {
       int item = 0;
       if (lane == 0) item = atomicAdd(&next_item, 1);
       item = __shfl_sync(0xffffffffu, item, 0);
       if (item >= nitems) break;
-#endif
       const int chunk = item / kSnicarTasks, task = item - chunk * kSnicarTasks;   // the tasks of a chunk run side by side
       const int flg = task / NBND_SNW + 1, b = task - (flg - 1) * NBND_SNW;
       const int idx = chunk * 32 + lane;
@@ -506,7 +498,7 @@ __global__ void __launch_bounds__(kBlock) k_phenology(const Cols S, const PhenSe
 
 // elmk_fn_call: one library-level physics function on the flat argument array of ONE column (include/elm/*.h)
 #define FlatRow(ptr) ColRow{(ptr), 1}
-constexpr int kFnSlots[ELMK_FN_COUNT] = {13, 14, 7, 150, 26, 11, 36, 39, 9, 18};
+constexpr int kFnSlots[ELMK_FN_COUNT] = {13, 14, 7, 150, 26, 11, 36, 39, 9, 18, 42, 25, 160, 93, 35, 61, 10, 6, 20, 22, 56};
 __global__ void k_fn_call(const int fn, double* __restrict__ a)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -558,6 +550,75 @@ __global__ void k_fn_call(const int fn, double* __restrict__ a)
                                      FlatRow(a + 9), FlatRow(a + 10), FlatRow(a + 11), FlatRow(a + 12), FlatRow(a + 13),
                                      FlatRow(a + 14), FlatRow(a + 15), a[16], a[17]);
       break;
+    // ---- canopy_temperature (phys_cantemp.h, namespace tmp); layer rows are [nlevsno + nlevgrnd] = 20, soil
+    //      property rows [nlevgrnd] = 15 ----
+    case ELMK_FN_TMP_OLD_GROUND_TEMP:   // t_h2osfc | t_soisno[20] | t_h2osfc_bef | tssbef[20]
+      tmp::old_ground_temp(a[0], FlatRow(a + 1), a[21], FlatRow(a + 22));
+      break;
+    case ELMK_FN_TMP_GROUND_TEMP: {   // snl frac_sno_eff frac_h2osfc t_h2osfc | t_soisno[20] | t_grnd
+      const int snl = (int)a[0];
+      a[24] = tmp::ground_temp(snl, a[1], a[2], a[3], a[4 + NLEVSNO - snl], a[4 + NLEVSNO]);
+    } break;
+    case ELMK_FN_TMP_CALC_SOILALPHA:
+      // frac_sno frac_h2osfc | h2osoi_liq[20] h2osoi_ice[20] dz[20] t_soisno[20] | watsat[15] sucsat[15] bsw[15] watdry[15]
+      // watopt[15] | qred hr soilalpha
+      tmp::calc_soilalpha(a[0], a[1], a[2 + NLEVSNO], a[22 + NLEVSNO], a[42 + NLEVSNO], a[62 + NLEVSNO], a[82], a[97], a[112],
+                          a[157], a[158], a[159]);
+      break;
+    case ELMK_FN_TMP_CALC_SOILBETA:   // frac_sno frac_h2osfc | watsat[15] watfc[15] | h2osoi_liq[20] h2osoi_ice[20] dz[20] | soilbeta
+      a[92] = tmp::calc_soilbeta(a[0], a[1], a[17], a[32 + NLEVSNO], a[52 + NLEVSNO], a[72 + NLEVSNO]);
+      break;
+    case ELMK_FN_TMP_HUMIDITIES: {
+      // snl forc_q forc_pbot t_h2osfc t_grnd frac_sno frac_sno_eff frac_h2osfc qred hr | t_soisno[20] | qg_snow qg_soil qg
+      // qg_h2osfc dqgdT
+      const int snl = (int)a[0];
+      tmp::humidities(snl, a[1], a[2], a[3], a[5], a[6], a[7], a[9], a[10 + NLEVSNO - snl], a[10 + NLEVSNO], a[30], a[31], a[32],
+                      a[33], a[34]);
+    } break;
+    case ELMK_FN_TMP_GROUND_PROPERTIES: {
+      // snl frac_sno forc_th forc_q elai esai htop | displar(vtype) z0mr(vtype) | h2osoi_liq[20] h2osoi_ice[20] | emg emv htvp
+      // z0mg z0hg z0qg z0mv z0hv z0qv thv z0m displa
+      const int top = NLEVSNO - (int)a[0];
+      tmp::ground_properties(a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9 + top], a[29 + top], a[49], a[50], a[51], a[52],
+                             a[53], a[54], a[55], a[56], a[57], a[58], a[59], a[60]);
+    } break;
+    case ELMK_FN_TMP_FORCING_HEIGHT:   // veg_active frac_veg_nosno z0m z0mg forc_t displa | hgt_u hgt_t hgt_q thm
+      tmp::forcing_height(a[0] != 0.0, (int)a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]);
+      break;
+    case ELMK_FN_TMP_INIT_ENERGY_FLUXES:
+      tmp::init_energy_fluxes(a[0], a[1], a[2], a[3], a[4], a[5]);
+      break;
+    // ---- bareground_fluxes (phys_bareground.h, namespace bgf): nothing happens on a column with exposed vegetation,
+    //      except that compute_flux zeroes cgrnd / cgrnds / cgrndl (bareground_fluxes_impl.hh:104-108) ----
+    case ELMK_FN_BGF_INITIALIZE_FLUX:
+      // frac_veg_nosno forc_u forc_v forc_q forc_th forc_hgt_u_patch thm thv t_grnd qg z0mg | dlrad ulrad zldis displa dth dqh
+      // obu ur um
+      if ((int)a[0] == 0)
+        bgf::initialize_flux(a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15],
+                             a[16], a[17], a[18], a[19]);
+      break;
+    case ELMK_FN_BGF_STABILITY_ITERATION:
+      // frac_veg_nosno hgt_t hgt_u hgt_q z0mg zldis displa dth dqh ur forc_q forc_th thv | z0hg z0qg obu um temp1 temp2 temp12m
+      // temp22m ustar
+      if ((int)a[0] == 0)
+        bgf::stability_iteration(a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15],
+                                 a[16], a[17], a[18], a[19], a[20], a[21]);
+      break;
+    case ELMK_FN_BGF_COMPUTE_FLUX: {
+      // frac_veg_nosno snl forc_rho soilbeta dqgdT htvp t_h2osfc qg_snow qg_soil qg_h2osfc | t_soisno[20] | forc_pbot dth dqh
+      // temp1 temp2 temp12m temp22m ustar forc_q thm | cgrnds cgrndl cgrnd eflx_sh_grnd eflx_sh_tot eflx_sh_snow eflx_sh_soil
+      // eflx_sh_h2osfc qflx_evap_soi qflx_evap_tot qflx_ev_snow qflx_ev_soil qflx_ev_h2osfc t_ref2m q_ref2m rh_ref2m
+      a[40] = 0.0; a[41] = 0.0; a[42] = 0.0;
+      if ((int)a[0] == 0) {
+        const int snl = (int)a[1];
+        const bgf::Fluxes f = bgf::compute_flux(a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10 + NLEVSNO - snl],
+                                                a[10 + NLEVSNO], a[30], a[31], a[32], a[33], a[34], a[35], a[36], a[37], a[38], a[39]);
+        a[40] = f.cgrnds; a[41] = f.cgrndl; a[42] = f.cgrnd; a[43] = f.eflx_sh_grnd; a[44] = f.eflx_sh_grnd;
+        a[45] = f.eflx_sh_snow; a[46] = f.eflx_sh_soil; a[47] = f.eflx_sh_h2osfc; a[48] = f.qflx_evap_soi; a[49] = f.qflx_evap_soi;
+        a[50] = f.qflx_ev_snow; a[51] = f.qflx_ev_soil; a[52] = f.qflx_ev_h2osfc; a[53] = f.t_ref2m; a[54] = f.q_ref2m;
+        a[55] = f.rh_ref2m;
+      }
+    } break;
     default: break;
   }
 }
@@ -618,7 +679,7 @@ constexpr uint32_t M_SFC = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | 
 constexpr uint32_t M_END = ELMK_G_SNOW_HYDROLOGY | ELMK_G_SURFACE_FLUXES | ELMK_G_CONSERVATION;
 // (register caps = resident blocks per SM, chosen by A/B runs on B200 at 2M columns: profiles/r2_experiments.md)
 const Launch kFused[] = {
-    {M_RAD, k_groups_occ<M_RAD_REST, 4>, "fracwet+albedo", kBlock, kBlock, kSnicarFirst},
+    {M_RAD, k_groups_occ<M_RAD_REST, 6>, "fracwet+albedo", kBlock, kBlock, kSnicarFirst},
     ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 8),
     {ELMK_G_CANOPY_FLUXES, k_groups<ELMK_G_CANOPY_FLUXES>, "canopy_fluxes", kBlock, kBlock, kCanfluxRepacked},
     ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 8),

@@ -53,4 +53,13 @@ struct StepArgs {
 #define C1(field) S.field[c]
 #define C2(field, lev) S.field[(long long)(lev) * S.np + c]
 
+// row of a multi-level field of one column: in the column-innermost layout of the state (ELMK_ROW), or contiguous
+// (stride 1: per-thread rows and the flat argument arrays of elmk_fn_call)
+struct ColRow {
+  double* p;
+  long long stride;
+  ELMK_HD double& operator[](const int i) const { return p[(long long)i * stride]; }
+};
+#define ELMK_ROW(field) ColRow{S.field + c, S.np}
+
 } // namespace elmk

@@ -470,7 +470,7 @@ ELMK_HD void column_albedo(const Cols& S, const Tables& T, const int c)
   const bool snicar_ran = SNICAR_DONE && (coszen > 0.0) && (h2osno > MIN_SNW);
   if (snicar_ran) {
     albsnd[0] = C2(albsnd, 0); albsnd[1] = C2(albsnd, 1); albsni[0] = C2(albsni, 0); albsni[1] = C2(albsni, 1);
-  } else if ((coszen > 0.0) && (h2osno > MIN_SNW)) {
+  } else if (!SNICAR_DONE && (coszen > 0.0) && (h2osno > MIN_SNW)) {
     snicar_solve(S, T, c, 1, coszen, h2osno, snl, albsoi, albsnd, flx_absd_snw, err);
     snicar_solve(S, T, c, 2, coszen, h2osno, snl, albsoi, albsni, flx_absi_snw, err);
   } else if ((coszen > 0.0) && (h2osno < MIN_SNW) && (h2osno > 0.0)) {

@@ -51,6 +51,138 @@ ELMK_HD void qsat(const double T, const double p, double& es, double& esdT, doub
   es = q.es; esdT = q.esdT; qs = q.qs; qsdT = q.qsdT;
 }
 
+// The eight functions of the group, one per reference function (the library-level API of include/elm/
+// canopy_temperature.h calls them one by one through elmk_fn_call; the column body below composes them).  Layer
+// values arrive as scalars: the caller picks the top snow / first soil layer out of its rows.
+namespace tmp {
+
+// old_ground_temp :9-29 - the temperatures the solver starts from
+ELMK_HD void old_ground_temp(const double t_h2osfc, const ColRow t_soisno, double& t_h2osfc_bef, const ColRow tssbef)
+{
+#pragma unroll
+  for (int i = 0; i < NLEVTOT; ++i) tssbef[i] = t_soisno[i];
+  t_h2osfc_bef = t_h2osfc;
+}
+
+// ground_temp :32-48; t_top = t_soisno(nlevsno - snl), t_soil1 = t_soisno(nlevsno)
+ELMK_HD double ground_temp(const int snl, const double fsno_eff, const double fsfc, const double t_sfc, const double t_top,
+                           const double t_soil1)
+{
+  if (snl > 0) return fsno_eff * t_top + (1.0 - fsno_eff - fsfc) * t_soil1 + fsfc * t_sfc;
+  return (1.0 - fsfc) * t_soil1 + fsfc * t_sfc;
+}
+
+// partial volume of ice and water of the first soil layer (calc_soilalpha :82, calc_soilevap_stress :27)
+ELMK_HD double surface_wetness(const double liq1, const double ice1, const double dz1)
+{
+  return (liq1 / DENH2O + ice1 / DENICE) / dz1;
+}
+
+// calc_soilalpha :51-130, soil / crop branch
+ELMK_HD void calc_soilalpha(const double fsno, const double fsfc, const double liq1, const double ice1, const double dz1,
+                            const double t_soil1, const double watsat1, const double sucsat1, const double bsw1, double& qred,
+                            double& hr, double& soilalpha)
+{
+  const double wx = surface_wetness(liq1, ice1, dz1);
+  double fac = dmin(1.0, wx / watsat1);
+  fac = dmax(fac, 0.01);
+  double psit = -sucsat1 * m_pow(fac, (-bsw1));
+  psit = dmax(-1.e8, psit);
+  hr = m_exp(psit / ROVERG / t_soil1);
+  qred = (1.0 - fsno - fsfc) * hr + fsno + fsfc;
+  soilalpha = qred;
+}
+
+// calc_soilbeta :133-140 -> surface_resistance::calc_soilevap_stress (surface_resistance_impl.hh:9-46), Lee & Pielke beta
+ELMK_HD double calc_soilbeta(const double fsno, const double fsfc, const double watfc1, const double liq1, const double ice1,
+                             const double dz1)
+{
+  const double wx = surface_wetness(liq1, ice1, dz1);
+  if (wx < watfc1) {
+    double fac_fc = dmin(1.0, wx / watfc1);
+    fac_fc = dmax(fac_fc, 0.01);
+    return (1.0 - fsno - fsfc) * 0.25 * sq(1.0 - m_cos(PI * fac_fc)) + fsno + fsfc;
+  }
+  return 1.0;
+}
+
+// humidities :143-202, soil / crop branch
+ELMK_HD void humidities(const int snl, const double forc_q, const double pbot, const double t_sfc, const double fsno,
+                        const double fsno_eff, const double fsfc, const double hr, const double t_top, const double t_soil1,
+                        double& qg_snow, double& qg_soil, double& qg, double& qg_h2osfc, double& dqgdT)
+{
+  double eg, degdT, qsatg, qsatgdT;
+  qsat(t_top, pbot, eg, degdT, qsatg, qsatgdT);
+  // (the reference's guard "qsatg > forc_q && forc_q > qsatg" can never hold: SURVEY.md quirk 6)
+  qg_snow = qsatg;
+  dqgdT = fsno * qsatgdT;
+  qsat(t_soil1, pbot, eg, degdT, qsatg, qsatgdT);
+  if (qsatg > forc_q && forc_q > hr * qsatg) {
+    qsatg = forc_q;
+    qsatgdT = 0.0;
+  }
+  qg_soil = hr * qsatg;
+  dqgdT = dqgdT + (1.0 - fsno - fsfc) * hr * qsatgdT;
+  if (snl == 0) {
+    qg_snow = qg_soil;
+    dqgdT = (1.0 - fsfc) * hr * dqgdT;
+  }
+  qsat(t_sfc, pbot, eg, degdT, qsatg, qsatgdT);
+  qg_h2osfc = qsatg;
+  dqgdT = dqgdT + fsfc * qsatgdT;
+  qg = fsno_eff * qg_snow + (1.0 - fsno_eff - fsfc) * qg_soil + fsfc * qg_h2osfc;
+}
+
+// ground_properties :205-257; displar_v / z0mr_v = the PFT-table entries at Land.vtype, liq_top / ice_top = the
+// water contents of layer nlevsno - snl
+ELMK_HD void ground_properties(const double fsno, const double forc_th, const double forc_q, const double elai,
+                               const double esai, const double htop, const double displar_v, const double z0mr_v,
+                               const double liq_top, const double ice_top, double& emg, double& emv, double& htvp,
+                               double& z0mg, double& z0hg, double& z0qg, double& z0mv, double& z0hv, double& z0qv, double& thv,
+                               double& z0m, double& displa)
+{
+  emg = (1.0 - fsno) * 0.96 + fsno * 0.97;
+  emv = 1.0 - m_exp(-(elai + esai) / 1.0);
+  htvp = HVAP;
+  if (liq_top <= 0 && ice_top > 0.0) htvp = HSUB;
+  z0mg = (fsno > 0.0) ? ZSNO : ZLND;
+  z0hg = z0mg;
+  z0qg = z0mg;
+  z0m = z0mr_v * htop;
+  displa = displar_v * htop;
+  z0mv = z0m;
+  z0hv = z0m;
+  z0qv = z0m;
+  thv = forc_th * (1.0 + 0.61 * forc_q);
+}
+
+// forcing_height :260-296, soil / crop branch: the patch heights accumulate (+=) on top of the per-step reset
+ELMK_HD void forcing_height(const bool veg_active, const int frac_veg_nosno, const double z0m, const double z0mg,
+                            const double forc_t, const double displa, double& hu, double& ht, double& hq, double& thm)
+{
+  if (veg_active) {
+    const double add = (frac_veg_nosno == 0) ? z0mg + displa : z0m + displa;
+    hu += add;
+    ht += add;
+    hq += add;
+  }
+  thm = forc_t + 0.0098 * ht;
+}
+
+// init_energy_fluxes :299-332
+ELMK_HD void init_energy_fluxes(double& eflx_sh_tot, double& eflx_lh_tot, double& eflx_sh_veg, double& qflx_evap_tot,
+                                double& qflx_evap_veg, double& qflx_tran_veg)
+{
+  eflx_sh_tot = 0.0;
+  eflx_lh_tot = 0.0;
+  eflx_sh_veg = 0.0;
+  qflx_evap_tot = 0.0;
+  qflx_evap_veg = 0.0;
+  qflx_tran_veg = 0.0;
+}
+
+} // namespace tmp
+
 ELMK_HD void column_canopy_temperature(const Cols& S, const Tables& T, const int c)
 {
   const int snl = C1(snl);
@@ -58,114 +190,55 @@ ELMK_HD void column_canopy_temperature(const Cols& S, const Tables& T, const int
   const double fsno = C1(frac_sno), fsno_eff = C1(frac_sno_eff), fsfc = C1(frac_h2osfc);
   const double t_sfc = C1(t_h2osfc);
 
-  // -- old_ground_temp: remember the temperatures the solver starts from --
-#pragma unroll
-  for (int i = 0; i < NLEVTOT; ++i) C2(tssbef, i) = C2(t_soisno, i);
-  C1(t_h2osfc_bef) = t_sfc;
-
+  double t_sfc_bef;
+  tmp::old_ground_temp(t_sfc, ELMK_ROW(t_soisno), t_sfc_bef, ELMK_ROW(tssbef));
+  C1(t_h2osfc_bef) = t_sfc_bef;
   const double t_soil1 = C2(t_soisno, NLEVSNO);
   const double t_top = C2(t_soisno, top);   // == t_soil1 when snl == 0
+  C1(t_grnd) = tmp::ground_temp(snl, fsno_eff, fsfc, t_sfc, t_top, t_soil1);
 
-  // -- ground_temp --
-  double tg;
-  if (snl > 0) {
-    tg = fsno_eff * t_top + (1.0 - fsno_eff - fsfc) * t_soil1 + fsfc * t_sfc;
-  } else {
-    tg = (1.0 - fsfc) * t_soil1 + fsfc * t_sfc;
-  }
-  C1(t_grnd) = tg;
-
-  // -- calc_soilalpha (qred, hr) and calc_soilbeta (Lee & Pielke beta) --
   const double liq1 = C2(h2osoi_liq, NLEVSNO), ice1 = C2(h2osoi_ice, NLEVSNO), dz1 = C2(dz, NLEVSNO);
-  const double watsat1 = C2(watsat, 0);
-  const double wx = (liq1 / DENH2O + ice1 / DENICE) / dz1;
-  double fac = dmin(1.0, wx / watsat1);
-  fac = dmax(fac, 0.01);
-  double psit = -C2(sucsat, 0) * m_pow(fac, (-C2(bsw, 0)));
-  psit = dmax(-1.e8, psit);
-  const double hr = m_exp(psit / ROVERG / t_soil1);
-  // qred = (1 - fsno - fsfc) hr + fsno + fsfc is computed by the reference but only feeds soilalpha (unused)
+  double qred, hr, soilalpha;   // (qred only feeds soilalpha, which nothing on the chain reads)
+  tmp::calc_soilalpha(fsno, fsfc, liq1, ice1, dz1, t_soil1, C2(watsat, 0), C2(sucsat, 0), C2(bsw, 0), qred, hr, soilalpha);
+  C1(soilbeta) = tmp::calc_soilbeta(fsno, fsfc, C2(watfc, 0), liq1, ice1, dz1);
 
-  const double watfc1 = C2(watfc, 0);
-  double soilbeta;
-  if (wx < watfc1) {
-    double fac_fc = dmin(1.0, wx / watfc1);
-    fac_fc = dmax(fac_fc, 0.01);
-    soilbeta = (1.0 - fsno - fsfc) * 0.25 * sq(1.0 - m_cos(PI * fac_fc)) + fsno + fsfc;
-  } else {
-    soilbeta = 1.0;
-  }
-  C1(soilbeta) = soilbeta;
-
-  // -- humidities --
-  const double forc_q = C1(forc_qbot), pbot = C1(forc_pbot);
-  double eg, degdT, qsatg, qsatgdT;
-  qsat(t_top, pbot, eg, degdT, qsatg, qsatgdT);
-  // (the reference's guard "qsatg > forc_q && forc_q > qsatg" can never hold: SURVEY.md quirk 6)
-  double qg_snow = qsatg;
-  double dqgdT = fsno * qsatgdT;
-  qsat(t_soil1, pbot, eg, degdT, qsatg, qsatgdT);
-  if (qsatg > forc_q && forc_q > hr * qsatg) {
-    qsatg = forc_q;
-    qsatgdT = 0.0;
-  }
-  const double qg_soil = hr * qsatg;
-  dqgdT = dqgdT + (1.0 - fsno - fsfc) * hr * qsatgdT;
-  if (snl == 0) {
-    qg_snow = qg_soil;
-    dqgdT = (1.0 - fsfc) * hr * dqgdT;
-  }
-  qsat(t_sfc, pbot, eg, degdT, qsatg, qsatgdT);
-  const double qg_h2osfc = qsatg;
-  dqgdT = dqgdT + fsfc * qsatgdT;
+  const double forc_q = C1(forc_qbot);
+  double qg_snow, qg_soil, qg, qg_h2osfc, dqgdT;
+  tmp::humidities(snl, forc_q, C1(forc_pbot), t_sfc, fsno, fsno_eff, fsfc, hr, t_top, t_soil1, qg_snow, qg_soil, qg, qg_h2osfc,
+                  dqgdT);
   C1(qg_snow) = qg_snow;
   C1(qg_soil) = qg_soil;
   C1(qg_h2osfc) = qg_h2osfc;
   C1(dqgdT) = dqgdT;
-  C1(qg) = fsno_eff * qg_snow + (1.0 - fsno_eff - fsfc) * qg_soil + fsfc * qg_h2osfc;
+  C1(qg) = qg;
 
-  // -- ground_properties --
-  const double lsai = C1(elai) + C1(esai);
-  C1(emg) = (1.0 - fsno) * 0.96 + fsno * 0.97;
-  C1(emv) = 1.0 - m_exp(-lsai / 1.0);
-  double htvp = HVAP;
-  if (C2(h2osoi_liq, top) <= 0 && C2(h2osoi_ice, top) > 0.0) htvp = HSUB;
-  C1(htvp) = htvp;
-  const double z0mg = (fsno > 0.0) ? ZSNO : ZLND;
-  C1(z0mg) = z0mg;
-  C1(z0hg) = z0mg;
-  C1(z0qg) = z0mg;
   // the reference indexes the PFT tables with the GLOBAL Land.vtype here
-  const double htop = C1(htop);
-  const double z0m = T.z0mr[T.vtype] * htop;
-  const double displa = T.displar[T.vtype] * htop;
+  double emg, emv, htvp, z0mg, z0hg, z0qg, z0mv, z0hv, z0qv, thv, z0m, displa;
+  tmp::ground_properties(fsno, C1(forc_thbot), forc_q, C1(elai), C1(esai), C1(htop), T.displar[T.vtype], T.z0mr[T.vtype],
+                         C2(h2osoi_liq, top), C2(h2osoi_ice, top), emg, emv, htvp, z0mg, z0hg, z0qg, z0mv, z0hv, z0qv, thv, z0m,
+                         displa);
+  C1(emg) = emg;
+  C1(emv) = emv;
+  C1(htvp) = htvp;
+  C1(z0mg) = z0mg;
+  C1(z0hg) = z0hg;
+  C1(z0qg) = z0qg;
   C1(z0m) = z0m;
   C1(displa) = displa;
-  C1(z0mv) = z0m;
-  C1(z0hv) = z0m;
-  C1(z0qv) = z0m;
-  C1(thv) = C1(forc_thbot) * (1.0 + 0.61 * forc_q);
+  C1(z0mv) = z0mv;
+  C1(z0hv) = z0hv;
+  C1(z0qv) = z0qv;
+  C1(thv) = thv;
 
-  // -- forcing_height: the patch heights accumulate (+=) on top of the per-step reset to forc_hgt --
-  double hu = C1(forc_hgt_u_patch), ht = C1(forc_hgt_t_patch), hq = C1(forc_hgt_q_patch);
-  if (C1(veg_active)) {
-    const double add = (C1(frac_veg_nosno) == 0) ? z0mg + displa : z0m + displa;
-    hu += add;
-    ht += add;
-    hq += add;
-  }
+  double hu = C1(forc_hgt_u_patch), ht = C1(forc_hgt_t_patch), hq = C1(forc_hgt_q_patch), thm;
+  tmp::forcing_height(C1(veg_active) != 0, C1(frac_veg_nosno), z0m, z0mg, C1(forc_tbot), displa, hu, ht, hq, thm);
+  C1(thm) = thm;
   C1(forc_hgt_u_patch) = hu;
   C1(forc_hgt_t_patch) = ht;
   C1(forc_hgt_q_patch) = hq;
-  C1(thm) = C1(forc_tbot) + 0.0098 * ht;
 
-  // -- init_energy_fluxes --
-  C1(eflx_sh_tot) = 0.0;
-  C1(eflx_lh_tot) = 0.0;
-  C1(eflx_sh_veg) = 0.0;
-  C1(qflx_evap_tot) = 0.0;
-  C1(qflx_evap_veg) = 0.0;
-  C1(qflx_tran_veg) = 0.0;
+  tmp::init_energy_fluxes(C1(eflx_sh_tot), C1(eflx_lh_tot), C1(eflx_sh_veg), C1(qflx_evap_tot), C1(qflx_evap_veg),
+                          C1(qflx_tran_veg));
 }
 
 } // namespace elmk

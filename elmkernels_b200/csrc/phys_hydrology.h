@@ -17,13 +17,6 @@ namespace elmk {
 // LandType, rows through any accessor with operator[]), so that the fused column kernels and the library-level
 // ELM::canopy_hydrology::* entry points (include/elm/canopy_hydrology.h -> elmk_fn_call) run the same device code.
 
-// row of a multi-level field of one column in the column-innermost layout
-struct ColRow {
-  double* p;
-  long long stride;
-  ELMK_HD double& operator[](const int i) const { return p[(long long)i * stride]; }
-};
-#define ELMK_ROW(field) ColRow{S.field + c, S.np}
 
 namespace hyd {
 // ---- a1: fraction_wet (canopy_hydrology_impl.hh:123-142) ----

@@ -331,7 +331,18 @@ int elmk_math_eval(elmk_handle h, int fn, int64_t n, const double* x, const doub
 #define ELMK_FN_RAD_LAYER_ABSORBED 7  /* surface_radiation::layer_absorbed_radiation  :77   39 slots (last: 0 where the reference asserts) */
 #define ELMK_FN_RAD_REFLECTED 8       /* surface_radiation::reflected_radiation       :179   9 slots */
 #define ELMK_FN_RAD_SUNSHADE 9        /* surface_radiation::canopy_sunshade_fractions :202  18 slots */
-#define ELMK_FN_COUNT 10
+#define ELMK_FN_TMP_OLD_GROUND_TEMP 10   /* canopy_temperature::old_ground_temp     canopy_temperature_impl.hh:9   42 slots */
+#define ELMK_FN_TMP_GROUND_TEMP 11       /* canopy_temperature::ground_temp         :32   25 slots */
+#define ELMK_FN_TMP_CALC_SOILALPHA 12    /* canopy_temperature::calc_soilalpha      :51  160 slots */
+#define ELMK_FN_TMP_CALC_SOILBETA 13     /* canopy_temperature::calc_soilbeta       :133  93 slots */
+#define ELMK_FN_TMP_HUMIDITIES 14        /* canopy_temperature::humidities          :143  35 slots */
+#define ELMK_FN_TMP_GROUND_PROPERTIES 15 /* canopy_temperature::ground_properties   :205  61 slots (displar, z0mr: the Land.vtype entries) */
+#define ELMK_FN_TMP_FORCING_HEIGHT 16    /* canopy_temperature::forcing_height      :260  10 slots */
+#define ELMK_FN_TMP_INIT_ENERGY_FLUXES 17 /* canopy_temperature::init_energy_fluxes :299   6 slots */
+#define ELMK_FN_BGF_INITIALIZE_FLUX 18     /* bareground_fluxes::initialize_flux      bareground_fluxes_impl.hh:7   20 slots */
+#define ELMK_FN_BGF_STABILITY_ITERATION 19 /* bareground_fluxes::stability_iteration  :30   22 slots */
+#define ELMK_FN_BGF_COMPUTE_FLUX 20        /* bareground_fluxes::compute_flux         :82   56 slots */
+#define ELMK_FN_COUNT 21
 int elmk_fn_call(int device, int fn, double* args, int64_t nargs);
 
 /* raw device pointer + level stride of a field (for zero-copy interop with torch tensors) */

@@ -35,7 +35,9 @@ def build(force=False):
 # read at run time are copied next to the binaries (build output: git-ignored, travels with the snapshot).
 REF_TESTS = {"CanHydro": ["CanopyHydrology_IN.txt", "CanopyHydrology_OUT.txt"],
              "SurfRad": ["SurfaceRadiation_IN.txt", "SurfaceRadiation_OUT.txt"],
-             "CanSunShade": ["CanopySunShadeFractions_IN.txt", "CanopySunShadeFractions_OUT.txt"]}
+             "CanSunShade": ["CanopySunShadeFractions_IN.txt", "CanopySunShadeFractions_OUT.txt"],
+             "CanTemp": ["CanopyTemperature_IN.txt", "CanopyTemperature_OUT.txt"],
+             "BGFlux": ["BareGroundFluxes_IN.txt", "BareGroundFluxes_OUT.txt"]}
 
 
 def build_reference_tests(force=False):

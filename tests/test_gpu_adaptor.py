@@ -78,7 +78,8 @@ def test_adaptor_advances_the_reference_state_on_the_gpu(checker, cuda_lib, para
     assert not bad, f"state members that differ from the checker after {nsteps} + 1 steps through the adaptor: {bad}"
 
 
-@pytest.mark.parametrize("name,checks", [("CanHydro", 1824), ("SurfRad", 1440), ("CanSunShade", 768)])
+@pytest.mark.parametrize("name,checks", [("CanHydro", 1824), ("SurfRad", 1440), ("CanSunShade", 768), ("CanTemp", 2784),
+                                         ("BGFlux", 2064)])
 def test_reference_unit_test_runs_on_the_gpu_through_the_function_api(name, checks):
     """The reference's own test/test_<name>.cc, compiled unchanged against include/elm/ (the library-level ELM::<ns>::<fn>
     API of this repository in place of the reference's src/physics) and linked against libelmk_b200.so: every physics
