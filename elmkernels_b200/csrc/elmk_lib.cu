@@ -98,42 +98,19 @@ __device__ __forceinline__ void run_groups(const Cols& S, const Tables& T, const
 #undef ELMK_GROUP
 }
 
-// ---- bulk prefetch of a block's input rows into L2 (TMA engine: cp.async.bulk.prefetch.L2, SASS UBLKPF) ----------
-// With the column-innermost layout every (field, level) row of a block's 128 columns is one contiguous, 16-byte
-// aligned segment of 1 KB (doubles).  The unsorted launches are bound by memory latency (ncu: long_scoreboard
-// 10-16 stalled slots per issue at ~2 TB/s): their loads sit between calls and data-dependent branches, so a warp
-// has one or two of them in flight.  The first warps of a block therefore ask the TMA engine for all rows the
-// block is going to read, before the column work starts; the demand loads then find their sectors in L2.
-__device__ __forceinline__ void prefetch_row(const void* p, const unsigned bytes)
-{
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-template <class T>
-__device__ __forceinline__ void prefetch_field(const Cols& S, const T* base, const int lev0, const int nlev, int& row, const int col0)
-{
-  // one row per thread, rows numbered across all fields of the list
-  for (int l = 0; l < nlev; ++l, ++row)
-    if (row % kBlock == (int)threadIdx.x) prefetch_row(base + (long long)(lev0 + l) * S.np + col0, (unsigned)(kBlock * sizeof(T)));
-}
-template <uint32_t MASK> __device__ __forceinline__ void prefetch_inputs(const Cols& S)
-{
+// ---- (experiment, -DELMK_BULK_PREFETCH) bulk prefetch of a block's input rows into L2 through the TMA engine:
+// cp.async.bulk.prefetch.L2, SASS UBLKPF.  With the column-innermost layout every (field, level) row of a block's 128
+// columns is one contiguous, 16-byte aligned segment of 1 KB.  The host passes the list of row base pointers the
+// launch is going to read (StepArgs::pf_rows, built once per handle); thread t of a block asks for rows t, t + 128, ...
+// before the column work starts.  Measured and not adopted: profiles/r2_experiments.md.
 #ifdef ELMK_BULK_PREFETCH
-  const int col0 = blockIdx.x * kBlock;
-  int row = 0;
-#define PF(field, lev0, nlev) prefetch_field(S, S.field, lev0, nlev, row, col0);
-  if (MASK & ELMK_G_SOIL_TEMPERATURE) {
-    PF(t_soisno, 0, 20) PF(zsoi, 0, 20) PF(h2osoi_liq, 0, 20) PF(h2osoi_ice, 0, 20) PF(dz, 0, 20) PF(zisoi, 0, 21)
-    PF(watsat, 0, 15) PF(tkdry, 0, 15) PF(tkmg, 0, 15) PF(csol, 5, 15) PF(sucsat, 0, 15) PF(bsw, 0, 15) PF(sabg_lyr, 0, 6)
-    PF(frac_sno, 0, 1) PF(frac_sno_eff, 0, 1) PF(frac_h2osfc, 0, 1) PF(h2osfc, 0, 1) PF(h2osno, 0, 1) PF(t_h2osfc, 0, 1)
-    PF(dlrad, 0, 1) PF(emg, 0, 1) PF(forc_lwrad, 0, 1) PF(htvp, 0, 1) PF(sabg_soil, 0, 1) PF(sabg_snow, 0, 1)
-    PF(eflx_sh_soil, 0, 1) PF(qflx_ev_soil, 0, 1) PF(eflx_sh_h2osfc, 0, 1) PF(qflx_ev_h2osfc, 0, 1) PF(eflx_sh_snow, 0, 1)
-    PF(qflx_ev_snow, 0, 1) PF(cgrnd, 0, 1) PF(t_grnd, 0, 1) PF(int_snow, 0, 1) PF(snow_depth, 0, 1)
-  }
-#undef PF
-#else
-  (void)S;
-#endif
+__device__ __forceinline__ void prefetch_rows(const StepArgs& A)
+{
+  const long long off = (long long)blockIdx.x * kBlock * (long long)sizeof(double);
+  for (int r = threadIdx.x; r < A.pf_nrows; r += kBlock)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.pf_rows[r] + off), "r"((unsigned)(kBlock * sizeof(double))) : "memory");
 }
+#endif
 
 template <uint32_t MASK>
 __global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
@@ -146,7 +123,9 @@ __global__ void __launch_bounds__(kBlock) k_groups(const Cols S, const Tables* _
 template <uint32_t MASK, int MINBLOCKS>
 __global__ void __launch_bounds__(kBlock, MINBLOCKS) k_groups_occ(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
 {
-  prefetch_inputs<MASK>(S);
+#ifdef ELMK_BULK_PREFETCH
+  if (A.pf_nrows) prefetch_rows(A);
+#endif
   const int c = blockIdx.x * kBlock + threadIdx.x;
   if (!kWholeBlocks<MASK> && c >= S.ncols) return;
   run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c, c < S.ncols);
@@ -877,6 +856,10 @@ struct Ctx {
   bool repack = true;
   void (*snicar_fn)(const Cols, const Tables*, double*, int) = k_snicar<4>;
   double* snicar_scratch = nullptr;   // kSnicarSlice doubles per resident block (allocated on first use)
+#ifdef ELMK_BULK_PREFETCH
+  const char** pf_rows = nullptr;
+  int pf_nrows = 0;
+#endif
   int snicar_blocks = 0;
   void (*iterate_fn)(const Cols, const CanfluxQueue) = k_canflux_iterate<kIterBlock, true>;
   int iterate_block = kIterBlock;
@@ -1809,7 +1792,31 @@ int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_
       c->launches += 2;
     } else if (want == L.mask) {
       TimedScope ts(c, L.name, L.mask);
+#ifdef ELMK_BULK_PREFETCH
+      StepArgs Ap = A;
+      if (L.mask == ELMK_G_SOIL_TEMPERATURE && !std::getenv("ELMK_NO_PREFETCH")) {
+        if (!c->pf_rows) {
+          std::vector<const char*> rows;
+          const Cols& S = c->cols;
+#define PF(field, lev0, nlev) for (int l = 0; l < (nlev); ++l) rows.push_back((const char*)(S.field + (long long)((lev0) + l) * S.np));
+          PF(t_soisno, 0, 20) PF(zsoi, 0, 20) PF(h2osoi_liq, 0, 20) PF(h2osoi_ice, 0, 20) PF(dz, 0, 20) PF(zisoi, 0, 21)
+          PF(watsat, 0, 15) PF(tkdry, 0, 15) PF(tkmg, 0, 15) PF(csol, 5, 15) PF(sucsat, 0, 15) PF(bsw, 0, 15) PF(sabg_lyr, 0, 6)
+          PF(frac_sno, 0, 1) PF(frac_sno_eff, 0, 1) PF(frac_h2osfc, 0, 1) PF(h2osfc, 0, 1) PF(h2osno, 0, 1) PF(t_h2osfc, 0, 1)
+          PF(dlrad, 0, 1) PF(emg, 0, 1) PF(forc_lwrad, 0, 1) PF(htvp, 0, 1) PF(sabg_soil, 0, 1) PF(sabg_snow, 0, 1)
+          PF(eflx_sh_soil, 0, 1) PF(qflx_ev_soil, 0, 1) PF(eflx_sh_h2osfc, 0, 1) PF(qflx_ev_h2osfc, 0, 1) PF(eflx_sh_snow, 0, 1)
+          PF(qflx_ev_snow, 0, 1) PF(cgrnd, 0, 1) PF(t_grnd, 0, 1) PF(int_snow, 0, 1) PF(snow_depth, 0, 1)
+#undef PF
+          c->pf_nrows = (int)rows.size();
+          CU(cudaMalloc(&c->pf_rows, sizeof(char*) * rows.size()));
+          CU(cudaMemcpy(c->pf_rows, rows.data(), sizeof(char*) * rows.size(), cudaMemcpyHostToDevice));
+        }
+        Ap.pf_rows = c->pf_rows;
+        Ap.pf_nrows = c->pf_nrows;
+      }
+      L.fn<<<grid_for(L), L.block, 0, c->stream>>>(c->cols, c->d_tables, Ap);
+#else
       L.fn<<<grid_for(L), L.block, 0, c->stream>>>(c->cols, c->d_tables, A);
+#endif
       c->launches += 1;
     } else {
       for (const Launch& G : kSplit) {

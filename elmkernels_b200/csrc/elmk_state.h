@@ -47,6 +47,10 @@ struct Tables {
 // per-step scalars
 struct StepArgs {
   double dtime, dayl, max_dayl;
+#ifdef ELMK_BULK_PREFETCH   // (experiment: row base pointers for the bulk L2 prefetch of csrc/elmk_lib.cu)
+  const char* const* pf_rows = nullptr;
+  int pf_nrows = 0;
+#endif
 };
 
 // field accessors used by the physics bodies: S is a `const Cols&`, c the column index
