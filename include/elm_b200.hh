@@ -180,6 +180,16 @@ public:
   // start_idx, wt1, wt2: monthly_data::first_month_idx / monthly_data_weights
   void phenology(int start_idx, double wt1, double wt2) { check(elmk_phenology(h_, start_idx, wt1, wt2), "elmk_phenology"); }
 
+  // solar geometry of kokkos_init_timestep (init_timestep_kokkos.cc:27-35): coordinates once (n == 1: the reference's
+  // single site for all columns), then per step average_cosz of every column on the device; the day lengths it
+  // returns are kept for step().  decday = Utils::decimal_doy(current) + 1, doy1 = current.doy + 1.
+  void set_coordinates(const double* lat_r, const double* lon_r, int64_t n = 1) {
+    check(elmk_set_coordinates(h_, lat_r, lon_r, n), "elmk_set_coordinates");
+  }
+  void solar_step(double dtime, double decday, int doy1) {
+    check(elmk_solar_step(h_, dtime, decday, doy1, &dayl_, &max_dayl_), "elmk_solar_step");
+  }
+
   // ---- stepping ----
   // per-column part of kokkos_init_timestep (init_timestep_kokkos.cc:53-72) incl. the reset of forc_hgt_*_patch
   void init_timestep(bool reset_forc_hgt = true) { check(elmk_init_timestep(h_, reset_forc_hgt ? 1 : 0), "elmk_init_timestep"); }
