@@ -170,6 +170,8 @@ class Workload:
         self.F, self.cfg, self.key, self.n = forcing, cfg, key, n
         self.cols = lib.columns(n, device=device)
         self.cols.set_tables(P)
+        if os.environ.get("ELMK_PLAN"):   # development: "split" = one launch per kernel group (per-group times)
+            self.cols.set_plan(os.environ["ELMK_PLAN"])
         self.step_no = 0
         full = key == 5
         ntimes = RING
@@ -474,7 +476,7 @@ def main():
     launches = cols.launch_count - l0
     kern = cols.timing_read()
     cols.timing(False)
-    hist = cols.canflux_pass_histogram() if key in (4, 5) else None
+    hist = cols.canflux_pass_histogram() if key in (4, 5) and not os.environ.get("ELMK_PLAN") else None
 
     # ---- end to end: host buffers in, per-column results out, every step, through the C ABI ----
     out_fields = cfg["out"]

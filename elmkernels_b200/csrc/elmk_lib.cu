@@ -648,8 +648,8 @@ const Launch kSplit[] = {
     ELMK_LAUNCH(ELMK_G_CONSERVATION, "conservation"),
 };
 // plan "fused" (the default): the chain cut where register pressure changes character -
-//   radiative transfer (SNICAR kernel, then soil / ground albedo + two-stream) | closed-form hydrology / radiation /
-//   temperature + bare-ground fluxes | canopy-flux iteration (re-packed) | banded solve | snow state machine + flux
+//   radiative transfer (SNICAR kernel, then soil / ground albedo + two-stream) | closed-form hydrology | radiation |
+//   temperature | bare-ground fluxes | canopy-flux iteration (re-packed) | banded solve | snow state machine + flux
 //   update + diagnostics
 constexpr uint32_t M_RAD = ELMK_G_FRAC_WET | ELMK_G_ALBEDO;
 constexpr uint32_t M_RAD_REST = ELMK_G_FRAC_WET | G_ALBEDO_REST;
@@ -659,7 +659,12 @@ constexpr uint32_t M_END = ELMK_G_SNOW_HYDROLOGY | ELMK_G_SURFACE_FLUXES | ELMK_
 // (register caps = resident blocks per SM, chosen by A/B runs on B200 at 2M columns: profiles/r2_experiments.md)
 const Launch kFused[] = {
     {M_RAD, k_groups_occ<M_RAD_REST, 6>, "fracwet+albedo", kBlock, kBlock, kSnicarFirst},
-    ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 8),
+    // (the closed-form surface groups run faster as four launches than fused - 1.54 vs 1.82 ms per 2M columns: each is
+    //  near its own HBM or latency bound at its own register count; profiles/r2_experiments.md)
+    ELMK_LAUNCH(ELMK_G_CANOPY_HYDROLOGY, "canopy_hydrology"),
+    ELMK_LAUNCH(ELMK_G_SURFACE_RADIATION, "surface_radiation"),
+    ELMK_LAUNCH(ELMK_G_CANOPY_TEMPERATURE, "canopy_temperature"),
+    ELMK_LAUNCH(ELMK_G_BAREGROUND_FLUXES, "bareground_fluxes"),
     {ELMK_G_CANOPY_FLUXES, k_groups<ELMK_G_CANOPY_FLUXES>, "canopy_fluxes", kBlock, kBlock, kCanfluxRepacked},
     ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 8),
     ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 6),
@@ -1172,25 +1177,48 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
       else if (nb == 512) c->iterate_fn = k_canflux_iterate<512, true>;
       else { c->iterate_block = kIterBlock; c->iterate_fn = ls ? k_canflux_iterate<384, true> : k_canflux_iterate<384, false>; }
     }
+    // launches of the fused plan found by the set of groups they cover
+    auto slot = [&](uint32_t mask) -> Launch* {
+      for (Launch& L : c->plan_own) if (L.mask == mask) return &L;
+      return nullptr;
+    };
     const char* e0 = std::getenv("ELMK_OCC_RAD");
-    const char* e1 = std::getenv("ELMK_OCC_SFC");
     const char* e2 = std::getenv("ELMK_OCC_SOIL");
     const char* e3 = std::getenv("ELMK_OCC_END");
-    const char* fz = std::getenv("ELMK_FUSE_RAD_SFC");   // albedo rest + surface chain in one launch
-    if (e0 || e1 || e2 || e3 || fz) {
+    const char* e4 = std::getenv("ELMK_OCC_BG");
+    const char* sm = std::getenv("ELMK_SFC_MODE");   // how the closed-form surface groups (a3..a6) are cut into launches
+    const char* em = std::getenv("ELMK_END_MODE");   // same for snow hydrology + surface fluxes + conservation
+    if (e0 || e2 || e3 || e4 || sm || em) {
       c->plan_own.assign(kFused, kFused + c->plan_len);
       GroupKernel k;
-      if (e0 && (k = occ_variant<M_RAD_REST>(std::atoi(e0)))) c->plan_own[0].fn = k;
-      if (e1 && (k = occ_variant<M_SFC>(std::atoi(e1)))) c->plan_own[1].fn = k;
-      if (e2 && (k = occ_variant<ELMK_G_SOIL_TEMPERATURE>(std::atoi(e2)))) c->plan_own[3].fn = k;
-      if (e3 && (k = occ_variant<M_END>(std::atoi(e3)))) c->plan_own[4].fn = k;
-      if (fz && (k = occ_variant<M_RAD_REST | M_SFC>(std::atoi(fz)))) {
-        c->plan_own[0].fn = k;
-        c->plan_own[0].mask = M_RAD | M_SFC;
-        c->plan_own[0].name = "fracwet+albedo+hydrology+radiation+temperature+bareground";
-        c->plan_own.erase(c->plan_own.begin() + 1);
-        c->plan_len -= 1;
+      if (e0 && (k = occ_variant<M_RAD_REST>(std::atoi(e0)))) slot(M_RAD)->fn = k;
+      if (e2 && (k = occ_variant<ELMK_G_SOIL_TEMPERATURE>(std::atoi(e2)))) slot(ELMK_G_SOIL_TEMPERATURE)->fn = k;
+      if (e3 && (k = occ_variant<M_END>(std::atoi(e3)))) slot(M_END)->fn = k;
+      if (e4 && (k = occ_variant<ELMK_G_BAREGROUND_FLUXES>(std::atoi(e4)))) slot(ELMK_G_BAREGROUND_FLUXES)->fn = k;
+      if (sm) {
+        constexpr uint32_t M_HRT = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | ELMK_G_CANOPY_TEMPERATURE;
+        const int mode = std::atoi(sm);
+        std::vector<Launch> cut;
+        if (mode == 0) cut = {ELMK_LAUNCH_OCC(M_SFC, "hydrology+radiation+temperature+bareground", 8)};
+        else if (mode == 2) cut = {ELMK_LAUNCH_OCC(M_HRT, "hydrology+radiation+temperature", 8), ELMK_LAUNCH(ELMK_G_BAREGROUND_FLUXES, "bareground_fluxes")};
+        if (!cut.empty()) {
+          const auto first = c->plan_own.begin() + (slot(ELMK_G_CANOPY_HYDROLOGY) - c->plan_own.data());
+          c->plan_own.erase(first, first + 4);
+          c->plan_own.insert(c->plan_own.begin() + 1, cut.begin(), cut.end());
+        }
       }
+      if (em) {
+        constexpr uint32_t M_FC = ELMK_G_SURFACE_FLUXES | ELMK_G_CONSERVATION;
+        const int emode = std::atoi(em);
+        std::vector<Launch> end;
+        if (emode == 1) end = {ELMK_LAUNCH(ELMK_G_SNOW_HYDROLOGY, "snow_hydrology"), ELMK_LAUNCH(M_FC, "surface_fluxes+conservation")};
+        else if (emode == 3) end = {ELMK_LAUNCH_OCC(ELMK_G_SNOW_HYDROLOGY, "snow_hydrology", 6), ELMK_LAUNCH_OCC(M_FC, "surface_fluxes+conservation", 8)};
+        if (!end.empty()) {
+          c->plan_own.pop_back();
+          c->plan_own.insert(c->plan_own.end(), end.begin(), end.end());
+        }
+      }
+      c->plan_len = (int)c->plan_own.size();
     }
   }
 #endif

@@ -328,10 +328,11 @@ ELMK_SNOW_LOOP
 }
 
 // ---- divide_layers :909-1285 ------------------------------------------------------------------
+// The cascade works on top-aligned rows (element 0 = top layer), rows of the aerosol masses at distance NS:
+// m[a * NS + k].
 // move the part of layer k thicker than `keep` into layer k+1
-ELMK_HD void divide_excess(const int k, const double keep, double (&dzsno)[snw::NS], double (&swice)[snw::NS],
-                           double (&swliq)[snw::NS], double (&tsno)[snw::NS], double (&m)[snw::NMSS][snw::NS],
-                           double (&rds)[snw::NS], const int rds_check, uint32_t& err)
+ELMK_HD void divide_excess(const int k, const double keep, double* dzsno, double* swice, double* swliq, double* tsno,
+                           double* m, double* rds, const int rds_check, uint32_t& err)
 {
   using namespace snw;
   const double drr = dzsno[k] - keep;
@@ -340,15 +341,15 @@ ELMK_HD void divide_excess(const int k, const double keep, double (&dzsno)[snw::
   double zwliq = propor * swliq[k];
   double zm[NMSS];
 ELMK_SNOW_LOOP
-  for (int a = 0; a < NMSS; ++a) zm[a] = propor * m[a][k];
+  for (int a = 0; a < NMSS; ++a) zm[a] = propor * m[a * NS + k];
   propor = keep / dzsno[k];
   swice[k] *= propor;
   swliq[k] *= propor;
 ELMK_SNOW_LOOP
-  for (int a = 0; a < NMSS; ++a) m[a][k] *= propor;
+  for (int a = 0; a < NMSS; ++a) m[a * NS + k] *= propor;
   dzsno[k] = keep;
 ELMK_SNOW_LOOP
-  for (int a = 0; a < NMSS; ++a) m[a][k + 1] += zm[a];
+  for (int a = 0; a < NMSS; ++a) m[a * NS + k + 1] += zm[a];
   rds[k + 1] = (rds[k + 1] * (swliq[k + 1] + swice[k + 1]) + rds[k] * (zwliq + zwice)) /
                (swliq[k + 1] + swice[k + 1] + zwliq + zwice);
   if (rds[rds_check] < RDS_MIN_TBL || rds[rds_check] > RDS_MAX_TBL) err |= ERR_DIVIDE_RADIUS;
@@ -358,9 +359,8 @@ ELMK_SNOW_LOOP
 // split layer k into two equal halves k and k+1 with a linear temperature profile.
 // `tchk`: index of the temperature compared with the freezing point (QUIRK 13: the reference tests
 // tsno[2] where tsno[3] is meant when creating the fourth layer).
-ELMK_HD void divide_split(const int k, const int tchk, double (&dzsno)[snw::NS], double (&swice)[snw::NS],
-                          double (&swliq)[snw::NS], double (&tsno)[snw::NS], double (&m)[snw::NMSS][snw::NS],
-                          double (&rds)[snw::NS])
+ELMK_HD void divide_split(const int k, const int tchk, double* dzsno, double* swice, double* swliq, double* tsno, double* m,
+                          double* rds)
 {
   using namespace snw;
   const double dtdz = (tsno[k - 1] - tsno[k]) / ((dzsno[k - 1] + dzsno[k]) / 2.0);
@@ -378,35 +378,17 @@ ELMK_HD void divide_split(const int k, const int tchk, double (&dzsno)[snw::NS],
   }
 ELMK_SNOW_LOOP
   for (int a = 0; a < NMSS; ++a) {
-    m[a][k] /= 2.0;
-    m[a][k + 1] = m[a][k];
+    m[a * NS + k] /= 2.0;
+    m[a * NS + k + 1] = m[a * NS + k];
   }
   rds[k + 1] = rds[k];
 }
 
-ELMK_HD void divide_layers(snw::Pack& P, const double frac_sno, uint32_t& err)
+// the reference's cascade of excess moves and splits on a pack of msno layers; returns the new layer count
+ELMK_HD_NOINLINE int divide_cascade(int msno, double* dzsno, double* swice, double* swliq, double* tsno, double* m, double* rds,
+                           uint32_t& err)
 {
   using namespace snw;
-  double dzsno[NS], swice[NS], swliq[NS], tsno[NS], rds[NS], m[NMSS][NS];
-  const int snl = P.snl;
-  int msno = snl;
-  int top = NS - snl;
-ELMK_SNOW_LOOP
-  for (int i = 0; i < NS; ++i) {
-    dzsno[i] = 0.0; swice[i] = 0.0; swliq[i] = 0.0; tsno[i] = 0.0; rds[i] = 0.0;
-ELMK_SNOW_LOOP
-    for (int a = 0; a < NMSS; ++a) m[a][i] = 0.0;
-  }
-  for (int i = 0; i < snl; ++i) {
-    dzsno[i] = frac_sno * P.dz[i + top];
-    swice[i] = P.ice[i + top];
-    swliq[i] = P.liq[i + top];
-    tsno[i] = P.t[i + top];
-ELMK_SNOW_LOOP
-    for (int a = 0; a < NMSS; ++a) m[a][i] = P.mss[a][i + top];
-    rds[i] = P.rds[i + top];
-  }
-
   if (msno == 1) {
     if (dzsno[0] > 0.03) {
       msno = 2;
@@ -419,8 +401,8 @@ ELMK_SNOW_LOOP
       tsno[1] = tsno[0];
 ELMK_SNOW_LOOP
       for (int a = 0; a < NMSS; ++a) {
-        m[a][0] /= 2.0;
-        m[a][1] = m[a][0];
+        m[a * NS + 0] /= 2.0;
+        m[a * NS + 1] = m[a * NS + 0];
       }
       rds[1] = rds[0];
     }
@@ -457,18 +439,66 @@ ELMK_SNOW_LOOP
       divide_excess(3, 0.23, dzsno, swice, swliq, tsno, m, rds, 3, err);   // QUIRK 13: checks rds[3]
     }
   }
+  return msno;
+}
 
-  P.snl = msno;
-  top = NS - msno;
-  for (int i = top; i < NS; ++i) {
-    P.dz[i] = dzsno[i - top] / frac_sno;
-    P.ice[i] = swice[i - top];
-    P.liq[i] = swliq[i - top];
-    P.t[i] = tsno[i - top];
-ELMK_SNOW_LOOP
-    for (int a = 0; a < NMSS; ++a) P.mss[a][i] = m[a][i - top];
-    P.rds[i] = rds[i - top];
+// The reference copies the pack into top-aligned scratch rows, runs the cascade and copies it back (13 rows of
+// five).  Whether the cascade creates a layer can be told beforehand: the thickness a layer has when its split is
+// tested is its own plus the excess handed down from above, dz[k] + max(0, dz'[k-1] - keep[k-1]) - the very
+// additions the cascade performs.  A pack that will keep its layer count (tested with a relative margin of 1e-9;
+// five layers never grow) is processed in place in the bottom-aligned rows of the thread's pack: same operations on
+// the same values, no copies.  Anything else, NaN included, takes the reference's route.
+ELMK_HD void divide_layers(snw::Pack& P, const double frac_sno, uint32_t& err)
+{
+  using namespace snw;
+  const int snl = P.snl;
+  int msno = snl;
+  int top = NS - snl;
+  for (int i = top; i < NS; ++i) P.dz[i] = frac_sno * P.dz[i];
+  constexpr double under = 1.0 - 1.0e-9;
+  const double* d = P.dz + top;
+  bool in_place = true;
+  if (snl >= 1 && snl < NS) {
+    double below = d[0];   // thickness of the layer whose split is tested, after the excess moves above it
+    if (snl >= 2) below = d[1] + dmax(0.0, d[0] - 0.02);
+    if (snl >= 3) below = d[2] + dmax(0.0, below - 0.05);
+    if (snl >= 4) below = d[3] + dmax(0.0, below - 0.11);
+    const double splits_at = (snl == 1) ? 0.03 : (snl == 2) ? 0.07 : (snl == 3) ? 0.18 : 0.41;
+    in_place = (below <= splits_at * under);
   }
+  if (in_place) {
+    divide_cascade(msno, P.dz + top, P.ice + top, P.liq + top, P.t + top, &P.mss[0][0] + top, P.rds + top, err);
+  } else {
+    double dzsno[NS], swice[NS], swliq[NS], tsno[NS], rds[NS], m[NMSS][NS];
+ELMK_SNOW_LOOP
+    for (int i = 0; i < NS; ++i) {
+      dzsno[i] = 0.0; swice[i] = 0.0; swliq[i] = 0.0; tsno[i] = 0.0; rds[i] = 0.0;
+ELMK_SNOW_LOOP
+      for (int a = 0; a < NMSS; ++a) m[a][i] = 0.0;
+    }
+    for (int i = 0; i < snl; ++i) {
+      dzsno[i] = P.dz[i + top];
+      swice[i] = P.ice[i + top];
+      swliq[i] = P.liq[i + top];
+      tsno[i] = P.t[i + top];
+ELMK_SNOW_LOOP
+      for (int a = 0; a < NMSS; ++a) m[a][i] = P.mss[a][i + top];
+      rds[i] = P.rds[i + top];
+    }
+    msno = divide_cascade(msno, dzsno, swice, swliq, tsno, &m[0][0], rds, err);
+    P.snl = msno;
+    top = NS - msno;
+    for (int i = top; i < NS; ++i) {
+      P.dz[i] = dzsno[i - top];
+      P.ice[i] = swice[i - top];
+      P.liq[i] = swliq[i - top];
+      P.t[i] = tsno[i - top];
+ELMK_SNOW_LOOP
+      for (int a = 0; a < NMSS; ++a) P.mss[a][i] = m[a][i - top];
+      P.rds[i] = rds[i - top];
+    }
+  }
+  for (int i = top; i < NS; ++i) P.dz[i] = P.dz[i] / frac_sno;
   for (int i = NS - 1; i >= top; --i) {
     P.z[i] = P.zi[i + 1] - 0.5 * P.dz[i];
     P.zi[i] = P.zi[i + 1] - P.dz[i];

@@ -24,6 +24,8 @@ for r in rows[1:]:
 GROUP = [("k_init_timestep", "init_timestep"), ("k_coszen", "coszen"), ("k_phenology", "phenology"), ("k_atm_forcing", "atm_forcing"),
          ("k_groups_sorted<3", "fracwet+albedo"), ("k_snicar", "fracwet+albedo"), ("k_groups_occ<1048577", "fracwet+albedo"),
          ("k_groups_occ<60", "hydrology+radiation+temperature+bareground"),
+         ("k_groups<4", "canopy_hydrology"), ("k_groups<8", "surface_radiation"), ("k_groups<16", "canopy_temperature"),
+         ("k_groups<32", "bareground_fluxes"),
          ("k_canflux", "canopy_fluxes"), ("k_groups_occ<128", "soil_temperature"), ("k_groups_occ<1792", "snow+surface_fluxes+conservation")]
 res = OrderedDict()
 for d in K.values():
