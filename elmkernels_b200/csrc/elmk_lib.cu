@@ -475,6 +475,43 @@ __global__ void __launch_bounds__(kBlock) k_phenology(const Cols S, const PhenSe
   column_phenology(S, P, m, wt1, wt2, c);
 }
 
+// ---- bare-ground fluxes on the compacted list of unvegetated columns -----------------------------------------------
+// Only columns without exposed vegetation do work in this group (three Monin-Obukhov passes; ncu: 10 of 32 lanes active
+// with one thread per column).  A block owns a window of 1024 consecutive columns, zeroes what compute_flux zeroes
+// for every column, compacts the indices of the bare ones in shared memory (warp-aggregated append) and its threads
+// then take the list entries: full warps, and the 8-byte accesses of a warp stay within the window's 8 KB per row.
+#ifndef ELMK_BARE_WINDOW
+#define ELMK_BARE_WINDOW 1024
+#endif
+#ifndef ELMK_BARE_OCC
+#define ELMK_BARE_OCC 8
+#endif
+constexpr int kBareWindow = ELMK_BARE_WINDOW;
+__global__ void __launch_bounds__(kBlock, ELMK_BARE_OCC) k_bareground_compact(const Cols S, const Tables* __restrict__ Tp, const StepArgs)
+{
+  __shared__ unsigned short list[kBareWindow];
+  __shared__ int count;
+  const long long w0 = (long long)blockIdx.x * kBareWindow;
+  const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+  if (threadIdx.x == 0) count = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (int i = threadIdx.x; i < kBareWindow; i += kBlock) {
+    const long long c = w0 + i;
+    const bool bare = (c < S.ncols) && (S.frac_veg_nosno[c] == 0);
+    if (c < S.ncols && !bare) { S.cgrnd[c] = 0.0; S.cgrnds[c] = 0.0; S.cgrndl[c] = 0.0; }
+    const unsigned m = __ballot_sync(0xffffffffu, bare);
+    int at = 0;
+    if (lane == 0 && m) at = atomicAdd(&count, __popc(m));
+    at = __shfl_sync(0xffffffffu, at, 0);
+    if (bare) list[at + __popc(m & below)] = (unsigned short)i;
+  }
+  __syncthreads();
+  const int n = count;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < n; i += kBlock) column_bareground_fluxes(S, *Tp, (int)(w0 + list[i]));
+}
+
 // elmk_fn_call: one library-level physics function on the flat argument array of ONE column (include/elm/*.h)
 #define FlatRow(ptr) ColRow{(ptr), 1}
 constexpr int kFnSlots[ELMK_FN_COUNT] = {13, 14, 7, 150, 26, 11, 36, 39, 9, 18, 42, 25, 160, 93, 35, 61, 10, 6, 20, 22, 56};
@@ -664,7 +701,7 @@ const Launch kFused[] = {
     ELMK_LAUNCH(ELMK_G_CANOPY_HYDROLOGY, "canopy_hydrology"),
     ELMK_LAUNCH(ELMK_G_SURFACE_RADIATION, "surface_radiation"),
     ELMK_LAUNCH(ELMK_G_CANOPY_TEMPERATURE, "canopy_temperature"),
-    ELMK_LAUNCH(ELMK_G_BAREGROUND_FLUXES, "bareground_fluxes"),
+    {ELMK_G_BAREGROUND_FLUXES, k_bareground_compact, "bareground_fluxes", kBareWindow, kBlock, kPlain},
     {ELMK_G_CANOPY_FLUXES, k_groups<ELMK_G_CANOPY_FLUXES>, "canopy_fluxes", kBlock, kBlock, kCanfluxRepacked},
     ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 8),
     ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 6),
@@ -1194,7 +1231,7 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
       if (e0 && (k = occ_variant<M_RAD_REST>(std::atoi(e0)))) slot(M_RAD)->fn = k;
       if (e2 && (k = occ_variant<ELMK_G_SOIL_TEMPERATURE>(std::atoi(e2)))) slot(ELMK_G_SOIL_TEMPERATURE)->fn = k;
       if (e3 && (k = occ_variant<M_END>(std::atoi(e3)))) slot(M_END)->fn = k;
-      if (e4 && (k = occ_variant<ELMK_G_BAREGROUND_FLUXES>(std::atoi(e4)))) slot(ELMK_G_BAREGROUND_FLUXES)->fn = k;
+      if (e4 && (k = occ_variant<ELMK_G_BAREGROUND_FLUXES>(std::atoi(e4)))) { slot(ELMK_G_BAREGROUND_FLUXES)->fn = k; slot(ELMK_G_BAREGROUND_FLUXES)->cols_per_block = kBlock; }
       if (sm) {
         constexpr uint32_t M_HRT = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | ELMK_G_CANOPY_TEMPERATURE;
         const int mode = std::atoi(sm);
