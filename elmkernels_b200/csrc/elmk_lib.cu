@@ -1144,7 +1144,8 @@ int elmk_field_info(int field, const char** name, int* dtype, int* nlev) {
 }
 
 int elmk_create(elmk_handle* out, int device, int64_t ncols) {
-  if (!out || ncols <= 0 || ncols > INT32_MAX - kColAlign) return ELMK_EINVAL;
+  // (element offsets lev * np + col are 32-bit in the kernels: 21 levels at most)
+  if (!out || ncols <= 0 || ncols > (INT32_MAX - kColAlign) / 21) return ELMK_EINVAL;
   *out = nullptr;
   Ctx* c = new Ctx;
   c->device = device;
@@ -1174,7 +1175,7 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
   for (int f = 0; f < kNumFields; ++f) c->base[f] = c->arena + offset[f];
   c->cols.np = c->np;
   c->cols.ncols = (int)ncols;
-  c->cols.pad_ = 0;
+  c->cols.npi = (int)c->np;
   {
     int f = 0;
 #define ELMK_FIELD(name, type, nlev, cls) c->cols.name = static_cast<elmk_##type*>(c->base[f++]);
@@ -1203,7 +1204,7 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
     const char* rp = std::getenv("ELMK_CANFLUX_REPACK");
     if (rp && rp[0] == '0') c->repack = false;
     const char* sn = std::getenv("ELMK_SNICAR_OCC");
-    if (sn) c->snicar_fn = std::atoi(sn) == 3 ? k_snicar<3> : std::atoi(sn) == 2 ? k_snicar<2> : k_snicar<4>;
+    if (sn) { const int o = std::atoi(sn); c->snicar_fn = o == 2 ? k_snicar<2> : o == 3 ? k_snicar<3> : o == 5 ? k_snicar<5> : o == 6 ? k_snicar<6> : o == 8 ? k_snicar<8> : k_snicar<4>; }
     const char* ib = std::getenv("ELMK_ITER");   // e.g. "256l" = 256-thread lock-step blocks, "128" = 128 threads free-running
     if (ib) {
       const int nb = std::atoi(ib);

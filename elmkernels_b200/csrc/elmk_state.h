@@ -19,7 +19,7 @@ typedef unsigned char elmk_U8;
 struct Cols {
   long long np;   // distance (in elements) between consecutive levels of a field
   int ncols;      // number of valid columns
-  int pad_;
+  int npi;        // np again, as a 32-bit value: element offsets lev * np + col fit 31 bits for every field (checked at create)
 #define ELMK_FIELD(name, type, nlev, cls) elmk_##type* name;
 #include "../../include/elmk_fields.def"
 #undef ELMK_FIELD
@@ -55,7 +55,12 @@ struct StepArgs {
 
 // field accessors used by the physics bodies: S is a `const Cols&`, c the column index
 #define C1(field) S.field[c]
+#ifdef ELMK_INDEX64
 #define C2(field, lev) S.field[(long long)(lev) * S.np + c]
+#else
+// 32-bit element offset: one IMAD + one IMAD.WIDE per access instead of a 64-bit multiply-add chain
+#define C2(field, lev) S.field[(int)(lev) * S.npi + (int)c]
+#endif
 
 // row of a multi-level field of one column: in the column-innermost layout of the state (ELMK_ROW), or contiguous
 // (stride 1: per-thread rows and the flat argument arrays of elmk_fn_call)

@@ -98,6 +98,7 @@ int elmk_create(elmk_handle* out, int, int64_t ncols) {
   c->np = (ncols + 31) / 32 * 32;
   c->cols.np = c->np;
   c->cols.ncols = static_cast<int>(ncols);
+  c->cols.npi = static_cast<int>(c->np);
   c->base.resize(kNumFields);
   for (int f = 0; f < kNumFields; ++f)
     c->base[f] = std::calloc(static_cast<size_t>(c->np) * kSpecs[f].nlev, esize(kSpecs[f].dtype));
