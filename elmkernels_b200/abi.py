@@ -107,6 +107,7 @@ class Library:
             "elmk_set_coordinates": (C.c_int, [H, _PD, _PD, C.c_int64]),
             "elmk_solar_step": (C.c_int, [H, C.c_double, C.c_double, C.c_int, _PD, _PD]),
             "elmk_fn_call": (C.c_int, [C.c_int, C.c_int, _PD, C.c_int64]),
+            "elmk_set_gas_pressures": (C.c_int, [C.c_void_p, _PD, _PD]),
             "elmk_sync": (C.c_int, [H]),
             "elmk_set_plan": (C.c_int, [H, C.c_int]),
             "elmk_launch_count": (C.c_int64, [H]),
@@ -399,6 +400,17 @@ class Columns:
 
     def step(self, dtime: float = 1800.0, dayl: float = 50000.0, max_dayl: float = 86400.0, groups: int = G_ALL):
         self._check(self.lib.dll.elmk_step(self._h, dtime, dayl, max_dayl, groups), "elmk_step")
+
+    def set_gas_pressures(self, forc_pco2=None, forc_po2=None):
+        """Per-column CO2 / O2 partial pressures [Pa] for the photosynthesis of group a7 (None, None: back to the
+        reference wrapper's constants)."""
+        if forc_pco2 is None and forc_po2 is None:
+            self._check(self.lib.dll.elmk_set_gas_pressures(self._h, None, None), "elmk_set_gas_pressures")
+            return
+        a = np.ascontiguousarray(forc_pco2, dtype=np.float64).reshape(self.ncols)
+        b = np.ascontiguousarray(forc_po2, dtype=np.float64).reshape(self.ncols)
+        self._check(self.lib.dll.elmk_set_gas_pressures(self._h, a.ctypes.data_as(_PD), b.ctypes.data_as(_PD)),
+                    "elmk_set_gas_pressures")
 
     def set_plan(self, plan: str):
         """'fused' (default, production) or 'split' (one launch per kernel group, one thread per column)."""

@@ -891,6 +891,7 @@ struct Ctx {
   cudaEvent_t ev_series = nullptr, ev_forcing = nullptr;
   bool series_pending = false;
   double* coords = nullptr;        // sin(lat), cos(lat), tan(lat), lon: [4][ncoords] (elmk_set_coordinates)
+  double* gas = nullptr;           // [2][np]: CO2, O2 partial pressures (elmk_set_gas_pressures)
   int64_t ncoords = 0;
   double lat0 = 0.0;
   CanfluxQueue cq = {nullptr, nullptr, nullptr, 0};   // CanopyFluxes re-packing scratch (allocated on first use)
@@ -1176,6 +1177,8 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
   c->cols.np = c->np;
   c->cols.ncols = (int)ncols;
   c->cols.npi = (int)c->np;
+  c->cols.pco2_in = nullptr;
+  c->cols.po2_in = nullptr;
   {
     int f = 0;
 #define ELMK_FIELD(name, type, nlev, cls) c->cols.name = static_cast<elmk_##type*>(c->base[f++]);
@@ -1286,6 +1289,7 @@ int elmk_destroy(elmk_handle h) {
   cudaFree(c->cq.scratch);
   cudaFree(c->cq.list);
   cudaFree(c->cq.counters);
+  cudaFree(c->gas);
   for (auto& t : c->timed) { cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -1618,6 +1622,27 @@ int elmk_init_columns(elmk_handle h, const double* pct_sand, const double* pct_c
   cudaFree(buf);
   if (rc == ELMK_OK) CU(cudaGetLastError());
   return rc;
+}
+
+int elmk_set_gas_pressures(elmk_handle h, const double* forc_pco2, const double* forc_po2) {
+  Ctx* c = ctx(h);
+  if (!c || ((forc_pco2 == nullptr) != (forc_po2 == nullptr))) return ELMK_EINVAL;
+  if (int rc = bind(c)) return rc;
+  if (!forc_pco2) {   // back to the constants of the reference's wrapper
+    c->cols.pco2_in = nullptr;
+    c->cols.po2_in = nullptr;
+    return ELMK_OK;
+  }
+  if (!c->gas) {
+    CU(cudaMalloc(&c->gas, sizeof(double) * 2 * (size_t)c->np));
+    CU(cudaMemsetAsync(c->gas, 0, sizeof(double) * 2 * (size_t)c->np, c->stream));
+  }
+  CU(cudaMemcpyAsync(c->gas, forc_pco2, sizeof(double) * (size_t)c->ncols, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->gas + c->np, forc_po2, sizeof(double) * (size_t)c->ncols, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->cols.pco2_in = c->gas;
+  c->cols.po2_in = c->gas + c->np;
+  return ELMK_OK;
 }
 
 int elmk_set_coordinates(elmk_handle h, const double* lat_r, const double* lon_r, int64_t n) {

@@ -20,6 +20,9 @@ struct Cols {
   long long np;   // distance (in elements) between consecutive levels of a field
   int ncols;      // number of valid columns
   int npi;        // np again, as a 32-bit value: element offsets lev * np + col fit 31 bits for every field (checked at create)
+  // optional per-column CO2 / O2 partial pressures [Pa] (elmk_set_gas_pressures); null: the wrapper's constants
+  const double* pco2_in;
+  const double* po2_in;
 #define ELMK_FIELD(name, type, nlev, cls) elmk_##type* name;
 #include "../../include/elmk_fields.def"
 #undef ELMK_FIELD

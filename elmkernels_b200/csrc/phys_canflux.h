@@ -513,8 +513,9 @@ ELMK_HD bool canflux_begin(const Cols& S, const Tables& T, const StepArgs& A, co
   I.elai = C1(elai); I.esai = C1(esai); I.emv = C1(emv); I.emg = C1(emg);
   I.z0mg = C1(z0mg);
   I.hgt_u = C1(forc_hgt_u_patch); I.hgt_t = C1(forc_hgt_t_patch); I.hgt_q = C1(forc_hgt_q_patch);
-  I.forc_po2 = O2_MOLAR_CONST * I.pbot;
-  I.forc_pco2 = CO2_PPMV * 1.0e-6 * I.pbot;
+  // derive_forc_po2 / derive_forc_pco2 (canopy_fluxes_kokkos.cc:49-51) unless the caller supplies the partial pressures
+  I.forc_po2 = S.po2_in ? S.po2_in[c] : O2_MOLAR_CONST * I.pbot;
+  I.forc_pco2 = S.pco2_in ? S.pco2_in[c] : CO2_PPMV * 1.0e-6 * I.pbot;
   I.forc_rho = air_density(I.pbot, I.forc_q, forc_t);
 
   // ---- initialize_flux (:133-181) ----

@@ -190,6 +190,12 @@ public:
     check(elmk_solar_step(h_, dtime, decday, doy1, &dayl_, &max_dayl_), "elmk_solar_step");
   }
 
+  // CO2 / O2 partial pressures [Pa] per column for the photosynthesis of kokkos_canopy_fluxes, which the reference
+  // derives from constants (canopy_fluxes_kokkos.cc:49-51); nullptr, nullptr returns to those
+  void set_gas_pressures(const double* forc_pco2, const double* forc_po2) {
+    check(elmk_set_gas_pressures(h_, forc_pco2, forc_po2), "elmk_set_gas_pressures");
+  }
+
   // ---- stepping ----
   // per-column part of kokkos_init_timestep (init_timestep_kokkos.cc:53-72) incl. the reset of forc_hgt_*_patch
   void init_timestep(bool reset_forc_hgt = true) { check(elmk_init_timestep(h_, reset_forc_hgt ? 1 : 0), "elmk_init_timestep"); }

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ELMK_ABI_VERSION 5
+#define ELMK_ABI_VERSION 6
 
 /* ---- dimensions (reference src/data/elm_constants.h:84-98) ---- */
 #define ELMK_NLEVSNO 5
@@ -207,6 +207,14 @@ int elmk_init_columns(elmk_handle h, const double* pct_sand, const double* pct_c
  *        the first coordinate, to be handed to elmk_step. ---- */
 int elmk_set_coordinates(elmk_handle h, const double* lat_r, const double* lon_r, int64_t n);
 int elmk_solar_step(elmk_handle h, double dtime, double decday, int doy1, double* dayl, double* max_dayl);
+
+/* ---- CO2 and O2 partial pressures [Pa] of every column for the photosynthesis of group a7.  The reference's wrapper
+ *      derives them from constants (355 ppmv CO2, 0.209 mol/mol O2: canopy_fluxes_kokkos.cc:49-51,
+ *      atm_physics_impl.hh derive_forc_pco2 / derive_forc_po2), its library functions take them as arguments
+ *      (canopy_fluxes::stability_iteration, canopy_fluxes_impl.hh:187-202) - a host model with its own CO2 supplies
+ *      them here: host arrays of ncols values, both or neither; NULL, NULL returns to the constants.
+ *      ELMK_EUNSUPPORTED on the reference checker (its wrapper has no such input). ---- */
+int elmk_set_gas_pressures(elmk_handle h, const double* forc_pco2, const double* forc_po2);
 
 /* ---- producers of the per-step inputs, on the device (the step before the chain in kokkos_init_timestep,
  *      init_timestep_kokkos.cc:39-47).

@@ -55,6 +55,7 @@ struct PortCtx {
   std::vector<double> snw[2][3], snowage[3];
   std::vector<double> atm[ATM_NVARS], phen[PHEN_NVARS];   // [ntimes][ncols]
   std::vector<double> coords;   // sin(lat), cos(lat), tan(lat), lon: [4][ncoords]
+  std::vector<double> gas[2];   // CO2, O2 partial pressures (elmk_set_gas_pressures)
   int64_t ncoords = 0;
   double lat0 = 0.0;
   bool tables_set = false;
@@ -99,6 +100,8 @@ int elmk_create(elmk_handle* out, int, int64_t ncols) {
   c->cols.np = c->np;
   c->cols.ncols = static_cast<int>(ncols);
   c->cols.npi = static_cast<int>(c->np);
+  c->cols.pco2_in = nullptr;
+  c->cols.po2_in = nullptr;
   c->base.resize(kNumFields);
   for (int f = 0; f < kNumFields; ++f)
     c->base[f] = std::calloc(static_cast<size_t>(c->np) * kSpecs[f].nlev, esize(kSpecs[f].dtype));
@@ -238,6 +241,20 @@ int elmk_atm_forcing(elmk_handle h, int t_idx, double wt1, double wt2, int qbot_
     A.v[v] = c.atm[v].data();
   }
   for_columns(c, [&](int i) { column_atm_forcing(c.cols, A, t_idx, wt1, wt2, qbot_is_rh != 0, i); });
+  return ELMK_OK;
+}
+int elmk_set_gas_pressures(elmk_handle h, const double* forc_pco2, const double* forc_po2) {
+  PortCtx& c = *ctx(h);
+  if ((forc_pco2 == nullptr) != (forc_po2 == nullptr)) return ELMK_EINVAL;
+  if (!forc_pco2) {
+    c.cols.pco2_in = nullptr;
+    c.cols.po2_in = nullptr;
+    return ELMK_OK;
+  }
+  c.gas[0].assign(forc_pco2, forc_pco2 + c.ncols);
+  c.gas[1].assign(forc_po2, forc_po2 + c.ncols);
+  c.cols.pco2_in = c.gas[0].data();
+  c.cols.po2_in = c.gas[1].data();
   return ELMK_OK;
 }
 int elmk_set_coordinates(elmk_handle h, const double* lat_r, const double* lon_r, int64_t n) {

@@ -381,6 +381,8 @@ int elmk_atm_series(elmk_handle h, int var, const double* host, int ntimes) {
 }
 // the first lines of kokkos_init_timestep (init_timestep_kokkos.cc:27-35) with the reference's own functions, evaluated
 // for every column's coordinates instead of the single site
+// (kokkos_canopy_fluxes derives the partial pressures from constants: the unmodified wrapper has no such input)
+int elmk_set_gas_pressures(elmk_handle, const double*, const double*) { return ELMK_EUNSUPPORTED; }
 int elmk_set_coordinates(elmk_handle h, const double* lat_r, const double* lon_r, int64_t n) {
   RefCtx& c = *ctx(h);
   if (!lat_r || !lon_r || !(n == 1 || n == c.ncols)) return ELMK_EINVAL;

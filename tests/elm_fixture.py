@@ -52,16 +52,19 @@ CANFLUX_COMPARED = ("btran displa z0mv z0hv z0qv t_veg qflx_tran_veg qflx_evap_v
                     "cgrndl cgrnd t_ref2m q_ref2m rh_ref2m h2ocan rootr eff_porosity").split()
 
 
-def replay_canopy_fluxes(lib, params):
+def replay_canopy_fluxes(lib, params, day=False):
     """The ELM Fortran dump of test_CanFlux (test/test_CanFlux.cc:328-453) through group a7.  The kernel-group
     wrapper derives the CO2 partial pressure from a constant 355 ppmv (canopy_fluxes_kokkos.cc:49-51) while the
-    dump carries ELM's time-varying value, so only the 47 night records - where the stomatal root-find and hence
-    CO2 do not enter - can be replayed exactly; they exercise moisture stress, the Monin-Obukhov iteration, the
-    leaf energy balance and compute_flux."""
+    dump carries ELM's time-varying value.  day=False: the 47 night records - where the stomatal root-find and hence
+    CO2 do not enter - replayed with the wrapper's constants; they exercise moisture stress, the Monin-Obukhov
+    iteration, the leaf energy balance and compute_flux.  day=True: the 50 daytime records with the dump's partial
+    pressures handed in through elmk_set_gas_pressures, as test_CanFlux.cc hands them to the library functions; they
+    exercise photosynthesis (C3, vtype 12) on top."""
     from elmkernels_b200.params import psn_rows
     z = np.load(os.path.join(ROOT, "tests", "golden", "elm_canopy_fluxes.npz"))
     night = (z["in_parsun_z"][:, 0] <= 0.0) & (z["in_parsha_z"][:, 0] <= 0.0)
-    n = int(night.sum())
+    pick = ~night if day else night
+    n = int(pick.sum())
     cols = lib.columns(n)
     cols.set_tables(params)
     for key in z.files:
@@ -69,16 +72,18 @@ def replay_canopy_fluxes(lib, params):
             continue
         name = CANFLUX_RENAME.get(key[3:], key[3:])
         if name in lib.fields:
-            a = z[key][night]
+            a = z[key][pick]
             _, dt, nl = lib.fields[name]
             cols.upload(name, a.reshape(n) if nl == 1 else a)
     cols.upload("psn_pft", np.repeat(psn_rows(params)[12][None, :], n, axis=0))
     cols.fill("veg_active", 1)
+    if day:
+        cols.set_gas_pressures(z["in_forc_pco2"][pick].reshape(n), z["in_forc_po2"][pick].reshape(n))
     cols.step(dtime=1800.0, dayl=float(z["in_dayl"][0, 0]), max_dayl=float(z["in_max_dayl"][0, 0]), groups=abi.G_CANOPY_FLUXES)
     assert cols.errors() == (0, -1)
     worst, got_all = {}, {}
     for v in CANFLUX_COMPARED:
-        ref = z["out_" + v][night]
+        ref = z["out_" + v][pick]
         got = cols.download(v).astype(np.float64).reshape(ref.shape)
         got_all[v] = got
         d = np.abs(got - ref)

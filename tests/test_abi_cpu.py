@@ -48,7 +48,7 @@ def test_product_library_exports_every_declared_symbol(product_path):
     dll.elmk_backend.restype = ctypes.c_char_p
     assert dll.elmk_backend() == b"cuda-sm100a"
     dll.elmk_abi_version.restype = ctypes.c_int
-    assert dll.elmk_abi_version() == 5
+    assert dll.elmk_abi_version() == 6
 
 
 def test_field_table_matches_def_file(product_path):

@@ -200,6 +200,22 @@ def test_elm_fortran_dump_of_test_canflux_night_records(cuda_lib, checker, param
     assert not bad, bad
 
 
+def test_elm_fortran_dump_of_test_canflux_day_records(cuda_lib, port_lib, params):
+    """The 50 daytime records (photosynthesis active, ELM's own CO2 / O2 partial pressures through
+    elmk_set_gas_pressures) on the GPU: bit-identical to the host port, which tests/test_oracle_cpu.py pins to the
+    Fortran values, and within the same bound of the Fortran values itself."""
+    import elm_fixture
+    n, worst = elm_fixture.replay_canopy_fluxes(cuda_lib, params, day=True)
+    got = elm_fixture.replay_canopy_fluxes.last
+    assert n == 50
+    elm_fixture.replay_canopy_fluxes(port_lib, params, day=True)
+    ref = elm_fixture.replay_canopy_fluxes.last
+    diff = [k for k in ref if parity.mismatch(ref[k], got[k]).any()]
+    assert not diff, f"CUDA and port replays differ in {diff}"
+    bad = {k: v for k, v in worst.items() if v > 3.5e-12}
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("case", ["capped_snow", "all_bare", "hot_and_wet"])
 def test_edge_ensembles(case, cuda_lib, checker, params):
     """Snow capping (do_capsnow), all-bare ensembles and ponded surface water (incl. the 1e97 ground heat flux of

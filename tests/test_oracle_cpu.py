@@ -109,3 +109,18 @@ def test_elm_fortran_dump_of_test_canflux_night_records(which, request, params):
     assert n == 47
     bad = {k: v for k, v in worst.items() if v > 3.4e-12}
     assert not bad, bad
+
+
+def test_elm_fortran_dump_of_test_canflux_day_records(port_lib, ref_lib, params):
+    """The 50 daytime records of the same dump (photosynthesis active) with the dump's CO2 / O2 partial pressures handed
+    in through elmk_set_gas_pressures, as test/test_CanFlux.cc:429-453 hands them to the library functions.  Same bound
+    as the night records.  The compiled reference wrapper has no such input (it derives the pressures from constants):
+    it must refuse."""
+    import elm_fixture
+    from elmkernels_b200 import abi
+    n, worst = elm_fixture.replay_canopy_fluxes(port_lib, params, day=True)
+    assert n == 50
+    bad = {k: v for k, v in worst.items() if v > 3.5e-12}
+    assert not bad, bad
+    with pytest.raises(abi.ElmkError):
+        ref_lib.columns(4).set_gas_pressures([30.0] * 4, [20000.0] * 4)
