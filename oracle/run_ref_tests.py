@@ -16,8 +16,8 @@ def run_all():
             continue
         r = subprocess.run([str(exe)], capture_output=True, text=True)
         txt = r.stdout + r.stderr
-        out[t] = {"returncode": r.returncode, "passed": len(re.findall(r"\bpass", txt, re.I)),
-                  "failed": len(re.findall(r"\bfail", txt, re.I)), "lines": txt.count("\n")}
+        out[t] = {"returncode": r.returncode, "passed": len(re.findall(r"passes: true", txt)),
+                  "failed": len(re.findall(r"passes: false", txt)), "lines": txt.count("\n")}
     return out
 
 if __name__ == "__main__":
