@@ -92,3 +92,54 @@ def replay_canopy_fluxes(lib, params, day=False):
         worst[v] = float(np.max(np.where(d <= 1e-15, 0.0, d / s)))
     replay_canopy_fluxes.last = got_all
     return n, worst
+
+
+SURFALB_RENAME = {"mss_cnc_bcphi": "cnc_bcphi", "mss_cnc_bcpho": "cnc_bcpho", "mss_cnc_dst1": "cnc_dst1",
+                  "mss_cnc_dst2": "cnc_dst2", "mss_cnc_dst3": "cnc_dst3", "mss_cnc_dst4": "cnc_dst4"}
+# what test_SurfAlb.cc:540-595 compares, as far as it is a per-column field of the ABI (fabd_sun / fabd_sha are
+# wrapper-local in the reference)
+SURFALB_COMPARED = ("albsod albsoi albsnd albsni albgrd albgri flx_absdv flx_absdn flx_absiv flx_absin tlai_z fsun_z "
+                    "fabd_sun_z fabd_sha_z fabi_sun_z fabi_sha_z albd ftid ftdd fabd albi ftii fabi fabi_sun fabi_sha").split()
+
+
+def replay_surface_albedo(lib, params):
+    """The ELM Fortran dump of test_SurfAlb (test/test_SurfAlb.cc:391-537; 95 records, 47 of them sunlit, all with a
+    thin snow cover h2osno = 0.015 m without snow layers - the flg_nosnl branch of SNICAR) through group a2: the test
+    calls surface_albedo::init_timestep, soil_albedo, the four SNICAR functions for direct and for diffuse light,
+    ground_albedo, flux_absorption_factor, canopy_layer_lai and two_stream_solver - the body of kokkos_albedo_snicar.
+    The soil-colour albedos arrive per record in the dump; they become rows of the colour table."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "elm_surface_albedo.npz"))
+    n = len(z["steps"])
+    pairs = np.concatenate([z["in_albsat"], z["in_albdry"]], axis=1)
+    uniq, colour = np.unique(pairs, axis=0, return_inverse=True)
+    assert len(uniq) <= 20
+    p = dict(params)
+    p["albsat"] = np.array(params["albsat"], dtype=np.float64)
+    p["albdry"] = np.array(params["albdry"], dtype=np.float64)
+    p["albsat"][:len(uniq)] = uniq[:, :2]
+    p["albdry"][:len(uniq)] = uniq[:, 2:]
+    cols = lib.columns(n)
+    cols.set_tables(p)
+    for key in z.files:
+        if not key.startswith("in_"):
+            continue
+        name = SURFALB_RENAME.get(key[3:], key[3:])
+        if name in lib.fields and name not in ("albsat", "albdry"):
+            a = z[key]
+            _, dt, nl = lib.fields[name]
+            a = np.nan_to_num(a, nan=0.0, posinf=0.0, neginf=0.0) if dt != abi.F64 else a
+            cols.upload(name, a.reshape(n) if nl == 1 else a)
+    cols.upload("isoicol", colour.reshape(n).astype(np.int32))
+    cols.fill("vtype", 12)
+    cols.step(dtime=1800.0, groups=abi.G_ALBEDO)
+    assert cols.errors() == (0, -1)
+    worst, got_all = {}, {}
+    for v in SURFALB_COMPARED:
+        ref = z["out_" + v]
+        got = cols.download(v).astype(np.float64).reshape(ref.shape)
+        got_all[v] = got
+        d = np.abs(got - ref)
+        s = np.maximum(np.abs(ref), 1e-300)
+        worst[v] = float(np.max(np.where(d == 0, 0.0, d / s)))
+    replay_surface_albedo.last = got_all
+    return n, worst

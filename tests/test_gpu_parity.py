@@ -200,6 +200,21 @@ def test_elm_fortran_dump_of_test_canflux_night_records(cuda_lib, checker, param
     assert not bad, bad
 
 
+def test_elm_fortran_dump_of_test_surfalb(cuda_lib, checker, params):
+    """ELM Fortran golden vectors of test_SurfAlb (95 records, SNICAR without snow layers + two-stream) on the GPU:
+    bit-identical to the checker's replay and within 1e-15 of the Fortran values."""
+    import elm_fixture
+    n, worst = elm_fixture.replay_surface_albedo(cuda_lib, params)
+    got = elm_fixture.replay_surface_albedo.last
+    assert n == 95
+    elm_fixture.replay_surface_albedo(checker, params)
+    ref = elm_fixture.replay_surface_albedo.last
+    diff = [k for k in ref if parity.mismatch(ref[k], got[k]).any()]
+    assert not diff, f"CUDA and checker replays differ in {diff}"
+    bad = {k: v for k, v in worst.items() if v > 1e-15}
+    assert not bad, bad
+
+
 def test_elm_fortran_dump_of_test_canflux_day_records(cuda_lib, port_lib, params):
     """The 50 daytime records (photosynthesis active, ELM's own CO2 / O2 partial pressures through
     elmk_set_gas_pressures) on the GPU: bit-identical to the host port, which tests/test_oracle_cpu.py pins to the

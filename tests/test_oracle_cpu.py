@@ -140,3 +140,15 @@ def test_reference_unit_tests_build_and_run_from_the_oracle_recipe():
     got = {t: (v["returncode"], v["passed"], v["failed"]) for t, v in run_ref_tests.run_all().items()}
     assert got == {"CanHydro": (0, 1824, 0), "CanSunShade": (0, 768, 0), "SurfRad": (0, 1440, 0), "CanTemp": (0, 2784, 0),
                    "BGFlux": (0, 2064, 0), "SurfAlb": (0, 2350, 0), "CanFlux": (0, 8560, 73)}, got
+
+
+@pytest.mark.parametrize("which", ["port", "reference"])
+def test_elm_fortran_dump_of_test_surfalb(which, request, params):
+    """The ELM Fortran golden vectors of test_SurfAlb (95 records; thin snow without layers: SNICAR's flg_nosnl branch,
+    two-stream, ground albedo) through group a2: 25 variables, every one within 1e-15 relative of the Fortran value."""
+    import elm_fixture
+    lib = request.getfixturevalue("port_lib" if which == "port" else "ref_lib")
+    n, worst = elm_fixture.replay_surface_albedo(lib, params)
+    assert n == 95
+    bad = {k: v for k, v in worst.items() if v > 1e-15}
+    assert not bad, bad

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Convert the reference's ELM (Fortran) golden dumps for test_CanHydro - test/data/CanopyHydrology_{IN,OUT}.txt,
+"""Convert the reference's ELM (Fortran) golden dumps (test_CanHydro, test_CanFlux, test_SurfAlb); first: test_CanHydro - test/data/CanopyHydrology_{IN,OUT}.txt,
 the fixture of BASELINE.json config 1 - into tests/golden/elm_canopy_hydrology.npz.  The 48 records (NSTEP 1..48,
 the range test/test_CanHydro.cc:154 loops over) become 48 columns.  Data only; format described in
 src/utils/read_test_input.cc:14-23 ("NSTEP n" / "name v0 v1 ..." / "!!! n")."""
@@ -61,6 +61,23 @@ def canopy_fluxes():
           "night records", int((out["in_parsun_z"][:, 0] <= 0).sum()))
 
 
+def surface_albedo():
+    """test/data/SurfaceAlbedo_{IN,OUT}.txt, records 2..96 (test/test_SurfAlb.cc:391 loops over 2..48)."""
+    i = parse(R / "test/data/SurfaceAlbedo_IN.txt")
+    o = parse(R / "test/data/SurfaceAlbedo_OUT.txt")
+    steps = sorted(set(i) & set(o))
+    out = {"steps": np.array(steps)}
+    for name in i[steps[0]]:
+        out["in_" + name] = stack(i, steps, name)
+    for name in o[steps[0]]:
+        out["out_" + name] = stack(o, steps, name)
+    dst = ROOT / "tests/golden/elm_surface_albedo.npz"
+    np.savez_compressed(dst, **out)
+    print(dst, dst.stat().st_size, "bytes;", len(steps), "records; sunlit", int((out["in_coszen"][:, 0] > 0).sum()),
+          "snl", np.unique(out["in_snl"]), "h2osno", np.unique(out["in_h2osno"]))
+
+
 if __name__ == "__main__":
     main()
     canopy_fluxes()
+    surface_albedo()
