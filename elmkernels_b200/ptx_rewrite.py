@@ -122,6 +122,15 @@ def _find_partner(body: list[str], i: int, general):
     return None
 
 
+def reciprocal_is_safe(c: float) -> bool:
+    """delta = |c * RN(1/c) - 1| * 2^53 < 1/2, evaluated exactly: the condition under which q = RN(a * RN(1/c)) is a
+    faithful quotient for every numerator (see _recip_div)."""
+    from fractions import Fraction
+    if c != c or c == 0.0 or abs(c) == float("inf"):
+        return False
+    return abs(Fraction(c) * Fraction(1.0 / c) - 1) * 2 ** 53 < Fraction(1, 2)
+
+
 def _f64_imm(x: float) -> str:
     return "0d%016X" % struct.unpack("<Q", struct.pack("<d", x))[0]
 
@@ -129,11 +138,15 @@ def _f64_imm(x: float) -> str:
 def _recip_div(ind: str, d: str, a: str, rc: str, nc: str, k: int, b_for_call: str, ok_pred: str | None) -> str:
     """d = a / c through the correctly rounded reciprocal rc = RN(1/c) (nc = -c):
          q = a * rc;  r = fma(q, -c, a);  d = fma(r, rc, q)
-    which is the correctly rounded quotient when rc is correctly rounded and nothing under- or overflows
-    (Markstein's theorem; the same three operations end the Newton sequence ptxas emits for div.rn.f64).  The
-    numerator's exponent is checked to lie in [-500, 500] (the divisor's in [-100, 100]: at build time for a
-    literal, by `ok_pred` for a kernel parameter); zero, subnormal, huge, infinite and NaN numerators take the
-    general m_div call."""
+    Markstein's theorem: d = RN(a / c) when rc = RN(1/c), r is exact and q is a FAITHFUL rounding of a / c (the same
+    three operations end the Newton sequence ptxas emits for div.rn.f64).  q = RN(a * rc) is within
+    m_q * delta / 2 + 1/2 ulp of a / c, where m_q in [1, 2) is the significand of the quotient and
+    delta = |c * rc - 1| * 2^53 in [0, 1] the rounding error of the reciprocal; it is faithful for EVERY numerator
+    when delta < 1/2 (reciprocal_is_safe), and only then is this sequence emitted: at build time for a literal, by
+    `ok_pred` for a kernel parameter (the predicate also holds the divisor's exponent range).  Divisors that fail the
+    test (e.g. 0.05, 1.5e-5) go to the general routine: for them specific numerators do round wrongly (Brisebarre,
+    Muller, Raina 2004).  The numerator's exponent is checked to lie in [-500, 500]; zero, subnormal, huge, infinite
+    and NaN numerators take the general m_div call."""
     guard = f"{ind}and.pred \t%pg, %pg, {ok_pred};\n" if ok_pred else ""
     return (f"{ind}{{ // elmk division by a constant / kernel parameter\n"
             f"{ind}.reg .b32 %lo, %hi, %ex;\n{ind}.reg .pred %pg;\n{ind}.reg .f64 %q, %r;\n"
@@ -212,7 +225,9 @@ def _rewrite_function(name: str, body: list[str], counter: list[int], stats: dic
         ind, d, a, b = (x.strip() if i else x for i, x in enumerate(m.groups()))
         if b.startswith("0d") and not a.startswith("0d"):
             c = struct.unpack("<d", struct.pack("<Q", int(b[2:], 16)))[0]
-            if c == c and 2.0 ** -100 < abs(c) < 2.0 ** 100:
+            if c == c and 2.0 ** -100 < abs(c) < 2.0 ** 100 and not reciprocal_is_safe(c):
+                stats["const_general"] = stats.get("const_general", 0) + 1
+            if c == c and 2.0 ** -100 < abs(c) < 2.0 ** 100 and reciprocal_is_safe(c):
                 out.append(_recip_div(ind, d, a, _f64_imm(1.0 / c), _f64_imm(-c), counter[0], b, None))
                 counter[0] += 1
                 stats["const"] += 1
@@ -250,14 +265,19 @@ def _rewrite_function(name: str, body: list[str], counter: list[int], stats: dic
             res.append(l)
             if l.strip() == "{" and not any(x.startswith("\t.reg .f64 %elmk_rc") for x in res):
                 n = len(params)
-                res.append(f"\t.reg .f64 \t%elmk_rc<{n}>;\n\t.reg .f64 \t%elmk_nc<{n}>;\n\t.reg .pred \t%elmk_pc<{n}>;\n"
+                res.append(f"\t.reg .f64 \t%elmk_rc<{n}>;\n\t.reg .f64 \t%elmk_nc<{n}>;\n\t.reg .f64 \t%elmk_dl<{n}>;\n\t.reg .pred \t%elmk_pc<{n}>;\n"
                            f"\t.reg .b32 \t%elmk_t<3>;")
             m = LDPARAM.match(l)
             if m and m.group(1) in used:
                 r, i = m.group(1), params[m.group(1)]
+                # exponent of the divisor within [-100, 100] and delta = |c * rc - 1| * 2^53 < 1/2 (c * rc - 1 is
+                # exactly representable: one fma), i.e. |c * rc - 1| < 2^-54
                 res.append(f"\trcp.rn.f64 \t%elmk_rc{i}, {r};\n\tneg.f64 \t%elmk_nc{i}, {r};\n"
                            f"\tmov.b64 \t{{%elmk_t0, %elmk_t1}}, {r};\n\tbfe.u32 \t%elmk_t2, %elmk_t1, 20, 11;\n"
-                           f"\tsub.u32 \t%elmk_t2, %elmk_t2, 923;\n\tsetp.lt.u32 \t%elmk_pc{i}, %elmk_t2, 201;")
+                           f"\tsub.u32 \t%elmk_t2, %elmk_t2, 923;\n\tsetp.lt.u32 \t%elmk_pc{i}, %elmk_t2, 201;\n"
+                           f"\tfma.rn.f64 \t%elmk_dl{i}, {r}, %elmk_rc{i}, 0dBFF0000000000000;\n"
+                           f"\tabs.f64 \t%elmk_dl{i}, %elmk_dl{i};\n"
+                           f"\tsetp.lt.and.f64 \t%elmk_pc{i}, %elmk_dl{i}, 0d3C90000000000000, %elmk_pc{i};")
         out = res
     return out
 
@@ -325,7 +345,7 @@ def main(path: str) -> None:
     open(path, "w").write(new)
     print(f"ptx_rewrite: {st['call']} double divisions routed through elmk::m_div, {st['pair']} pairwise through "
           f"elmk::m_div2, {st['inline']} kept in line (marked stretches), {st['const']} by literals and {st['param']} by kernel parameters through exact reciprocal "
-          f"sequences, in {path}")
+          f"sequences ({st.get('const_general', 0)} literal divisors fail the faithful-quotient test and take the general routine), in {path}")
 
 
 if __name__ == "__main__":

@@ -64,6 +64,23 @@ def test_rewrite_forms():
     assert "div.rn.f64 \t%fd3, %fd1, %fd2;" in out[:out.index(".entry k_test")]
 
 
+def test_reciprocal_sequence_only_where_the_quotient_estimate_is_provably_faithful():
+    """q = RN(a * RN(1/c)) is a faithful quotient for every numerator iff delta = |c RN(1/c) - 1| 2^53 < 1/2 (then
+    Markstein's theorem applies); other divisors - 0.05 sits exactly on the bound, 1.5e-5 is far beyond it - must go
+    to the general routine, and a kernel-parameter divisor is tested on the device before the sequence is used."""
+    assert R.reciprocal_is_safe(1800.0) and R.reciprocal_is_safe(1000.0) and R.reciprocal_is_safe(917.0)
+    assert R.reciprocal_is_safe(2.0) and R.reciprocal_is_safe(86400.0)
+    assert not R.reciprocal_is_safe(0.05) and not R.reciprocal_is_safe(1.5e-5) and not R.reciprocal_is_safe(0.0)
+    unsafe = "0d%016X" % struct.unpack("<Q", struct.pack("<d", 1.5e-5))[0]
+    out, st = R.rewrite(SNIPPET.replace("0d408F400000000000", unsafe))
+    assert (st["call"], st["const"], st["param"], st.get("const_general")) == (2, 0, 1, 1)
+    body = out[out.index(".entry k_test"):]
+    assert "mul.rn.f64 \t%q, %fd1" not in body
+    # the run-time test of a parameter divisor: |c * rc - 1| < 2^-54
+    assert "fma.rn.f64 \t%elmk_dl0, %fd9, %elmk_rc0, 0dBFF0000000000000" in body
+    assert "setp.lt.and.f64 \t%elmk_pc0, %elmk_dl0, 0d3C90000000000000, %elmk_pc0" in body
+
+
 def test_pairing_does_not_move_a_division_across_the_load_that_defines_its_operand():
     """Vector destinations ({%fd7, %fd8} of an ld.v2.f64) count as written; an f64 instruction in a form the pass does
     not parse ends the pairing window (fail closed)."""
