@@ -2,12 +2,14 @@
 # The measurement sequence whose outputs are committed under profiles/ (run under gpurun on one B200): tools/final_measure.sh [tag]
 TAG=${1:-r2}
 set -x
+if [ -z "$ONLY_NCU" ]; then
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err || exit 1
 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/${TAG}_bench_reference_arm.json 2>> gpurun_out/${TAG}_bench.err
 for c in 2 3 4; do
   python bench.py --config $c --steps 20 > gpurun_out/${TAG}_bench_config$c.json 2>> gpurun_out/${TAG}_bench.err
 done
-K='regex:k_groups|k_canflux|k_init|k_snicar|k_coszen|k_phenology|k_atm'
+fi
+K='regex:k_groups|k_canflux|k_init_timestep|k_snicar|k_coszen|k_phenology|k_atm|k_bareground'
 # launch list of the default workload (2M columns), two timed steps
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-verify"
 $CMD > gpurun_out/${TAG}_plain_launches.log 2>&1 &&

@@ -25,7 +25,7 @@ GROUP = [("k_init_timestep", "init_timestep"), ("k_coszen", "coszen"), ("k_pheno
          ("k_groups_sorted<3", "fracwet+albedo"), ("k_snicar", "fracwet+albedo"), ("k_groups_occ<1048577", "fracwet+albedo"),
          ("k_groups_occ<60", "hydrology+radiation+temperature+bareground"),
          ("k_groups<4", "canopy_hydrology"), ("k_groups<8", "surface_radiation"), ("k_groups<16", "canopy_temperature"),
-         ("k_groups<32", "bareground_fluxes"),
+         ("k_groups<32", "bareground_fluxes"), ("k_bareground", "bareground_fluxes"),
          ("k_canflux", "canopy_fluxes"), ("k_groups_occ<128", "soil_temperature"), ("k_groups_occ<1792", "snow+surface_fluxes+conservation")]
 res = OrderedDict()
 for d in K.values():
