@@ -703,7 +703,7 @@ const Launch kFused[] = {
     ELMK_LAUNCH(ELMK_G_CANOPY_TEMPERATURE, "canopy_temperature"),
     {ELMK_G_BAREGROUND_FLUXES, k_bareground_compact, "bareground_fluxes", kBareWindow, kBlock, kPlain},
     {ELMK_G_CANOPY_FLUXES, k_groups<ELMK_G_CANOPY_FLUXES>, "canopy_fluxes", kBlock, kBlock, kCanfluxRepacked},
-    ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 8),
+    ELMK_LAUNCH_OCC(ELMK_G_SOIL_TEMPERATURE, "soil_temperature", 10),
     ELMK_LAUNCH_OCC(M_END, "snow+surface_fluxes+conservation", 6),
 };
 #ifdef ELMK_DEV_VARIANTS

@@ -53,20 +53,21 @@ ELMK_HD void column_soil_temperature(const Cols& S, const Tables&, const double 
   // phase change - and re-reads the few per-layer inputs each pass needs instead of holding the ~340 doubles
   // of the column (state, conductivities, five bands, right-hand side, solver work arrays) at once: the first
   // version of this kernel ran at 255 registers with 2.9 KB of spills per thread.
-  double t[NLEVTOT], z[NLEVTOT];
-#pragma unroll
-  for (int i = 0; i < NLEVTOT; ++i) {
-    t[i] = C2(t_soisno, i);
-    z[i] = C2(zsoi, i);
-  }
+  // (the old temperatures, the node depths, the absorbed radiation of the snow layers and - once computed - fact are
+  //  read from the state where they are needed: per-thread copies of them were half of a 1.5 KB frame, and at 28 resident
+  //  warps per SM the frames of the launch exceed L2; the rows are L1 / L2 hits for the block that has just read them)
+#define t_old(i) C2(t_soisno, i)
+#define z_node(i) C2(zsoi, i)
 
-  // ---- pass 1: thermal conductivity (Johansen) and heat capacity of every layer -> fact ----
-  double thk[NLEVTOT], fact[NLEVTOT];
+  // ---- pass 1: thermal conductivity (Johansen) and heat capacity of every layer -> fact; the conductivity at the
+  //      interface above and the diffusive heat flux through it as soon as both neighbours are known ----
+  double tk[NLEVTOT], fn[NLEVTOT];
+  double thk_above = 0.0, thk_soil1 = 0.0;
 ELMK_SOIL_LOOP
   for (int i = 0; i < NLEVTOT; ++i) {
     if (i % 5 == 0 && i > 0) ELMK_REALIGN(REALIGN);
     const double liq = C2(h2osoi_liq, i), ice = C2(h2osoi_ice, i), dz = C2(dz, i);
-    double cv;
+    double cv, thk_i;
     if (i >= NLEVSNO) {
       const int k = i - NLEVSNO;
       const double watsat = C2(watsat, k);
@@ -75,47 +76,51 @@ ELMK_SOIL_LOOP
       satw = dmin(1.0, satw);
       const double tkdry = C2(tkdry, k);
       if (satw > 1.0e-6) {
-        const double dke = (t[i] >= TFRZ) ? dmax(0.0, m_log10(satw) + 1.0) : satw;
+        const double dke = (t_old(i) >= TFRZ) ? dmax(0.0, m_log10(satw) + 1.0) : satw;
         const double fl = hold.q0 / (hold.q0 + hold.q1);
         const double dksat = C2(tkmg, k) * pow_cbase(TKWAT, ELMK_LN_TKWAT, fl * watsat) * pow_cbase(TKICE, ELMK_LN_TKICE, (1.0 - fl) * watsat);
-        thk[i] = dke * dksat + (1.0 - dke) * tkdry;
+        thk_i = dke * dksat + (1.0 - dke) * tkdry;
       } else {
-        thk[i] = tkdry;
+        thk_i = tkdry;
       }
       // (no layer lies below nlevbed == nlevgrnd, so the bedrock override never applies)
       cv = C2(csol, i) * (1.0 - watsat) * dz + (ice * CPICE + liq * CPWAT);
       if (i == NLEVSNO && snl == 0 && h2osno > 0.0) cv += CPICE * h2osno;
     } else if (i < top) {
-      thk[i] = 0.0;
+      thk_i = 0.0;
       cv = 0.0;
     } else {
       const double bw = (ice + liq) / (fsno * dz);
-      thk[i] = TKAIR + (7.75e-5 * bw + 1.105e-6 * bw * bw) * (TKICE - TKAIR);
+      thk_i = TKAIR + (7.75e-5 * bw + 1.105e-6 * bw * bw) * (TKICE - TKAIR);
       cv = (fsno > 0.0) ? dmax(THIN_SFCLAYER, (CPWAT * liq + CPICE * ice) / fsno) : THIN_SFCLAYER;
     }
-    if (i < top) fact[i] = 0.0;
-    else if (i == top) fact[i] = dtime / cv * dz / (0.5 * (z[i] - C2(zisoi, i) + CAPR * (z[(i + 1 < NLEVTOT) ? i + 1 : i] - C2(zisoi, i))));
-    else fact[i] = dtime / cv;
-    C2(fact, i) = fact[i];
+    const double zi = z_node(i);
+    double fact_i;
+    if (i < top) fact_i = 0.0;
+    else if (i == top) fact_i = dtime / cv * dz / (0.5 * (zi - C2(zisoi, i) + CAPR * (z_node((i + 1 < NLEVTOT) ? i + 1 : i) - C2(zisoi, i))));
+    else fact_i = dtime / cv;
+    C2(fact, i) = fact_i;
+    if (i == NLEVSNO) thk_soil1 = thk_i;
+    if (i > 0) {
+      // interface between layers i - 1 and i
+      const int j = i - 1;
+      if (j < top) {
+        tk[j] = 0.0;
+        fn[j] = 0.0;
+      } else {
+        const double zj = z_node(j), zi1 = C2(zisoi, i);
+        tk[j] = thk_above * thk_i * (zi - zj) / (thk_above * (zi - zi1) + thk_i * (zi1 - zj));
+        fn[j] = tk[j] * (t_old(i) - t_old(j)) / (zi - zj);
+      }
+    }
+    thk_above = thk_i;
   }
   ELMK_REALIGN(REALIGN);
-  // conductivity at the interfaces and the diffusive heat flux through them
-  double tk[NLEVTOT], fn[NLEVTOT];
-ELMK_SOIL_LOOP
-  for (int i = 0; i < NLEVTOT - 1; ++i) {
-    if (i < top) {
-      tk[i] = 0.0;
-      fn[i] = 0.0;
-    } else {
-      const double zi1 = C2(zisoi, i + 1);
-      tk[i] = thk[i] * thk[i + 1] * (z[i + 1] - z[i]) / (thk[i] * (z[i + 1] - zi1) + thk[i + 1] * (zi1 - z[i]));
-      fn[i] = tk[i] * (t[i + 1] - t[i]) / (z[i + 1] - z[i]);
-    }
-  }
   tk[NLEVTOT - 1] = 0.0;
   fn[NLEVTOT - 1] = 0.0;
   const double zh2osfc = 1.0e-3 * (0.5 * h2osfc);
-  const double tk_sfc = TKWAT * thk[NLEVSNO] * (z[NLEVSNO] + zh2osfc) / (TKWAT * z[NLEVSNO] + thk[NLEVSNO] * zh2osfc);
+  const double z_soil1 = z_node(NLEVSNO);
+  const double tk_sfc = TKWAT * thk_soil1 * (z_soil1 + zh2osfc) / (TKWAT * z_soil1 + thk_soil1 * zh2osfc);
   const bool ponded = (h2osfc > THIN_SFCLAYER) && (fsfc > THIN_SFCLAYER);
   const double c_sfc = ponded ? dmax(THIN_SFCLAYER, CPWAT * h2osfc / fsfc) : THIN_SFCLAYER;
   const double dz_sfc = ponded ? dmax(THIN_SFCLAYER, 1.0e-3 * h2osfc / fsfc) : THIN_SFCLAYER;
@@ -124,19 +129,13 @@ ELMK_SOIL_LOOP
   const int veg = C1(frac_veg_nosno);
   const double dlrad = C1(dlrad), emg = C1(emg), lwrad = C1(forc_lwrad), htvp = C1(htvp);
   const double sabg_soil = C1(sabg_soil), sabg_snow = C1(sabg_snow);
-  double sabg_lyr[NLEVSNO + 1];
-#pragma unroll
-  for (int i = 0; i <= NLEVSNO; ++i) sabg_lyr[i] = C2(sabg_lyr, i);
   C1(sabg_chk) = fse * sabg_snow + (1.0 - fse) * sabg_soil;
   const double lw_in = (1.0 - veg) * emg * lwrad;
-  const double hs_soil = sabg_soil + dlrad + lw_in - emg * STEBOL * pow4(t[NLEVSNO]) -
+  const double hs_soil = sabg_soil + dlrad + lw_in - emg * STEBOL * pow4(t_old(NLEVSNO)) -
                          (C1(eflx_sh_soil) + C1(qflx_ev_soil) * htvp);
   const double hs_sfc = sabg_soil + dlrad + lw_in - emg * STEBOL * pow4(t_sfc) -
                         (C1(eflx_sh_h2osfc) + C1(qflx_ev_h2osfc) * htvp);
-  double t_top = t[NLEVSNO], sabg_top = sabg_lyr[NLEVSNO];
-#pragma unroll
-  for (int i = 0; i < NLEVSNO; ++i)
-    if (i == top) { t_top = t[i]; sabg_top = sabg_lyr[i]; }
+  const double t_top = t_old(top), sabg_top = C2(sabg_lyr, top);   // (top == NLEVSNO without snow layers)
   const double hs_top_snow = sabg_top + dlrad + lw_in - emg * STEBOL * pow4(t_top) -
                              (C1(eflx_sh_snow) + C1(qflx_ev_snow) * htvp);
   const double dhsdT = -C1(cgrnd) - 4.0 * emg * STEBOL * cube(C1(t_grnd));
@@ -149,7 +148,7 @@ ELMK_SOIL_LOOP
   constexpr double OMC = 1.0 - CNFAC;
   constexpr int N = NROWS;
   double A[N], B[N], Z[N];
-  const double fn_sfc = tk_sfc * (t[NLEVSNO] - t_sfc) / (0.5 * dz_sfc + z[NLEVSNO]);
+  const double fn_sfc = tk_sfc * (t_old(NLEVSNO) - t_sfc) / (0.5 * dz_sfc + z_node(NLEVSNO));
 ELMK_SOIL_LOOP
   for (int r = 0; r < N; ++r) {
     if (r % 5 == 0 && r > 0) ELMK_REALIGN(REALIGN);
@@ -159,60 +158,60 @@ ELMK_SOIL_LOOP
       const int i = r;
       active = (i >= top);
       if (i == top) {
-        const double dzp = z[i + 1] - z[i];
-        b2 = 1.0 + OMC * fact[i] * tk[i] / dzp - fact[i] * dhsdT;
-        if (snl > 1) b1 = -OMC * fact[i] * tk[i] / dzp;
-        rhs = t[i] + fact[i] * (hs_top_snow - dhsdT * t[i] + CNFAC * fn[i]);
+        const double dzp = z_node(i + 1) - z_node(i);
+        b2 = 1.0 + OMC * C2(fact, i) * tk[i] / dzp - C2(fact, i) * dhsdT;
+        if (snl > 1) b1 = -OMC * C2(fact, i) * tk[i] / dzp;
+        rhs = t_old(i) + C2(fact, i) * (hs_top_snow - dhsdT * t_old(i) + CNFAC * fn[i]);
       } else if (i > top) {
         const int im = (i > 0) ? i - 1 : 0;
-        const double dzm = z[i] - z[im];
-        const double dzp = z[i + 1] - z[i];
-        b3 = -OMC * fact[i] * tk[im] / dzm;
-        b2 = 1.0 + OMC * fact[i] * (tk[i] / dzp + tk[im] / dzm);
-        if (i != NLEVSNO - 1) b1 = -OMC * fact[i] * tk[i] / dzp;
-        rhs = t[i] + CNFAC * fact[i] * (fn[i] - fn[im]) + fact[i] * sabg_lyr[i];
+        const double dzm = z_node(i) - z_node(im);
+        const double dzp = z_node(i + 1) - z_node(i);
+        b3 = -OMC * C2(fact, i) * tk[im] / dzm;
+        b2 = 1.0 + OMC * C2(fact, i) * (tk[i] / dzp + tk[im] / dzm);
+        if (i != NLEVSNO - 1) b1 = -OMC * C2(fact, i) * tk[i] / dzp;
+        rhs = t_old(i) + CNFAC * C2(fact, i) * (fn[i] - fn[im]) + C2(fact, i) * C2(sabg_lyr, i);
       }
       // bottom snow layer -> top soil layer, across the surface-water row
-      if (i == NLEVSNO - 1 && snl > 0) b0 = -OMC * fact[i] * tk[i] / (z[NLEVSNO] - z[i]);
+      if (i == NLEVSNO - 1 && snl > 0) b0 = -OMC * C2(fact, i) * tk[i] / (z_node(NLEVSNO) - z_node(i));
     } else if (r == NLEVSNO) {
-      b2 = 1.0 + OMC * (dtime / c_sfc) * tk_sfc / (0.5 * dz_sfc + z[NLEVSNO]) - (dtime / c_sfc) * dhsdT;
-      b1 = -OMC * (dtime / c_sfc) * tk_sfc / (0.5 * dz_sfc + z[NLEVSNO]);
+      b2 = 1.0 + OMC * (dtime / c_sfc) * tk_sfc / (0.5 * dz_sfc + z_node(NLEVSNO)) - (dtime / c_sfc) * dhsdT;
+      b1 = -OMC * (dtime / c_sfc) * tk_sfc / (0.5 * dz_sfc + z_node(NLEVSNO));
       rhs = t_sfc + (dtime / c_sfc) * (hs_sfc - dhsdT * t_sfc + CNFAC * fn_sfc);
     } else if (r == NLEVSNO + 1) {
       const int s = NLEVSNO;
-      const double dzp = z[s + 1] - z[s];
+      const double dzp = z_node(s + 1) - z_node(s);
       if (snl == 0) {
-        b2 = 1.0 + OMC * fact[s] * tk[s] / dzp - fact[s] * dhsdT;
-        b1 = -OMC * fact[s] * tk[s] / dzp;
-        rhs = t[s] + fact[s] * (hs_top_snow - dhsdT * t[s] + CNFAC * fn[s]);
+        b2 = 1.0 + OMC * C2(fact, s) * tk[s] / dzp - C2(fact, s) * dhsdT;
+        b1 = -OMC * C2(fact, s) * tk[s] / dzp;
+        rhs = t_old(s) + C2(fact, s) * (hs_top_snow - dhsdT * t_old(s) + CNFAC * fn[s]);
       } else {
-        const double dzm = z[s] - z[s - 1];
-        b2 = 1.0 + OMC * fact[s] * (tk[s] / dzp + fse * tk[s - 1] / dzm) - (1.0 - fse) * fact[s] * dhsdT;
-        b1 = -OMC * fact[s] * tk[s] / dzp;
-        b4 = -fse * OMC * fact[s] * tk[s - 1] / dzm;
-        double rr = t[s] + fact[s] * ((1.0 - fse) * (hs_soil - dhsdT * t[s]) + CNFAC * (fn[s] - fse * fn[s - 1]));
-        rr += fse * fact[s] * sabg_lyr[s];
+        const double dzm = z_node(s) - z_node(s - 1);
+        b2 = 1.0 + OMC * C2(fact, s) * (tk[s] / dzp + fse * tk[s - 1] / dzm) - (1.0 - fse) * C2(fact, s) * dhsdT;
+        b1 = -OMC * C2(fact, s) * tk[s] / dzp;
+        b4 = -fse * OMC * C2(fact, s) * tk[s - 1] / dzm;
+        double rr = t_old(s) + C2(fact, s) * ((1.0 - fse) * (hs_soil - dhsdT * t_old(s)) + CNFAC * (fn[s] - fse * fn[s - 1]));
+        rr += fse * C2(fact, s) * C2(sabg_lyr, s);
         rhs = rr;
       }
       if (fsfc != 0.0) {
-        const double dzm = 0.5 * dz_sfc + z[s];
-        b2 += fsfc * (OMC * fact[s] * tk_sfc / dzm + fact[s] * dhsdT);
-        b3 = -fsfc * OMC * fact[s] * tk_sfc / (0.5 * dz_sfc + z[s]);
+        const double dzm = 0.5 * dz_sfc + z_node(s);
+        b2 += fsfc * (OMC * C2(fact, s) * tk_sfc / dzm + C2(fact, s) * dhsdT);
+        b3 = -fsfc * OMC * C2(fact, s) * tk_sfc / (0.5 * dz_sfc + z_node(s));
       }
     } else if (r < N - 1) {
       const int j = r - 1;
-      const double dzm = z[j] - z[j - 1];
-      const double dzp = z[j + 1] - z[j];
-      b3 = -OMC * fact[j] * tk[j - 1] / dzm;
-      b2 = 1.0 + OMC * fact[j] * (tk[j] / dzp + tk[j - 1] / dzm);
-      b1 = -OMC * fact[j] * tk[j] / dzp;
-      rhs = t[j] + CNFAC * fact[j] * (fn[j] - fn[j - 1]);
+      const double dzm = z_node(j) - z_node(j - 1);
+      const double dzp = z_node(j + 1) - z_node(j);
+      b3 = -OMC * C2(fact, j) * tk[j - 1] / dzm;
+      b2 = 1.0 + OMC * C2(fact, j) * (tk[j] / dzp + tk[j - 1] / dzm);
+      b1 = -OMC * C2(fact, j) * tk[j] / dzp;
+      rhs = t_old(j) + CNFAC * C2(fact, j) * (fn[j] - fn[j - 1]);
     } else {
       const int b = NLEVTOT - 1;
-      const double dzm = z[b] - z[b - 1];
-      b3 = -OMC * fact[b] * tk[b - 1] / dzm;
-      b2 = 1.0 + OMC * fact[b] * tk[b - 1] / dzm;
-      rhs = t[b] - CNFAC * fact[b] * fn[b - 1] + fact[b] * fn[b];
+      const double dzm = z_node(b) - z_node(b - 1);
+      b3 = -OMC * C2(fact, b) * tk[b - 1] / dzm;
+      b2 = 1.0 + OMC * C2(fact, b) * tk[b - 1] / dzm;
+      rhs = t_old(b) - CNFAC * C2(fact, b) * fn[b - 1] + C2(fact, b) * fn[b];
     }
 
     // forward elimination of row r
@@ -246,8 +245,7 @@ ELMK_SOIL_LOOP
   }
   ELMK_REALIGN(REALIGN);
   // back substitution; the solution overwrites Z
-  double sol[N];
-  sol[N - 1] = Z[N - 1];
+  double* const sol = Z;
   sol[N - 2] = Z[N - 2] - A[N - 2] * sol[N - 1];
 ELMK_SOIL_LOOP
   for (int i = N - 3; i >= 0; --i) sol[i] = Z[i] - A[i] * sol[i + 1] - B[i] * sol[i + 2];
@@ -257,7 +255,7 @@ ELMK_SOIL_LOOP
 
   // ---- phase change of standing surface water (touches the bottom snow slot only) ----
   constexpr int SB = NLEVSNO - 1;   // bottom snow slot
-  const double fact_sb = fact[SB];
+  const double fact_sb = C2(fact, SB);
   double t_sb = (SB >= top) ? sol[SB] : C2(t_soisno, SB);
   double ice_sb = C2(h2osoi_ice, SB);
   double int_snow = C1(int_snow), snow_depth = C1(snow_depth);
@@ -336,7 +334,7 @@ ELMK_SOIL_LOOP
     double ti = (i == SB) ? t_sb : ((i < NLEVSNO) ? sol[i] : sol[(i + 1 < N) ? i + 1 : i]);
     double liq = C2(h2osoi_liq, i);
     double ice = (i == SB) ? ice_sb : C2(h2osoi_ice, i);
-    const double fi = fact[i];
+    const double fi = C2(fact, i);
     int imelt = 0;
     double tinc = 0.0, supercool = 0.0;
     if (i < NLEVSNO) {
@@ -461,5 +459,8 @@ ELMK_SOIL_LOOP
   C1(int_snow) = int_snow;
   C1(snow_depth) = snow_depth;
 }
+
+#undef t_old
+#undef z_node
 
 } // namespace elmk
