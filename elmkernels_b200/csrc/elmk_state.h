@@ -69,9 +69,10 @@ struct StepArgs {
 // (stride 1: per-thread rows and the flat argument arrays of elmk_fn_call)
 struct ColRow {
   double* p;
-  long long stride;
-  ELMK_HD double& operator[](const int i) const { return p[(long long)i * stride]; }
+  int stride;   // (32-bit element offsets: i * stride < 2^31, as for C2)
+  ELMK_HD double& operator[](const int i) const { return p[i * stride]; }
+  ELMK_HD ColRow from(const int first) const { return ColRow{p + first * stride, stride}; }   // the row from element `first` on
 };
-#define ELMK_ROW(field) ColRow{S.field + c, S.np}
+#define ELMK_ROW(field) ColRow{S.field + c, S.npi}
 
 } // namespace elmk
