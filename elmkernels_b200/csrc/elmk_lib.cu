@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_canflux_begin(const Cols S, const
   if (c < S.ncols) {
     const PsnPft P = load_psn_pft(S, c);
     CanopyIter I;
-    if (canflux_begin(S, *Tp, A, P, c, I)) {
+    if (canflux_begin(S, Tp->vtype, A, P, c, I)) {
       canflux_store(Q, c, I, true);
       cls = (I.parsun > 0.0 || I.parsha > 0.0) ? 2 : 1;
     }
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(kBlock, ELMK_BARE_OCC) k_bareground_compact(co
 
 // elmk_fn_call: one library-level physics function on the flat argument array of ONE column (include/elm/*.h)
 #define FlatRow(ptr) ColRow{(ptr), 1}
-constexpr int kFnSlots[ELMK_FN_COUNT] = {13, 14, 7, 150, 26, 11, 36, 39, 9, 18, 42, 25, 160, 93, 35, 61, 10, 6, 20, 22, 56};
+constexpr int kFnSlots[ELMK_FN_COUNT] = {13, 14, 7, 150, 26, 11, 36, 39, 9, 18, 42, 25, 160, 93, 35, 61, 10, 6, 20, 22, 56, 217, 127, 83};
 __global__ void k_fn_call(const int fn, double* __restrict__ a)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -634,6 +634,113 @@ __global__ void k_fn_call(const int fn, double* __restrict__ a)
         a[50] = f.qflx_ev_snow; a[51] = f.qflx_ev_soil; a[52] = f.qflx_ev_h2osfc; a[53] = f.t_ref2m; a[54] = f.q_ref2m;
         a[55] = f.rh_ref2m;
       }
+    } break;
+    // ---- canopy_fluxes (phys_canflux.h): the three functions are canflux_begin, the loop over canflux_iterate and
+    //      canflux_end of the re-packed kernels, run here on a one-column view of the argument array: the fields of
+    //      the state the device code reads or writes point at the argument slots (np == 1), fields that are not
+    //      arguments of the function at zeros / a sink ----
+    case ELMK_FN_CF_INITIALIZE_FLUX: {
+      // snl veg frac_sno hgt_u thm thv max_dayl dayl altmax altmax_last | t_soisno[20] ice[20] liq[20] dz[20] rootfr[15]
+      // | tc_stress | sucsat[15] watsat[15] bsw[15] | smpso smpsc elai esai emv emg qg t_grnd forc_t pbot lwrad u v q th z0mg
+      // || btran displa z0mv z0hv z0qv rootr[15] eff_porosity[15] dayl_factor air bir cir el qsatl qsatldT taf qaf um ur
+      // obu zldis delq t_veg
+      double zero[NLEVTOT + 1] = {}, sink[4] = {};
+      int iv[3] = {(int)a[0], (int)a[1], 0};
+      Cols S = {};
+      S.np = 1; S.npi = 1; S.ncols = 1;
+      S.snl = &iv[0]; S.frac_veg_nosno = &iv[1]; S.nrad = &iv[2];
+      S.frac_sno = a + 2; S.forc_hgt_u_patch = a + 3; S.forc_hgt_t_patch = a + 3; S.forc_hgt_q_patch = a + 3;
+      S.thm = a + 4; S.thv = a + 5; S.t_soisno = a + 10; S.h2osoi_ice = a + 30; S.h2osoi_liq = a + 50; S.dz = a + 70;
+      S.rootfr = a + 90; S.sucsat = a + 106; S.watsat = a + 121; S.bsw = a + 136; S.elai = a + 153; S.esai = a + 154;
+      S.emv = a + 155; S.emg = a + 156; S.qg = a + 157; S.t_grnd = a + 158; S.forc_tbot = a + 159; S.forc_pbot = a + 160;
+      S.forc_lwrad = a + 161; S.forc_u = a + 162; S.forc_v = a + 163; S.forc_qbot = a + 164; S.forc_thbot = a + 165;
+      S.z0mg = a + 166; S.btran = a + 167; S.displa = a + 168; S.z0mv = a + 169; S.z0hv = a + 170; S.z0qv = a + 171;
+      S.rootr = a + 172; S.eff_porosity = a + 187; S.t_veg = a + 216;
+      S.cgrnd = sink; S.cgrnds = sink + 1; S.cgrndl = sink + 2;
+      S.fwet = zero; S.fdry = zero; S.laisun = zero; S.laisha = zero; S.snow_depth = zero; S.soilbeta = zero;
+      S.frac_h2osfc = zero; S.t_h2osfc = zero; S.sabv = zero; S.htop = zero; S.t10 = zero; S.h2ocan = zero;
+      S.vcmaxcintsha = zero; S.vcmaxcintsun = zero; S.parsha_z = zero; S.parsun_z = zero; S.laisha_z = zero;
+      S.laisun_z = zero; S.qflx_tran_veg = zero; S.qflx_evap_veg = zero; S.eflx_sh_veg = zero;
+      PsnPft P = {};
+      P.tc_stress = a[105]; P.smpso = a[151]; P.smpsc = a[152];
+      StepArgs A{0.0, a[7], a[6]};
+      CanopyIter I = {};
+      if (canflux_begin(S, 0, A, P, 0, I)) {
+        a[167] = I.btran; a[202] = I.dayl_factor; a[203] = I.air; a[204] = I.bir; a[205] = I.cir; a[206] = I.el;
+        a[207] = I.qsatl; a[208] = I.qsatldT; a[209] = I.taf; a[210] = I.qaf; a[211] = I.um; a[212] = I.ur;
+        a[213] = I.obu; a[214] = I.zldis; a[215] = I.delq;
+      }
+    } break;
+    case ELMK_FN_CF_STABILITY_ITERATION: {
+      // vtype | dtime snl veg frac_sno hgt_u hgt_t hgt_q fwet fdry laisun laisha forc_rho snow_depth soilbeta frac_h2osfc
+      // t_h2osfc sabv h2ocan htop | t_soisno[20] | air bir cir ur zldis displa elai esai t_grnd pbot forc_q forc_th z0mg
+      // z0mv z0hv z0qv thm thv qg | psn_pft[27] | nrad t10 tlai_z vcmaxcintsha vcmaxcintsun parsha_z parsun_z laisha_z
+      // laisun_z forc_pco2 forc_po2 dayl_factor || btran qflx_tran_veg qflx_evap_veg eflx_sh_veg wtg wtl0 wta0 wtal el
+      // qsatl qsatldT taf qaf um dth dqh obu temp1 temp2 temp12m temp22m tlbef delq dt_veg t_veg wtgq wtalq wtlq0 wtaq0
+      if ((int)a[3] == 0) break;   // (no exposed vegetation: the reference's function does nothing)
+      const int vtype = (int)a[0], snl = (int)a[2];
+      PsnPft P;
+      {
+        double* q = reinterpret_cast<double*>(&P);
+        for (int k = 0; k < 27; ++k) q[k] = a[59 + k];
+      }
+      CanopyIter I = {};
+      I.veg = (int)a[3]; I.dtime = a[1]; I.fsno = a[4]; I.hgt_u = a[5]; I.hgt_t = a[6]; I.hgt_q = a[7]; I.fwet = a[8];
+      I.fdry = a[9]; I.laisun = a[10]; I.laisha = a[11]; I.forc_rho = a[12]; I.snow_depth = a[13]; I.soilbeta = a[14];
+      I.fsfc = a[15]; I.t_sfc = a[16]; I.sabv = a[17]; I.h2ocan0 = a[18]; I.htop = a[19];
+      I.t_snotop = a[20 + NLEVSNO - snl]; I.t_soil1 = a[20 + NLEVSNO];
+      I.air = a[40]; I.bir = a[41]; I.cir = a[42]; I.ur = a[43]; I.zldis = a[44]; I.displa = a[45]; I.elai = a[46];
+      I.esai = a[47]; I.tg = a[48]; I.pbot = a[49]; I.forc_q = a[50]; I.forc_th = a[51]; I.z0mg = a[52]; I.z0mv = a[53];
+      I.thm = a[56]; I.thv = a[57]; I.qg = a[58];
+      I.nrad = (int)a[86]; I.t10 = a[87]; I.vcsha = a[89]; I.vcsun = a[90]; I.parsha = a[91]; I.parsun = a[92];
+      I.laisha_z = a[93]; I.laisun_z = a[94]; I.forc_pco2 = a[95]; I.forc_po2 = a[96]; I.dayl_factor = a[97];
+      I.btran = a[98]; I.qflx_tran_veg = a[99]; I.qflx_evap_veg = a[100]; I.eflx_sh_veg = a[101];
+      I.el = a[106]; I.qsatl = a[107]; I.qsatldT = a[108]; I.taf = a[109]; I.qaf = a[110]; I.um = a[111]; I.obu = a[114];
+      I.delq = a[120]; I.t_veg = a[122];
+      I.dth = I.thm - I.taf; I.dqh = I.forc_q - I.qaf;   // (both are assigned inside the loop before their first use)
+      I.soybean = (vtype == PFT_SOYBEAN || vtype == PFT_SOYBEAN_IRRIG) ? 1 : 0;
+      I.lw_grnd = (I.fsno * pow4(I.t_snotop) + (1.0 - I.fsno - I.fsfc) * pow4(I.t_soil1) + I.fsfc * pow4(I.t_sfc));
+      const PsnColumn PC = psn_column(P, I.t10, I.pbot, I.thm, I.forc_po2, I.dayl_factor);
+#pragma unroll 1
+      while (!canflux_iterate(P, PC, I)) {
+      }
+      const double t12 = canflux_temp12m(I);
+      a[98] = I.btran; a[99] = I.qflx_tran_veg; a[100] = I.qflx_evap_veg; a[101] = I.eflx_sh_veg; a[102] = I.wtg;
+      a[103] = I.wtl0; a[104] = I.wta0; a[105] = I.wtal; a[106] = I.el; a[107] = I.qsatl; a[108] = I.qsatldT;
+      a[109] = I.taf; a[110] = I.qaf; a[111] = I.um; a[112] = I.dth; a[113] = I.dqh; a[114] = I.obu; a[115] = I.p_temp1;
+      a[116] = I.p_temp2; a[117] = t12; a[118] = t12; a[119] = I.tlbef; a[120] = I.delq; a[121] = I.dt_veg;
+      a[122] = I.t_veg; a[123] = I.wtgq; a[124] = I.wtalq; a[125] = I.wtlq0; a[126] = I.wtaq0;
+    } break;
+    case ELMK_FN_CF_COMPUTE_FLUX: {
+      // dtime snl veg frac_sno | t_soisno[20] | frac_h2osfc t_h2osfc sabv qg_snow qg_soil qg_h2osfc dqgdT htvp wtg wtl0 wta0
+      // wtal air bir cir qsatl qsatldT dth dqh temp1 temp2 temp12m temp22m tlbef delq dt_veg t_veg t_grnd pbot qflx_tran_veg
+      // qflx_evap_veg eflx_sh_veg forc_q forc_rho thm emv emg forc_lwrad wtgq wtalq wtlq0 wtaq0 || h2ocan eflx_sh_grnd
+      // eflx_sh_snow eflx_sh_soil eflx_sh_h2osfc qflx_evap_soi qflx_ev_snow qflx_ev_soil qflx_ev_h2osfc dlrad ulrad cgrnds
+      // cgrndl cgrnd t_ref2m q_ref2m rh_ref2m
+      a[77] = 0.0; a[78] = 0.0; a[79] = 0.0;
+      if ((int)a[2] == 0) break;
+      const int snl = (int)a[1];
+      double sink[8] = {};
+      int isink[1] = {0};
+      Cols S = {};
+      S.np = 1; S.npi = 1; S.ncols = 1;
+      S.btran = sink; S.t_veg = sink + 1; S.qflx_tran_veg = sink + 2; S.qflx_evap_veg = sink + 3; S.eflx_sh_veg = sink + 4;
+      S.errmask = isink;
+      S.htvp = a + 31; S.qg_snow = a + 27; S.qg_soil = a + 28; S.qg_h2osfc = a + 29; S.dqgdT = a + 30;
+      S.h2ocan = a + 66; S.eflx_sh_grnd = a + 67; S.eflx_sh_snow = a + 68; S.eflx_sh_soil = a + 69; S.eflx_sh_h2osfc = a + 70;
+      S.qflx_evap_soi = a + 71; S.qflx_ev_snow = a + 72; S.qflx_ev_soil = a + 73; S.qflx_ev_h2osfc = a + 74;
+      S.dlrad = a + 75; S.ulrad = a + 76; S.cgrnds = a + 77; S.cgrndl = a + 78; S.cgrnd = a + 79; S.t_ref2m = a + 80;
+      S.q_ref2m = a + 81; S.rh_ref2m = a + 82;
+      CanopyIter I = {};
+      I.dtime = a[0]; I.fsno = a[3]; I.t_snotop = a[4 + NLEVSNO - snl]; I.t_soil1 = a[4 + NLEVSNO]; I.fsfc = a[24];
+      I.t_sfc = a[25]; I.sabv = a[26]; I.wtg = a[32]; I.wtl0 = a[33]; I.wta0 = a[34]; I.wtal = a[35]; I.air = a[36];
+      I.bir = a[37]; I.cir = a[38]; I.qsatl = a[39]; I.qsatldT = a[40]; I.dth = a[41]; I.dqh = a[42]; I.p_temp1 = a[43];
+      I.p_temp2 = a[44]; I.tlbef = a[47]; I.delq = a[48]; I.dt_veg = a[49]; I.t_veg = a[50]; I.tg = a[51]; I.pbot = a[52];
+      I.qflx_tran_veg = a[53]; I.qflx_evap_veg = a[54]; I.eflx_sh_veg = a[55]; I.forc_q = a[56]; I.forc_rho = a[57];
+      I.thm = a[58]; I.emv = a[59]; I.emg = a[60]; I.forc_lwrad = a[61]; I.wtgq = a[62]; I.wtalq = a[63]; I.wtlq0 = a[64];
+      I.wtaq0 = a[65]; I.h2ocan0 = a[66];
+      I.lw_grnd = (I.fsno * pow4(I.t_snotop) + (1.0 - I.fsno - I.fsfc) * pow4(I.t_soil1) + I.fsfc * pow4(I.t_sfc));
+      canflux_end_with(S, 0, I, a[45], a[46]);
     } break;
     default: break;
   }

@@ -485,7 +485,7 @@ struct CanopyIter {
 
 // Non-vegetated columns: initialize_flux (:121-131) and the unconditional zeroing of compute_flux.
 // Returns false when the column has no exposed vegetation (nothing else to do).
-ELMK_HD bool canflux_begin(const Cols& S, const Tables& T, const StepArgs& A, const PsnPft& P, const int c, CanopyIter& I)
+ELMK_HD bool canflux_begin(const Cols& S, const int vtype, const StepArgs& A, const PsnPft& P, const int c, CanopyIter& I)
 {
   // canopy_fluxes::compute_flux zeroes these for every column (:475-480) - including the bare
   // columns whose values kokkos_bareground_fluxes has just computed
@@ -593,7 +593,7 @@ ELMK_HD bool canflux_begin(const Cols& S, const Tables& T, const StepArgs& A, co
   I.parsha = C2(parsha_z, 0); I.parsun = C2(parsun_z, 0);
   I.laisha_z = C2(laisha_z, 0); I.laisun_z = C2(laisun_z, 0);
   I.t_snotop = C2(t_soisno, NLEVSNO - snl); I.t_soil1 = C2(t_soisno, NLEVSNO);
-  I.soybean = (T.vtype == PFT_SOYBEAN || T.vtype == PFT_SOYBEAN_IRRIG) ? 1 : 0;
+  I.soybean = (vtype == PFT_SOYBEAN || vtype == PFT_SOYBEAN_IRRIG) ? 1 : 0;
   // ground-emitted longwave does not change during the iteration
   I.lw_grnd = (I.fsno * pow4(I.t_snotop) + (1.0 - I.fsno - I.fsfc) * pow4(I.t_soil1) + I.fsfc * pow4(I.t_sfc));
 
@@ -804,8 +804,9 @@ ELMK_HD bool canflux_iterate(const PsnPft& P, const PsnColumn& PC, CanopyIter& I
   return stop || !(I.itlef <= itmax);
 }
 
-// compute_flux (:482-539) and the write-back of the iteration results
-ELMK_HD void canflux_end(const Cols& S, const int c, const CanopyIter& I)
+// compute_flux (:482-539) and the write-back of the iteration results; p_temp12m / p_temp22m: the 2 m profile relations
+// of the last pass
+ELMK_HD void canflux_end_with(const Cols& S, const int c, const CanopyIter& I, const double p_temp12m, const double p_temp22m)
 {
   const double t_veg = I.t_veg, thm = I.thm, tg = I.tg, forc_q = I.forc_q, forc_rho = I.forc_rho;
   const double wtg = I.wtg, wtl0 = I.wtl0, wta0 = I.wta0, wtal = I.wtal, wtgq = I.wtgq, wtalq = I.wtalq,
@@ -836,8 +837,6 @@ ELMK_HD void canflux_end(const Cols& S, const int c, const CanopyIter& I)
   C1(qflx_ev_soil) = forc_rho * wtgq * delq_soil;
   const double delq_h2osfc = wtalq * C1(qg_h2osfc) - wtlq0 * qsatl - wtaq0 * forc_q;
   C1(qflx_ev_h2osfc) = forc_rho * wtgq * delq_h2osfc;
-  const double p_temp12m = mo_scalar_profile(2.0 + I.z0mv, I.p_obu, I.z0mv, true);
-  const double p_temp22m = p_temp12m;   // same roughness length for heat and moisture
   const double t_ref2m = thm + I.p_temp1 * I.dth * (1.0 / p_temp12m - 1.0 / I.p_temp1);
   const double q_ref2m = forc_q + I.p_temp2 * I.dqh * (1.0 / p_temp22m - 1.0 / I.p_temp2);
   double e2m, de2m, qsat2m, dqsat2m;
@@ -860,11 +859,20 @@ ELMK_HD void canflux_end(const Cols& S, const int c, const CanopyIter& I)
   if (I.err) C1(errmask) |= I.err;
 }
 
+// the 2 m relations the reference evaluates in every pass (friction_velocity_temp2m / _humidity2m with z0h = z0q = z0m),
+// from the Obukhov length the last pass started with
+ELMK_HD double canflux_temp12m(const CanopyIter& I) { return mo_scalar_profile(2.0 + I.z0mv, I.p_obu, I.z0mv, true); }
+ELMK_HD void canflux_end(const Cols& S, const int c, const CanopyIter& I)
+{
+  const double p_temp12m = canflux_temp12m(I);
+  canflux_end_with(S, c, I, p_temp12m, p_temp12m);   // same roughness length for heat and moisture
+}
+
 ELMK_HD void column_canopy_fluxes(const Cols& S, const Tables& T, const StepArgs& A, const int c)
 {
   const PsnPft P = load_psn_pft(S, c);
   CanopyIter I;
-  if (!canflux_begin(S, T, A, P, c, I)) return;
+  if (!canflux_begin(S, T.vtype, A, P, c, I)) return;
   const PsnColumn PC = psn_column(P, I.t10, I.pbot, I.thm, I.forc_po2, I.dayl_factor);
 #pragma unroll 1
   while (!canflux_iterate(P, PC, I)) {

@@ -350,7 +350,10 @@ int elmk_math_eval(elmk_handle h, int fn, int64_t n, const double* x, const doub
 #define ELMK_FN_BGF_INITIALIZE_FLUX 18     /* bareground_fluxes::initialize_flux      bareground_fluxes_impl.hh:7   20 slots */
 #define ELMK_FN_BGF_STABILITY_ITERATION 19 /* bareground_fluxes::stability_iteration  :30   22 slots */
 #define ELMK_FN_BGF_COMPUTE_FLUX 20        /* bareground_fluxes::compute_flux         :82   56 slots */
-#define ELMK_FN_COUNT 21
+#define ELMK_FN_CF_INITIALIZE_FLUX 21     /* canopy_fluxes::initialize_flux      canopy_fluxes_impl.hh:95  217 slots */
+#define ELMK_FN_CF_STABILITY_ITERATION 22 /* canopy_fluxes::stability_iteration  :187  127 slots (slot 0: Land.vtype, psn_pft as its 27 members) */
+#define ELMK_FN_CF_COMPUTE_FLUX 23        /* canopy_fluxes::compute_flux         :456   83 slots */
+#define ELMK_FN_COUNT 24
 int elmk_fn_call(int device, int fn, double* args, int64_t nargs);
 
 /* raw device pointer + level stride of a field (for zero-copy interop with torch tensors) */

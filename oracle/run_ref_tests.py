@@ -20,7 +20,19 @@ def run_all():
                   "failed": len(re.findall(r"passes: false", txt)), "lines": txt.count("\n")}
     return out
 
+def write_canflux_golden():
+    """tests/golden/ref_test_CanFlux_failing_comparisons.txt: the 73 comparisons (variable, step) that the reference's own
+    implementation fails against the Fortran dump at the test's 1e-15 - the GPU run of the same test through
+    include/elm/canopy_fluxes.h must fail exactly these and pass all others."""
+    r = subprocess.run([str(HERE / "_ref" / "test_CanFlux")], capture_output=True, text=True)
+    lines = sorted(l for l in r.stdout.splitlines() if "passes: false" in l)
+    (HERE.parent / "tests" / "golden" / "ref_test_CanFlux_failing_comparisons.txt").write_text("\n".join(lines) + "\n")
+    return len(lines)
+
+
 if __name__ == "__main__":
     build_ref.build_tests()
     for t, v in run_all().items():
         print(t, v)
+    if "--golden" in sys.argv:
+        print("CanFlux failing comparisons written:", write_canflux_golden())

@@ -37,7 +37,13 @@ REF_TESTS = {"CanHydro": ["CanopyHydrology_IN.txt", "CanopyHydrology_OUT.txt"],
              "SurfRad": ["SurfaceRadiation_IN.txt", "SurfaceRadiation_OUT.txt"],
              "CanSunShade": ["CanopySunShadeFractions_IN.txt", "CanopySunShadeFractions_OUT.txt"],
              "CanTemp": ["CanopyTemperature_IN.txt", "CanopyTemperature_OUT.txt"],
-             "BGFlux": ["BareGroundFluxes_IN.txt", "BareGroundFluxes_OUT.txt"]}
+             "BGFlux": ["BareGroundFluxes_IN.txt", "BareGroundFluxes_OUT.txt"],
+             "CanFlux": ["CanopyFluxes_IN.txt", "CanopyFluxes_OUT.txt"]}
+# test_CanFlux also reads the PFT constants of clm_params_c180524.nc through ELM::IO::read_pft_var: served, as in the
+# oracle's build of the same test, by oracle/shim_serial/netcdf.h from the text dumps of oracle/dump_params.py (copied
+# next to the binary), with the zero-filling operator new of oracle/shim_serial/zero_new.cc (the test reads scratch
+# arrays it never initialises)
+NEEDS_PARAMS = {"CanFlux"}
 
 
 def build_reference_tests(force=False):
@@ -55,8 +61,21 @@ def build_reference_tests(force=False):
         if not force and exe.exists() and all(s.stat().st_mtime <= exe.stat().st_mtime for s in deps):
             built.append(exe)
             continue
-        cmd = ["g++", "-std=c++17", "-O1", "-w", '-DTEST_DATA_DIR="data/"', f"-I{ROOT}/include/elm", f"-I{ROOT}/include",
-               f"-I{REF}/src/data", f"-I{REF}/src/utils", str(REF / f"test/test_{t}.cc"), str(REF / "src/utils/read_test_input.cc"),
+        extra, inc, tail_inc = [], [], []
+        if t in NEEDS_PARAMS:
+            sys.path.insert(0, str(ROOT / "oracle"))
+            import dump_params
+            if not (dump_params.OUT / "pftname.txt").exists():
+                dump_params.dump()
+            shutil.copytree(dump_params.OUT, out / "data" / "clm_params", dirs_exist_ok=True)
+            inc = [f"-I{ROOT}/oracle/shim_serial", '-DELMK_NC_DUMP_DEFAULT="data/clm_params"']
+            # (test_CanFlux includes data_types.hh -> elm_state.h, whose data headers pull snow_snicar.h, atm_physics.h
+            #  and phenology_physics.h for constants and data-manager functors: those resolve to the reference's
+            #  src/physics, placed AFTER include/elm - every function the test calls resolves to include/elm)
+            tail_inc = [f"-I{REF}/src/physics"]
+            extra = [str(REF / "src/utils/read_input.cc"), str(REF / "src/utils/utils.cc"), str(ROOT / "oracle/shim_serial/zero_new.cc")]
+        cmd = ["g++", "-std=c++17", "-O1", "-w", '-DTEST_DATA_DIR="data/"'] + inc + [f"-I{ROOT}/include/elm", f"-I{ROOT}/include",
+               f"-I{REF}/src/data", f"-I{REF}/src/utils"] + tail_inc + [str(REF / f"test/test_{t}.cc"), str(REF / "src/utils/read_test_input.cc")] + extra + [
                f"-L{ROOT}/elmkernels_b200", "-lelmk_b200", "-Wl,-rpath,$ORIGIN/../../../elmkernels_b200", "-o", str(exe)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

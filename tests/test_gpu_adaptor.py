@@ -79,7 +79,7 @@ def test_adaptor_advances_the_reference_state_on_the_gpu(checker, cuda_lib, para
 
 
 @pytest.mark.parametrize("name,checks", [("CanHydro", 1824), ("SurfRad", 1440), ("CanSunShade", 768), ("CanTemp", 2784),
-                                         ("BGFlux", 2064)])
+                                         ("BGFlux", 2064), ("CanFlux", 8560)])
 def test_reference_unit_test_runs_on_the_gpu_through_the_function_api(name, checks):
     """The reference's own test/test_<name>.cc, compiled unchanged against include/elm/ (the library-level ELM::<ns>::<fn>
     API of this repository in place of the reference's src/physics) and linked against libelmk_b200.so: every physics
@@ -91,6 +91,12 @@ def test_reference_unit_test_runs_on_the_gpu_through_the_function_api(name, chec
     r = subprocess.run([exe], capture_output=True, text=True, cwd=os.path.dirname(exe))
     assert r.returncode == 0, r.stderr[-2000:]
     passed = len(re.findall(r"passes: true", r.stdout))
-    failed = [l for l in r.stdout.splitlines() if "passes: false" in l]
-    assert not failed, failed[:10]
+    failed = sorted(l for l in r.stdout.splitlines() if "passes: false" in l)
+    # test_CanFlux: the reference's own implementation misses the Fortran values at the test's 1e-15 in 73 of its 8633
+    # comparisons (by up to 3.4e-12); the GPU run must miss exactly the same ones (tests/golden, written by
+    # oracle/run_ref_tests.py --golden from the reference's own run)
+    expected = []
+    if name == "CanFlux":
+        expected = open(os.path.join(ROOT, "tests", "golden", "ref_test_CanFlux_failing_comparisons.txt")).read().splitlines()
+    assert failed == expected, [l for l in failed if l not in expected][:10]
     assert passed == checks, (passed, checks)
