@@ -263,10 +263,12 @@ int elmk_init_timestep(elmk_handle h, int reset_forc_hgt);
  *      handle's stream: replaces the 11 wrapper calls of ELMInterface::advance ---- */
 int elmk_step(elmk_handle h, double dtime, double dayl, double max_dayl, uint32_t group_mask);
 
-/* Launch plan of elmk_step.  ELMK_PLAN_FUSED (default): the production plan - fused launches, the SNICAR kernel with
- * one lane per (column, flux type, band), the re-packed CanopyFluxes iteration.  ELMK_PLAN_SPLIT: one launch per kernel
- * group with one thread per column, the reference's wrapper granularity (23 parallel_for -> 11 launches); the two plans
- * give identical bits (tests/test_gpu_parity.py).  Takes effect from the next elmk_step. */
+/* Launch plan of elmk_step.  ELMK_PLAN_FUSED (default): the production plan - the SNICAR kernel (a warp solves one
+ * band of one flux type for 32 sunlit snow columns), bare-ground fluxes on compacted columns, the re-packed
+ * CanopyFluxes iteration, snow hydrology + surface fluxes + conservation in one launch; the closed-form groups as
+ * launches of their own (measured faster than fused).  ELMK_PLAN_SPLIT: one plain launch per kernel group with one
+ * thread per column, the reference's wrapper granularity (23 parallel_for -> 11 launches); the two plans give
+ * identical bits (tests/test_gpu_parity.py).  Takes effect from the next elmk_step. */
 #define ELMK_PLAN_FUSED 0
 #define ELMK_PLAN_SPLIT 1
 int elmk_set_plan(elmk_handle h, int plan);
