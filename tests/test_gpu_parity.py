@@ -166,6 +166,42 @@ def test_large_ensemble_properties(cuda_lib, params):
     assert np.isfinite(t).all() and t[:, 5:].min() > 150.0 and t.max() < 350.0
 
 
+def test_full_size_handle_is_periodic_in_its_tiles(cuda_lib, params):
+    """BASELINE.json config 5 at its per-GPU size, ragged: 2,097,152 + 77 columns built as eight copies (and a head) of
+    one 262,144-column ensemble.  Columns are independent, so after three full steps of the production plan every tile
+    of the big handle must hold, bit for bit, what a 262,144-column handle of its own holds - whatever block, SNICAR /
+    bare-ground window or queue position a column lands in at the large size.  (The 262,144-column results themselves
+    are tied to the oracle by the tests above and, at full size, by bench.py's verification.)"""
+    m, tiles, tail = 1 << 18, 8, 77
+    n = m * tiles + tail
+    cfg = ensemble.EnsembleConfig(ncols=m, seed=123, soil_temp_spread=6.0, h2osfc_fraction=0.1)
+    st = ensemble.make_state(cfg, params, cuda_lib.fields)
+    F = ensemble.Forcing(m, seed=9, night_fraction=0.3)
+    small = cuda_lib.columns(m)
+    small.set_tables(params)
+    small.upload_state(st)
+    big = cuda_lib.columns(n)
+    big.set_tables(params)
+    for t in range(tiles):
+        big.upload_state(st, col0=t * m)
+    big.upload_state({k: v[:tail] for k, v in st.items()}, col0=tiles * m)
+    for step in range(3):
+        f = F.at(step, {k: small.download(k) for k in parity.FORCING_STATE})
+        small.upload_state(f)
+        for t in range(tiles):
+            big.upload_state(f, col0=t * m)
+        big.upload_state({k: v[:tail] for k, v in f.items()}, col0=tiles * m)
+        for c in (small, big):
+            c.init_timestep(True)
+            c.step()
+    assert small.errors() == (0, -1) and big.errors() == (0, -1)
+    for k in cuda_lib.field_names:
+        want = small.download(k)
+        for t in (0, 3, tiles - 1):
+            assert not parity.mismatch(want, big.download(k, col0=t * m, n=m)).any(), (k, t)
+        assert not parity.mismatch(want[:tail], big.download(k, col0=tiles * m, n=tail)).any(), (k, "tail")
+
+
 # ELM's Fortran is another implementation (different compiler, different libm): the reference's own tests accept
 # it at 1e-15 .. 1e-10 depending on the variable.  Two comparisons: the CUDA replay against the checker's replay of the
 # same records, bit for bit; and against the Fortran values at the tolerances of BASELINE.json.
