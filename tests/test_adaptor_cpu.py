@@ -23,3 +23,17 @@ def test_adaptor_compiles_against_reference_state_and_round_trips(port_lib, tmp_
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 mismatches" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present")
+def test_reference_unit_tests_compile_unchanged_against_the_function_api():
+    """Six of the reference's seven test/test_*.cc build from where they lie with include/elm in place of the
+    reference's src/physics (tests/adaptor/build_adaptor.py); they run on the GPU in tests/test_gpu_adaptor.py."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "adaptor"))
+    import build_adaptor
+    import __graft_entry__ as ge
+    ge.build_product()
+    built = [os.path.basename(str(p)) for p in build_adaptor.build_reference_tests()]
+    assert sorted(built) == ["ref_test_BGFlux", "ref_test_CanFlux", "ref_test_CanHydro", "ref_test_CanSunShade",
+                             "ref_test_CanTemp", "ref_test_SurfRad"]
