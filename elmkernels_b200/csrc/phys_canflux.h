@@ -523,22 +523,32 @@ ELMK_HD bool canflux_begin(const Cols& S, const int vtype, const StepArgs& A, co
   // root-zone moisture stress: effective porosity, liquid volume, per-layer resistance
   double btran = 0.0;
   double rootr[NLEVGRND];
+  // The inputs of layer i + 1 are requested before the power function of layer i is called: the loop is rolled and the
+  // call is a barrier for the compiler, so without this a warp has one layer's loads in flight at a time (set-up launch
+  // 1.62 -> 1.29 ms).
+  double n_watsat = C2(watsat, 0), n_dz = C2(dz, NLEVSNO), n_ice = C2(h2osoi_ice, NLEVSNO), n_liq = C2(h2osoi_liq, NLEVSNO),
+         n_t = C2(t_soisno, NLEVSNO), n_sucsat = C2(sucsat, 0), n_bsw = C2(bsw, 0), n_rootfr = C2(rootfr, 0);
 #pragma unroll 1
   for (int i = 0; i < NLEVGRND; ++i) {
-    const int k = NLEVSNO + i;
-    const double watsat = C2(watsat, i), dzk = C2(dz, k);
-    const double vol_ice = dmin(watsat, (C2(h2osoi_ice, k) / (DENICE * dzk)));
+    const double watsat = n_watsat, dzk = n_dz, ice_k = n_ice, liq_k = n_liq, t_k = n_t, sucsat_i = n_sucsat, bsw_i = n_bsw,
+                 rootfr_i = n_rootfr;
+    if (i + 1 < NLEVGRND) {
+      const int k1 = NLEVSNO + i + 1;
+      n_watsat = C2(watsat, i + 1); n_dz = C2(dz, k1); n_ice = C2(h2osoi_ice, k1); n_liq = C2(h2osoi_liq, k1);
+      n_t = C2(t_soisno, k1); n_sucsat = C2(sucsat, i + 1); n_bsw = C2(bsw, i + 1); n_rootfr = C2(rootfr, i + 1);
+    }
+    const double vol_ice = dmin(watsat, (ice_k / (DENICE * dzk)));
     const double eff_por = watsat - vol_ice;
     C2(eff_porosity, i) = eff_por;
-    const double liqvol = dmin(eff_por, (C2(h2osoi_liq, k) / (dzk * DENH2O)));
-    if (liqvol <= 0.0 || C2(t_soisno, k) <= TFRZ + P.tc_stress) {
+    const double liqvol = dmin(eff_por, (liq_k / (dzk * DENH2O)));
+    if (liqvol <= 0.0 || t_k <= TFRZ + P.tc_stress) {
       rootr[i] = 0.0;
     } else {
       const double s_node = dmax(liqvol / eff_por, 0.01);
-      double smp_node = -C2(sucsat, i) * m_pow(s_node, (-C2(bsw, i)));
+      double smp_node = -sucsat_i * m_pow(s_node, (-bsw_i));
       smp_node = dmax(P.smpsc, smp_node);
       const double rresis = dmin((eff_por / watsat) * (smp_node - P.smpsc) / (P.smpso - P.smpsc), 1.0);
-      rootr[i] = C2(rootfr, i) * rresis;
+      rootr[i] = rootfr_i * rresis;
       btran += dmax(rootr[i], 0.0);
     }
   }
