@@ -314,16 +314,23 @@ __device__ __forceinline__ void canflux_store(const CanfluxQueue& Q, const int c
 {
   double* p = Q.scratch + c;
   long long k = 0;
+  // `all` (set-up launch): constants + the carried values that do not start at zero; else (a converged column of
+  // the iteration kernel): every carried value
 #define X(n) if (all) p[k * Q.np] = I.n; ++k;
   ELMK_CANFLUX_CONST(X)
 #undef X
 #define X(n) p[k * Q.np] = I.n; ++k;
-  ELMK_CANFLUX_CARRIED(X)
+  ELMK_CANFLUX_CARRIED_SET(X)
+#undef X
+#define X(n) if (!all) p[k * Q.np] = I.n; ++k;
+  ELMK_CANFLUX_CARRIED_ZERO(X)
 #undef X
 #define X(n) p[k * Q.np] = (double)I.n; ++k;
   ELMK_CANFLUX_INT(X)
 #undef X
 }
+// FRESH: the column comes from the set-up launch (the values that start at zero are not in the scratch)
+template <bool FRESH = false>
 __device__ __forceinline__ void canflux_load(const Cols& S, const CanfluxQueue& Q, const int c, CanopyIter& I)
 {
 #define X(n, e) I.n = e;
@@ -333,7 +340,10 @@ __device__ __forceinline__ void canflux_load(const Cols& S, const CanfluxQueue& 
   long long k = 0;
 #define X(n) I.n = p[k * Q.np]; ++k;
   ELMK_CANFLUX_CONST(X)
-  ELMK_CANFLUX_CARRIED(X)
+  ELMK_CANFLUX_CARRIED_SET(X)
+#undef X
+#define X(n) I.n = FRESH ? 0.0 : p[k * Q.np]; ++k;
+  ELMK_CANFLUX_CARRIED_ZERO(X)
 #undef X
 #define X(n) I.n = (int)p[k * Q.np]; ++k;
   ELMK_CANFLUX_INT(X)
@@ -390,7 +400,7 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
         const int q = base + __popc(need & below);
         if (q < total) {
           c = (q < nday) ? Q.list[q] : Q.list[Q.np - 1 - (q - nday)];
-          canflux_load(S, Q, c, I);
+          canflux_load<true>(S, Q, c, I);
           P = load_psn_pft(S, c);
           PC = psn_column(P, I.t10, I.pbot, I.thm, I.forc_po2, I.dayl_factor);
           have = true;

@@ -464,10 +464,15 @@ ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const PsnColumn& C, cons
 #define ELMK_CANFLUX_CONST(X)                                                                                     \
   X(forc_po2) X(forc_pco2) X(forc_rho) X(dayl_factor) X(air) X(bir) X(cir) X(ur) X(zldis) X(lw_grnd) X(t_snotop)  \
   X(dtime)
-#define ELMK_CANFLUX_CARRIED(X)                                                                                   \
-  X(btran) X(t_veg) X(el) X(qsatl) X(qsatldT) X(taf) X(qaf) X(dth) X(dqh) X(delq) X(um) X(obu) X(obuold) X(del)  \
-  X(efeb) X(qflx_tran_veg) X(qflx_evap_veg) X(eflx_sh_veg) X(wtg) X(wtl0) X(wta0) X(wtal) X(wtgq) X(wtalq)       \
-  X(wtlq0) X(wtaq0) X(tlbef) X(dt_veg) X(p_ustar) X(p_temp1) X(p_temp2) X(p_obu)
+// (CARRIED_SET: given a value by canflux_begin; CARRIED_ZERO: start the iteration at zero - the set-up launch does not
+//  store them and a lane of the iteration kernel that takes a new column does not load them)
+#define ELMK_CANFLUX_CARRIED_SET(X)                                                                               \
+  X(btran) X(t_veg) X(el) X(qsatl) X(qsatldT) X(taf) X(qaf) X(dth) X(dqh) X(delq) X(um) X(obu) X(qflx_tran_veg)   \
+  X(qflx_evap_veg) X(eflx_sh_veg)
+#define ELMK_CANFLUX_CARRIED_ZERO(X)                                                                              \
+  X(obuold) X(del) X(efeb) X(wtg) X(wtl0) X(wta0) X(wtal) X(wtgq) X(wtalq) X(wtlq0) X(wtaq0) X(tlbef) X(dt_veg)  \
+  X(p_ustar) X(p_temp1) X(p_temp2) X(p_obu)
+#define ELMK_CANFLUX_CARRIED(X) ELMK_CANFLUX_CARRIED_SET(X) ELMK_CANFLUX_CARRIED_ZERO(X)
 #define ELMK_CANFLUX_INT(X) X(nrad) X(veg) X(soybean) X(itlef) X(nmozsgn) X(err)
 
 struct CanopyIter {
