@@ -378,10 +378,28 @@ __global__ void __launch_bounds__(kBlock, 8) k_canflux_begin(const Cols S, const
   if (cls == 1) Q.list[Q.np - 1 - (base_night + __popc(night & below))] = c;
 }
 
-template <int BLOCK, bool LOCKSTEP>
+// "any thread of my lock-step group still owns a column": a named barrier over GROUP threads (warps of one group are
+// consecutive), GROUP == 0: the whole block
+template <int GROUP>
+__device__ __forceinline__ bool lockstep_any(const bool have)
+{
+  if (GROUP == 0) return __syncthreads_or(have);
+  unsigned r;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+               : "=r"(r)
+               : "r"((unsigned)have), "r"(1u + threadIdx.x / (GROUP ? GROUP : 1)), "r"((unsigned)GROUP)
+               : "memory");
+  return r != 0;
+}
+
+template <int BLOCK, bool LOCKSTEP, int GROUP = 0>
 __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const CanfluxQueue Q)
 {
   const int nday = Q.counters[0], total = nday + Q.counters[1];
+#ifdef ELMK_ITER_TRACE
+  long long t_start = clock64(), t_exhaust = 0;
+  int rounds = 0, rounds_at_exhaust = 0;
+#endif
   const unsigned lane = threadIdx.x & 31u;
   const unsigned below = (1u << lane) - 1u;
   bool have = false;
@@ -398,6 +416,9 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
       base = __shfl_sync(0xffffffffu, base, 0);
       if (!have) {
         const int q = base + __popc(need & below);
+#ifdef ELMK_ITER_TRACE
+        if (q >= total && t_exhaust == 0) { t_exhaust = clock64(); rounds_at_exhaust = rounds; }
+#endif
         if (q < total) {
           c = (q < nday) ? Q.list[q] : Q.list[Q.np - 1 - (q - nday)];
           canflux_load<true>(S, Q, c, I);
@@ -413,10 +434,13 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
       // instruction fetch serves the others (ncu: "no_instruction" was the top stall reason; measured
       // 7.4 ms -> 4.9 ms per 512k columns with 384-thread lock-step blocks; more barriers inside the pass
       // cost more than they saved).
-      if (!__syncthreads_or(have)) break;
+      if (!lockstep_any<GROUP>(have)) break;
     } else {
       if (!__any_sync(0xffffffffu, have)) break;
     }
+#ifdef ELMK_ITER_TRACE
+    rounds += 1;
+#endif
     // ---- one pass for every lane that owns a column ----
     if (have) {
       if (canflux_iterate(P, PC, I)) {
@@ -425,6 +449,20 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
       }
     }
   }
+#ifdef ELMK_ITER_TRACE
+  {
+    __shared__ long long s_ex;
+    __shared__ int s_rex;
+    if (threadIdx.x == 0) { s_ex = 0x7fffffffffffffffll; s_rex = 0x7fffffff; }
+    __syncthreads();
+    if (t_exhaust) { atomicMin(&s_ex, t_exhaust - t_start); atomicMin(&s_rex, rounds_at_exhaust); }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+      long long* tr = reinterpret_cast<long long*>(Q.counters + 4) + 4 * blockIdx.x;
+      tr[0] = s_ex; tr[1] = clock64() - t_start; tr[2] = s_rex; tr[3] = rounds;
+    }
+  }
+#endif
 }
 
 __global__ void __launch_bounds__(kBlock) k_canflux_end(const Cols S, const CanfluxQueue Q)
@@ -1169,7 +1207,7 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
   if (!c->cq.scratch) {
     CU(cudaMalloc(&c->cq.scratch, sizeof(double) * (size_t)kCanfluxDoubles * c->np));
     CU(cudaMalloc(&c->cq.list, sizeof(int) * (size_t)c->np));
-    CU(cudaMalloc(&c->cq.counters, sizeof(int) * 4));
+    CU(cudaMalloc(&c->cq.counters, sizeof(int) * 4 + sizeof(long long) * 4 * 1024));
     c->cq.np = c->np;
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->iterate_fn, c->iterate_block, 0));
@@ -1333,6 +1371,9 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
       if (nb == 128) c->iterate_fn = ls ? k_canflux_iterate<128, true> : k_canflux_iterate<128, false>;
       else if (nb == 256) c->iterate_fn = ls ? k_canflux_iterate<256, true> : k_canflux_iterate<256, false>;
       else if (nb == 512) c->iterate_fn = k_canflux_iterate<512, true>;
+      else if (nb == 384 && std::strstr(ib, "g64")) c->iterate_fn = k_canflux_iterate<384, true, 64>;
+      else if (nb == 384 && std::strstr(ib, "g128")) c->iterate_fn = k_canflux_iterate<384, true, 128>;
+      else if (nb == 384 && std::strstr(ib, "g192")) c->iterate_fn = k_canflux_iterate<384, true, 192>;
       else { c->iterate_block = kIterBlock; c->iterate_fn = ls ? k_canflux_iterate<384, true> : k_canflux_iterate<384, false>; }
     }
     // launches of the fused plan found by the set of groups they cover

@@ -119,3 +119,20 @@ def test_constant_divisor_sequence_equals_ieee_division(tmp_path):
     r = subprocess.run([str(exe), "-n1500000"] + lits, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "0 mismatches" in r.stdout.splitlines()[-1]
+
+
+def test_evict_first_hint_only_on_plain_global_accesses_of_the_listed_kernels():
+    """The .cs (evict-first) hint of the STREAM table: loads / stores by mode, never on .nc, local, shared or param
+    accesses, and only inside entries the table names."""
+    ld, st = "\tld.global.f64 \t%fd1, [%rd3];", "\t@%p3 st.global.f64 \t[%rd3+8], %fd2;"
+    assert R._stream(ld, "ls") == "\tld.global.cs.f64 \t%fd1, [%rd3];"
+    assert R._stream(st, "ls") == "\t@%p3 st.global.cs.f64 \t[%rd3+8], %fd2;"
+    assert R._stream(ld, "s") == ld and R._stream(st, "l") == st
+    assert R._stream("\tld.global.v2.f64 \t{%fd1, %fd2}, [%rd3];") == "\tld.global.cs.v2.f64 \t{%fd1, %fd2}, [%rd3];"
+    for other in ("\tld.global.nc.f64 \t%fd1, [%rd3];", "\tld.local.f64 \t%fd1, [%rd3];", "\tst.shared.f64 \t[%r3], %fd1;",
+                  "\tld.param.f64 \t%fd1, [retval0];", "\tatom.global.add.u32 \t%r1, [%rd1], %r2;"):
+        assert R._stream(other) == other
+    names = [r for r, _ in R.STREAM]
+    assert any("k_canflux_iterate" in n for n in names)
+    for rx, mode in R._stream_table():
+        assert set(mode) <= {"l", "s"} and not rx.search("_ZN4elmk5m_divEdd")
