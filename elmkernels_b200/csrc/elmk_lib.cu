@@ -131,6 +131,60 @@ __global__ void __launch_bounds__(kBlock, MINBLOCKS) k_groups_occ(const Cols S, 
   run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c, c < S.ncols);
 }
 
+// ---- (experiment, development builds) one thread per column, the columns of a block re-ordered by work class ----------
+// The snow state machine only does work for columns that carry snow layers, and how much depends on the layer count; in
+// column order a warp holds a mixture (ncu: 15.9 of 32 lanes active in the snow launch).  The block's 128 columns are
+// counting-sorted (stable) by class in shared memory and thread t takes the t-th column of that order: warps become
+// homogeneous, while every (field, level) access of the block still falls into the same 1 KB row segment it reads in
+// column order - the same sectors reach the SM, only their assignment to warps changes.  KEY: 1 = snl (0..5),
+// 2 = snl > 0, 3 = exposed vegetation.  Padding columns sort last.  Measured and not adopted (profiles/r2_experiments.md:
+// snow launch 3.0 -> 3.9 / 3.6 ms with keys 1 / 2): the 8-byte accesses of a class-ordered warp touch up to 32 sectors
+// instead of 8, and these launches are bound by that load / store path, not by idle lanes.
+#ifdef ELMK_DEV_VARIANTS
+template <int KEY>
+__device__ __forceinline__ int work_class(const Cols& S, const int c)
+{
+  if (KEY == 1) return S.snl[c];
+  if (KEY == 2) return S.snl[c] > 0 ? 0 : 1;
+  return S.frac_veg_nosno[c] != 0 ? 0 : 1;
+}
+template <int KEY>
+__device__ __forceinline__ int block_order_by_class(const Cols& S)
+{
+  constexpr int NCLS = 7, NW = kBlock / 32;
+  __shared__ unsigned char perm[kBlock];
+  __shared__ unsigned char cnt[NW][NCLS];
+  const int t = threadIdx.x, w = t >> 5;
+  const unsigned lane = t & 31u, below = (1u << lane) - 1u;
+  const int c = blockIdx.x * kBlock + t;
+  const int cls = (c < S.ncols) ? work_class<KEY>(S, c) : NCLS - 1;
+  unsigned mine = 0;
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k) {
+    const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+    if (lane == 0) cnt[w][k] = (unsigned char)__popc(m);
+    if (cls == k) mine = m;
+  }
+  __syncthreads();
+  int pos = __popc(mine & below);
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k)
+#pragma unroll
+    for (int v = 0; v < NW; ++v)
+      if (k < cls || (k == cls && v < w)) pos += cnt[v][k];
+  perm[pos] = (unsigned char)t;
+  __syncthreads();
+  return blockIdx.x * kBlock + perm[t];
+}
+template <uint32_t MASK, int MINBLOCKS, int KEY>
+__global__ void __launch_bounds__(kBlock, MINBLOCKS) k_groups_classed(const Cols S, const Tables* __restrict__ Tp, const StepArgs A)
+{
+  const int c = block_order_by_class<KEY>(S);
+  if (!kWholeBlocks<MASK> && c >= S.ncols) return;
+  run_groups<MASK, kWholeBlocks<MASK>>(S, *Tp, A, c, c < S.ncols);
+}
+#endif
+
 // ---- SNICAR with one warp-task per (32 columns, incident-flux type, spectral band) -------------------------------
 // kokkos_albedo_snicar spends ~85 % of its instructions in the snow radiative transfer (round-1 ncu source view), and
 // that part is ten independent solves per column: direct / diffuse x five bands (snow_snicar_impl.hh:313-670), each a
@@ -1387,12 +1441,24 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
     const char* e4 = std::getenv("ELMK_OCC_BG");
     const char* sm = std::getenv("ELMK_SFC_MODE");   // how the closed-form surface groups (a3..a6) are cut into launches
     const char* em = std::getenv("ELMK_END_MODE");   // same for snow hydrology + surface fluxes + conservation
-    if (e0 || e2 || e3 || e4 || sm || em) {
+    if (e0 || e2 || e3 || e4 || sm || em || std::getenv("ELMK_END_CLASSED") || std::getenv("ELMK_SOIL_CLASSED") || std::getenv("ELMK_HYD_CLASSED")) {
       c->plan_own.assign(kFused, kFused + c->plan_len);
       GroupKernel k;
       if (e0 && (k = occ_variant<M_RAD_REST>(std::atoi(e0)))) slot(M_RAD)->fn = k;
       if (e2 && (k = occ_variant<ELMK_G_SOIL_TEMPERATURE>(std::atoi(e2)))) slot(ELMK_G_SOIL_TEMPERATURE)->fn = k;
       if (e3 && (k = occ_variant<M_END>(std::atoi(e3)))) slot(M_END)->fn = k;
+      if (const char* pe = std::getenv("ELMK_END_CLASSED")) {   // snow launch on class-ordered blocks: key, blocks/SM as "16", "26", "18" ...
+        const int v = std::atoi(pe);
+        slot(M_END)->fn = v == 16 ? k_groups_classed<M_END, 6, 1> : v == 26 ? k_groups_classed<M_END, 6, 2> : v == 18 ? k_groups_classed<M_END, 8, 1> : k_groups_classed<M_END, 5, 1>;
+      }
+      if (const char* pe = std::getenv("ELMK_SOIL_CLASSED")) {
+        const int v = std::atoi(pe);
+        slot(ELMK_G_SOIL_TEMPERATURE)->fn = v == 2 ? k_groups_classed<ELMK_G_SOIL_TEMPERATURE, 10, 2> : k_groups_classed<ELMK_G_SOIL_TEMPERATURE, 10, 1>;
+      }
+      if (const char* pe = std::getenv("ELMK_HYD_CLASSED")) {
+        (void)pe;
+        slot(ELMK_G_CANOPY_HYDROLOGY)->fn = k_groups_classed<ELMK_G_CANOPY_HYDROLOGY, 4, 3>;
+      }
       if (e4 && (k = occ_variant<ELMK_G_BAREGROUND_FLUXES>(std::atoi(e4)))) { slot(ELMK_G_BAREGROUND_FLUXES)->fn = k; slot(ELMK_G_BAREGROUND_FLUXES)->cols_per_block = kBlock; }
       if (sm) {
         constexpr uint32_t M_HRT = ELMK_G_CANOPY_HYDROLOGY | ELMK_G_SURFACE_RADIATION | ELMK_G_CANOPY_TEMPERATURE;

@@ -306,8 +306,8 @@ def marked_ranges(csrc_dir: str) -> dict:
 import os as _os
 STREAM = [
     ("k_canflux_iterate", "ls"),       # 7.36 -> 6.95 ms (loads alone 7.14, stores alone 7.32)
-    ("k_groups_occILj1792E", "ls"),    # snow hydrology + surface fluxes + conservation: 3.26 -> 2.99 ms (3.15 / 3.17)
-    ("k_groups_occILj128E", "s"),      # soil temperature re-reads its rows: stores only, 3.59 -> 3.56 ms (loads too: 3.64-3.69)
+    ("k_groups_(occ|classed)ILj1792E", "ls"),    # snow hydrology + surface fluxes + conservation: 3.26 -> 2.99 ms (3.15 / 3.17)
+    ("k_groups_(occ|classed)ILj128E", "s"),      # soil temperature re-reads its rows: stores only, 3.59 -> 3.56 ms (loads too: 3.64-3.69)
 ]
 
 
@@ -322,7 +322,34 @@ _LDST = re.compile(r"^(\s*(?:@!?%p\d+\s+)?)(ld|st)\.global\.((?:v2\.)?(?:f64|[us
 
 
 def _stream(line: str, mode: str = "ls") -> str:
-    return _LDST.sub(lambda m: f"{m.group(1)}{m.group(2)}.global.cs.{m.group(3)}" if m.group(2)[0] in mode else m.group(0), line)
+    """mode letters: l / s = .cs on loads / stores; experiments: N = loads .L1::no_allocate, L / S = loads (with
+    .L1::no_allocate) / stores under an L2 evict-first cache policy (register %elmkpol, see _stream_function)."""
+    m = _LDST.match(line)
+    if not m:
+        return line
+    pre, op, ty = m.group(1), m.group(2), m.group(3)
+    rest = line[m.end():]
+    if op == "ld":
+        if "l" in mode:
+            return f"{pre}ld.global.cs.{ty}{rest}"
+        if "N" in mode:
+            return f"{pre}ld.global.L1::no_allocate.{ty}{rest}"
+        if "L" in mode:
+            return f"{pre}ld.global.L1::no_allocate.L2::cache_hint.{ty}{rest.rstrip().rstrip(';')}, %elmkpol;"
+    else:
+        if "s" in mode:
+            return f"{pre}st.global.cs.{ty}{rest}"
+        if "S" in mode:
+            return f"{pre}st.global.L2::cache_hint.{ty}{rest.rstrip().rstrip(';')}, %elmkpol;"
+    return line
+
+
+def _stream_function(body: list[str], mode: str) -> list[str]:
+    out = [_stream(l, mode) for l in body]
+    if "L" in mode or "S" in mode:
+        k = next(i for i, l in enumerate(out) if l.startswith("{"))
+        out[k + 1:k + 1] = ["\t.reg .b64 %elmkpol;", "\tcreatepolicy.fractional.L2::evict_first.b64 %elmkpol, 1.0;"]
+    return out
 
 
 def rewrite(text: str, ranges_by_name: dict | None = None) -> tuple[str, dict]:
@@ -356,7 +383,7 @@ def rewrite(text: str, ranges_by_name: dict | None = None) -> tuple[str, dict]:
                 body = _rewrite_function(m.group(1), lines[i:k + 1], counter, stats)
                 for rx, mode in stream_table:
                     if rx.search(m.group(1)):
-                        body = [_stream(l, mode) for l in body]
+                        body = _stream_function(body, mode)
                         stats["stream"] = stats.get("stream", 0) + 1
                         break
                 out.extend(body)
