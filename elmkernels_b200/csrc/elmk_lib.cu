@@ -411,11 +411,13 @@ __global__ void __launch_bounds__(kBlock, 8) k_canflux_begin(const Cols S, const
   int cls = 0;   // 0: nothing to iterate, 1: night, 2: day
   if (c < S.ncols) {
     const PsnPft P = load_psn_pft(S, c);
-    CanopyIter I;
-    if (canflux_begin(S, Tp->vtype, A, P, c, I)) {
-      canflux_store(Q, c, I, true);
-      cls = (I.parsun > 0.0 || I.parsha > 0.0) ? 2 : 1;
-    }
+    // Unvegetated columns store zeros: every 32-byte sector of a scratch row is then written whole.  With only the
+    // vegetated lanes storing, the partially written sectors cost a read-modify-write in HBM (ECC granule): 1.21 -> 1.16 ms.
+    CanopyIter I = {};
+    const bool veg = canflux_begin(S, Tp->vtype, A, P, c, I);
+    if (!veg) I = CanopyIter{};
+    canflux_store(Q, c, I, true);
+    if (veg) cls = (I.parsun > 0.0 || I.parsha > 0.0) ? 2 : 1;
   }
   // warp-aggregated append: one atomic per warp and list
   const unsigned lane = threadIdx.x & 31u;
