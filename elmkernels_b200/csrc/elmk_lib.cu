@@ -351,6 +351,8 @@ constexpr int kCanfluxDoubles = 0
 
 // 384-thread lock-step blocks: fastest of 128...768 threads with and without lock-step on B200
 constexpr int kIterBlock = 384;
+// which read-only values of a column in flight the iteration kernel keeps in shared memory (IterView below)
+constexpr int kIterSet = 3;
 // row of the scratch that holds the pass count of a column (itlef) after the launch
 constexpr int kCanfluxItlefRow = 0
 #define X(n) +1
@@ -364,7 +366,8 @@ struct CanfluxQueue {
   long long np;
 };
 
-__device__ __forceinline__ void canflux_store(const CanfluxQueue& Q, const int c, const CanopyIter& I, const bool all)
+template <class IT>
+__device__ __forceinline__ void canflux_store(const CanfluxQueue& Q, const int c, const IT& I, const bool all)
 {
   double* p = Q.scratch + c;
   long long k = 0;
@@ -384,8 +387,8 @@ __device__ __forceinline__ void canflux_store(const CanfluxQueue& Q, const int c
 #undef X
 }
 // FRESH: the column comes from the set-up launch (the values that start at zero are not in the scratch)
-template <bool FRESH = false>
-__device__ __forceinline__ void canflux_load(const Cols& S, const CanfluxQueue& Q, const int c, CanopyIter& I)
+template <bool FRESH = false, class IT = CanopyIter>
+__device__ __forceinline__ void canflux_load(const Cols& S, const CanfluxQueue& Q, const int c, IT& I)
 {
 #define X(n, e) I.n = e;
   ELMK_CANFLUX_STATE(X)
@@ -448,9 +451,78 @@ __device__ __forceinline__ bool lockstep_any(const bool have)
   return r != 0;
 }
 
-template <int BLOCK, bool LOCKSTEP, int GROUP = 0>
+// Read-only values of a column in flight live in shared memory instead of registers / the spilled frame - one record per
+// thread, an ODD number of doubles apart, so that the 64-bit accesses of a half-warp fall into 16 different bank pairs:
+//   SET 1: the per-column constants of the photosynthesis model (PsnPft: 27 PFT values, PsnColumn: 16 derived ones)
+//   SET 2: + the 12 CONST members of the iteration state
+//   SET 3: + the 18 STATE_A members (read once or twice per pass)
+// IterView is the iteration state with those members as references into the record; canflux_iterate / load / store
+// are templates on the state type.
+struct IterConst {
+  PsnPft P;
+  PsnColumn PC;
+};
+constexpr int kIterConstDoubles = (int)(sizeof(IterConst) / sizeof(double));
+enum {
+#define X(n) kIterSlot_##n,
+  ELMK_CANFLUX_CONST(X)
+#undef X
+#define X(n, e) kIterSlot_##n,
+  ELMK_CANFLUX_STATE_A(X)
+#undef X
+  kIterSlotCount
+};
+constexpr int kIterConstSlots = 0
+#define X(n) +1
+    ELMK_CANFLUX_CONST(X)
+#undef X
+    ;
+constexpr int iter_record_doubles(const int set)
+{
+  return (kIterConstDoubles + (set >= 3 ? kIterSlotCount : set == 2 ? kIterConstSlots : 0)) | 1;
+}
+template <bool REF> struct IterSlot { typedef double type; };
+template <> struct IterSlot<true> { typedef double& type; };
+template <int SET>
+struct IterView {
+#define X(n, e) typename IterSlot<(SET >= 3)>::type n;
+  ELMK_CANFLUX_STATE_A(X)
+#undef X
+#define X(n, e) double n;
+  ELMK_CANFLUX_STATE_B(X)
+#undef X
+#define X(n) typename IterSlot<(SET >= 2)>::type n;
+  ELMK_CANFLUX_CONST(X)
+#undef X
+#define X(n) double n;
+  ELMK_CANFLUX_CARRIED(X)
+#undef X
+#define X(n) int n;
+  ELMK_CANFLUX_INT(X)
+#undef X
+  // ro: the thread's slots in shared memory; members that are plain doubles start at zero (`zero` is a local 0.0)
+  __device__ __forceinline__ IterView(double* ro, double& zero)
+      :
+#define X(n, e) n(SET >= 3 ? ro[kIterSlot_##n] : zero),
+        ELMK_CANFLUX_STATE_A(X)
+#undef X
+#define X(n, e) n(0.0),
+        ELMK_CANFLUX_STATE_B(X)
+#undef X
+#define X(n) n(SET >= 2 ? ro[kIterSlot_##n] : zero),
+        ELMK_CANFLUX_CONST(X)
+#undef X
+#define X(n) n(0.0),
+        ELMK_CANFLUX_CARRIED(X)
+#undef X
+        nrad(0), veg(0), soybean(0), itlef(0), nmozsgn(0), err(0)
+  {
+  }
+};
+template <int BLOCK, bool LOCKSTEP, int GROUP = 0, int SET = 1>
 __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const CanfluxQueue Q)
 {
+  extern __shared__ double iter_smem[];
   const int nday = Q.counters[0], total = nday + Q.counters[1];
 #ifdef ELMK_ITER_TRACE
   long long t_start = clock64(), t_exhaust = 0;
@@ -460,9 +532,14 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
   const unsigned below = (1u << lane) - 1u;
   bool have = false;
   int c = 0;
-  PsnPft P = {};
-  PsnColumn PC = {};
-  CanopyIter I = {};
+  PsnPft P_reg = {};
+  PsnColumn PC_reg = {};
+  double* const record = iter_smem + (SET ? threadIdx.x * iter_record_doubles(SET) : 0);
+  IterConst* const mine = reinterpret_cast<IterConst*>(record);
+  PsnPft& P = SET ? mine->P : P_reg;
+  PsnColumn& PC = SET ? mine->PC : PC_reg;
+  double zero = 0.0;
+  IterView<SET> I(record + kIterConstDoubles, zero);
   while (true) {
     // ---- refill idle lanes from the queue ----
     const unsigned need = __ballot_sync(0xffffffffu, !have);
@@ -1115,8 +1192,9 @@ struct Ctx {
   int pf_nrows = 0;
 #endif
   int snicar_blocks = 0;
-  void (*iterate_fn)(const Cols, const CanfluxQueue) = k_canflux_iterate<kIterBlock, true>;
+  void (*iterate_fn)(const Cols, const CanfluxQueue) = k_canflux_iterate<kIterBlock, true, 0, kIterSet>;
   int iterate_block = kIterBlock;
+  int iterate_smem = kIterBlock * iter_record_doubles(kIterSet) * (int)sizeof(double);   // dynamic shared memory of the iteration kernel: one record per thread
   unsigned int* d_err = nullptr;   // [0] any, then long long first at +8
   double* d_diag = nullptr;
   void* h_pinned = nullptr;        // small pinned buffer for scalar read-backs
@@ -1266,7 +1344,8 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
     CU(cudaMalloc(&c->cq.counters, sizeof(int) * 4 + sizeof(long long) * 4 * 1024));
     c->cq.np = c->np;
     int per_sm = 0, sms = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->iterate_fn, c->iterate_block, 0));
+    if (c->iterate_smem) CU(cudaFuncSetAttribute(c->iterate_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->iterate_smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->iterate_fn, c->iterate_block, c->iterate_smem));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     c->iterate_blocks = std::max(1, per_sm) * std::max(1, sms);
   }
@@ -1286,7 +1365,7 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
   k_canflux_begin<<<grid, kBlock, 0, c->stream>>>(c->cols, c->d_tables, A, c->cq);
   if (split) done(tb), mark(ti, "canopy_fluxes:iterate");
   const unsigned persistent = (unsigned)std::min<int64_t>(c->iterate_blocks, (c->ncols + kBlock - 1) / kBlock);
-  c->iterate_fn<<<persistent, c->iterate_block, 0, c->stream>>>(c->cols, c->cq);
+  c->iterate_fn<<<persistent, c->iterate_block, c->iterate_smem, c->stream>>>(c->cols, c->cq);
   if (split) done(ti), mark(te, "canopy_fluxes:end");
   k_canflux_end<<<grid, kBlock, 0, c->stream>>>(c->cols, c->cq);
   if (split) done(te);
@@ -1424,13 +1503,20 @@ int elmk_create(elmk_handle* out, int device, int64_t ncols) {
       const int nb = std::atoi(ib);
       const bool ls = std::strchr(ib, 'l') != nullptr;
       c->iterate_block = nb;
-      if (nb == 128) c->iterate_fn = ls ? k_canflux_iterate<128, true> : k_canflux_iterate<128, false>;
-      else if (nb == 256) c->iterate_fn = ls ? k_canflux_iterate<256, true> : k_canflux_iterate<256, false>;
-      else if (nb == 512) c->iterate_fn = k_canflux_iterate<512, true>;
-      else if (nb == 384 && std::strstr(ib, "g64")) c->iterate_fn = k_canflux_iterate<384, true, 64>;
-      else if (nb == 384 && std::strstr(ib, "g128")) c->iterate_fn = k_canflux_iterate<384, true, 128>;
-      else if (nb == 384 && std::strstr(ib, "g192")) c->iterate_fn = k_canflux_iterate<384, true, 192>;
-      else { c->iterate_block = kIterBlock; c->iterate_fn = ls ? k_canflux_iterate<384, true> : k_canflux_iterate<384, false>; }
+      c->iterate_smem = 0;
+      const char* mm = std::strchr(ib, 'm');
+      const int set = mm ? (mm[1] >= '1' && mm[1] <= '3' ? mm[1] - '0' : 1) : 0;
+      if (nb == 128) c->iterate_fn = ls ? k_canflux_iterate<128, true, 0, 0> : k_canflux_iterate<128, false, 0, 0>;
+      else if (nb == 256) c->iterate_fn = ls ? k_canflux_iterate<256, true, 0, 0> : k_canflux_iterate<256, false, 0, 0>;
+      else if (nb == 512) c->iterate_fn = k_canflux_iterate<512, true, 0, 0>;
+      else if (nb == 384 && set) {
+        c->iterate_fn = set == 3 ? k_canflux_iterate<384, true, 0, 3> : set == 2 ? k_canflux_iterate<384, true, 0, 2> : k_canflux_iterate<384, true, 0, 1>;
+        c->iterate_smem = 384 * iter_record_doubles(set) * (int)sizeof(double);
+      }
+      else if (nb == 384 && std::strstr(ib, "g64")) c->iterate_fn = k_canflux_iterate<384, true, 64, 0>;
+      else if (nb == 384 && std::strstr(ib, "g128")) c->iterate_fn = k_canflux_iterate<384, true, 128, 0>;
+      else if (nb == 384 && std::strstr(ib, "g192")) c->iterate_fn = k_canflux_iterate<384, true, 192, 0>;
+      else { c->iterate_block = kIterBlock; c->iterate_fn = ls ? k_canflux_iterate<384, true, 0, 0> : k_canflux_iterate<384, false, 0, 0>; }
     }
     // launches of the fused plan found by the set of groups they cover
     auto slot = [&](uint32_t mask) -> Launch* {

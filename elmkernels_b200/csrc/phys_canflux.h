@@ -451,16 +451,19 @@ ELMK_HD double psn_stomatal_resistance(const PsnPft& P, const PsnColumn& C, cons
 // doubles of the iteration state.  STATE: plain copies of per-column state fields that CanopyFluxes does not change
 // before its last phase (the re-packed kernels re-read them from the state instead of carrying them through
 // scratch memory); CONST: values derived once in canflux_begin; CARRIED: the loop-carried values.
-#define ELMK_CANFLUX_STATE(X)                                                                                     \
+// (STATE_A: read once or twice per pass - the members the iteration kernel keeps in shared memory, elmk_lib.cu IterView)
+#define ELMK_CANFLUX_STATE_A(X)                                                                                   \
+  X(hgt_u, C1(forc_hgt_u_patch)) X(hgt_t, C1(forc_hgt_t_patch)) X(hgt_q, C1(forc_hgt_q_patch)) X(displa, C1(displa)) \
+  X(z0mv, C1(z0mv)) X(z0mg, C1(z0mg)) X(fwet, C1(fwet)) X(fdry, C1(fdry)) X(laisun, C1(laisun)) X(laisha, C1(laisha)) \
+  X(snow_depth, C1(snow_depth)) X(soilbeta, C1(soilbeta)) X(sabv, C1(sabv)) X(htop, C1(htop)) X(h2ocan0, C1(h2ocan)) \
+  X(vcsha, C1(vcmaxcintsha)) X(vcsun, C1(vcmaxcintsun)) X(t10, C1(t10))
+#define ELMK_CANFLUX_STATE_B(X)                                                                                   \
   X(pbot, C1(forc_pbot)) X(forc_q, C1(forc_qbot)) X(forc_th, C1(forc_thbot)) X(forc_lwrad, C1(forc_lwrad))        \
   X(thm, C1(thm)) X(thv, C1(thv)) X(tg, C1(t_grnd)) X(qg, C1(qg)) X(elai, C1(elai)) X(esai, C1(esai))             \
-  X(emv, C1(emv)) X(emg, C1(emg)) X(z0mg, C1(z0mg)) X(hgt_u, C1(forc_hgt_u_patch)) X(hgt_t, C1(forc_hgt_t_patch)) \
-  X(hgt_q, C1(forc_hgt_q_patch)) X(displa, C1(displa)) X(z0mv, C1(z0mv)) X(fwet, C1(fwet)) X(fdry, C1(fdry))      \
-  X(laisun, C1(laisun)) X(laisha, C1(laisha)) X(snow_depth, C1(snow_depth)) X(soilbeta, C1(soilbeta))             \
-  X(fsno, C1(frac_sno)) X(fsfc, C1(frac_h2osfc)) X(sabv, C1(sabv)) X(htop, C1(htop)) X(t10, C1(t10))              \
-  X(h2ocan0, C1(h2ocan)) X(vcsha, C1(vcmaxcintsha)) X(vcsun, C1(vcmaxcintsun)) X(parsha, C2(parsha_z, 0))         \
-  X(parsun, C2(parsun_z, 0)) X(laisha_z, C2(laisha_z, 0)) X(laisun_z, C2(laisun_z, 0))                            \
+  X(emv, C1(emv)) X(emg, C1(emg)) X(fsno, C1(frac_sno)) X(fsfc, C1(frac_h2osfc))                                  \
+  X(parsha, C2(parsha_z, 0)) X(parsun, C2(parsun_z, 0)) X(laisha_z, C2(laisha_z, 0)) X(laisun_z, C2(laisun_z, 0))  \
   X(t_soil1, C2(t_soisno, NLEVSNO)) X(t_sfc, C1(t_h2osfc))
+#define ELMK_CANFLUX_STATE(X) ELMK_CANFLUX_STATE_A(X) ELMK_CANFLUX_STATE_B(X)
 #define ELMK_CANFLUX_CONST(X)                                                                                     \
   X(forc_po2) X(forc_pco2) X(forc_rho) X(dayl_factor) X(air) X(bir) X(cir) X(ur) X(zldis) X(lw_grnd) X(t_snotop)  \
   X(dtime)
@@ -623,7 +626,8 @@ ELMK_HD bool canflux_begin(const Cols& S, const int vtype, const StepArgs& A, co
 
 // One pass of the stability iteration.  Returns true when the loop of the reference would end
 // (converged, or 41 passes done).
-ELMK_HD bool canflux_iterate(const PsnPft& P, const PsnColumn& PC, CanopyIter& I)
+template <class IT = CanopyIter>
+ELMK_HD bool canflux_iterate(const PsnPft& P, const PsnColumn& PC, IT& I)
 {
   constexpr double ria = 0.5, dlemin = 0.1, dtmin = 0.01;
   constexpr int itmax = 40, itmin = 2;
