@@ -524,10 +524,6 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
 {
   extern __shared__ double iter_smem[];
   const int nday = Q.counters[0], total = nday + Q.counters[1];
-#ifdef ELMK_ITER_TRACE
-  long long t_start = clock64(), t_exhaust = 0;
-  int rounds = 0, rounds_at_exhaust = 0;
-#endif
   const unsigned lane = threadIdx.x & 31u;
   const unsigned below = (1u << lane) - 1u;
   bool have = false;
@@ -549,9 +545,6 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
       base = __shfl_sync(0xffffffffu, base, 0);
       if (!have) {
         const int q = base + __popc(need & below);
-#ifdef ELMK_ITER_TRACE
-        if (q >= total && t_exhaust == 0) { t_exhaust = clock64(); rounds_at_exhaust = rounds; }
-#endif
         if (q < total) {
           c = (q < nday) ? Q.list[q] : Q.list[Q.np - 1 - (q - nday)];
           canflux_load<true>(S, Q, c, I);
@@ -571,9 +564,6 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
     } else {
       if (!__any_sync(0xffffffffu, have)) break;
     }
-#ifdef ELMK_ITER_TRACE
-    rounds += 1;
-#endif
     // ---- one pass for every lane that owns a column ----
     if (have) {
       if (canflux_iterate(P, PC, I)) {
@@ -582,20 +572,6 @@ __global__ void __launch_bounds__(BLOCK) k_canflux_iterate(const Cols S, const C
       }
     }
   }
-#ifdef ELMK_ITER_TRACE
-  {
-    __shared__ long long s_ex;
-    __shared__ int s_rex;
-    if (threadIdx.x == 0) { s_ex = 0x7fffffffffffffffll; s_rex = 0x7fffffff; }
-    __syncthreads();
-    if (t_exhaust) { atomicMin(&s_ex, t_exhaust - t_start); atomicMin(&s_rex, rounds_at_exhaust); }
-    __syncthreads();
-    if (threadIdx.x == 0 && blockIdx.x < 1024) {
-      long long* tr = reinterpret_cast<long long*>(Q.counters + 4) + 4 * blockIdx.x;
-      tr[0] = s_ex; tr[1] = clock64() - t_start; tr[2] = s_rex; tr[3] = rounds;
-    }
-  }
-#endif
 }
 
 __global__ void __launch_bounds__(kBlock) k_canflux_end(const Cols S, const CanfluxQueue Q)
@@ -1341,7 +1317,7 @@ int launch_canflux_repacked(Ctx* c, const StepArgs& A) {
   if (!c->cq.scratch) {
     CU(cudaMalloc(&c->cq.scratch, sizeof(double) * (size_t)kCanfluxDoubles * c->np));
     CU(cudaMalloc(&c->cq.list, sizeof(int) * (size_t)c->np));
-    CU(cudaMalloc(&c->cq.counters, sizeof(int) * 4 + sizeof(long long) * 4 * 1024));
+    CU(cudaMalloc(&c->cq.counters, sizeof(int) * 4));
     c->cq.np = c->np;
     int per_sm = 0, sms = 0;
     if (c->iterate_smem) CU(cudaFuncSetAttribute(c->iterate_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->iterate_smem));
