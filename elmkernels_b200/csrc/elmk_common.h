@@ -178,7 +178,7 @@ ELMK_HD double pow_cbase(const double base, const double lhi, const double llo, 
 // Re-alignment point for the warps of a block inside a long straight-line kernel body (device only, and only in the
 // instantiation whose launch keeps every thread of the block alive to the end): the soil-temperature body is ~270 KB
 // of SASS executed once from top to bottom, and warps that walk it together share each instruction-cache line.
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(ELMK_NO_REALIGN)
 #define ELMK_REALIGN(on) do { if (on) __syncthreads(); } while (0)
 #else
 #define ELMK_REALIGN(on) ((void)0)
