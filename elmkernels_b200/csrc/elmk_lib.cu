@@ -481,6 +481,10 @@ constexpr int iter_record_doubles(const int set)
 {
   return (kIterConstDoubles + (set >= 3 ? kIterSlotCount : set == 2 ? kIterConstSlots : 0)) | 1;
 }
+static_assert(iter_record_doubles(3) % 2 == 1 && iter_record_doubles(2) % 2 == 1 && iter_record_doubles(1) % 2 == 1,
+              "iteration records: odd stride in doubles (conflict-free 64-bit shared-memory accesses)");
+static_assert((size_t)kIterBlock * iter_record_doubles(kIterSet) * sizeof(double) <= 227u * 1024u,
+              "iteration records of one block exceed the 227 KB of shared memory a block can opt into on sm_100a");
 template <bool REF> struct IterSlot { typedef double type; };
 template <> struct IterSlot<true> { typedef double& type; };
 template <int SET>
